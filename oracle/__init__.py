@@ -1,0 +1,251 @@
+"""CPU ORACLE -- test infrastructure only (never imported by the product path).
+
+numpy-in / numpy-out ctypes wrappers over ``oracle/lumina_oracle.c`` (the plain-C
+restatement of the arithmetic behind the reference's
+``backend/utils/image_preprocessing.py`` call sites), plus ``oracle.db_post``
+(upstream PaddleOCR DBPostProcess restated with cv2 + a restated Clipper offset).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblumina_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "lumina_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_median_angle.restype = C.c_double
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _hwc(img):
+    img = _u8(img)
+    if img.ndim == 2:
+        return img, img.shape[0], img.shape[1], 1
+    return img, img.shape[0], img.shape[1], img.shape[2]
+
+
+# --- A1 ---------------------------------------------------------------------
+def target_size(width: int, height: int, max_dim: int):
+    """image_preprocessing.py:97-105 (int() truncation)."""
+    if max(width, height) <= max_dim:
+        return width, height
+    if width > height:
+        return max_dim, int(height * (max_dim / width))
+    return int(width * (max_dim / height)), max_dim
+
+
+def lanczos_coeffs(in_size: int, out_size: int):
+    k = lib().orc_lanczos_ksize(in_size, out_size)
+    b = np.zeros((out_size, 2), np.int32)
+    c = np.zeros((out_size, k), np.int32)
+    lib().orc_lanczos_coeffs(in_size, out_size, _p(b), _p(c))
+    return b, c
+
+
+def resize_lanczos(img, out_w: int, out_h: int):
+    img, h, w, c = _hwc(img)
+    out = np.empty((out_h, out_w) + ((c,) if img.ndim == 3 else ()), np.uint8)
+    lib().orc_resize_lanczos_u8(_p(img), h, w, c, _p(out), out_h, out_w)
+    return out
+
+
+# --- A2 ---------------------------------------------------------------------
+def gray_pil(rgb):
+    rgb = _u8(rgb)
+    out = np.empty(rgb.shape[:2], np.uint8)
+    lib().orc_gray_pil(_p(rgb), C.c_size_t(out.size), _p(out))
+    return out
+
+
+def gray_cv(rgb):
+    rgb = _u8(rgb)
+    out = np.empty(rgb.shape[:2], np.uint8)
+    lib().orc_gray_cv(_p(rgb), C.c_size_t(out.size), _p(out))
+    return out
+
+
+# --- A3/A4/A5 ---------------------------------------------------------------
+def contrast_mean(img):
+    img, h, w, c = _hwc(img)
+    return int(lib().orc_contrast_mean(_p(img), C.c_size_t(h * w), c))
+
+
+def contrast(img, factor: float):
+    img, h, w, c = _hwc(img)
+    out = np.empty_like(img)
+    lib().orc_contrast(_p(img), h, w, c, C.c_float(factor), _p(out))
+    return out
+
+
+def smooth3(img):
+    img, h, w, c = _hwc(img)
+    out = np.empty_like(img)
+    lib().orc_smooth3(_p(img), h, w, c, _p(out))
+    return out
+
+
+def sharpness(img, factor: float):
+    img, h, w, c = _hwc(img)
+    out = np.empty_like(img)
+    lib().orc_sharpness(_p(img), h, w, c, C.c_float(factor), _p(out))
+    return out
+
+
+def median3(img):
+    img, h, w, c = _hwc(img)
+    out = np.empty_like(img)
+    lib().orc_median3(_p(img), h, w, c, _p(out))
+    return out
+
+
+def threshold(gray, thr: int = 128):
+    gray = _u8(gray)
+    out = np.empty_like(gray)
+    lib().orc_threshold(_p(gray), C.c_size_t(gray.size), thr, _p(out))
+    return out
+
+
+def exif_transpose(img, orientation: int):
+    img, h, w, c = _hwc(img)
+    oh, ow = (w, h) if 5 <= orientation <= 8 else (h, w)
+    out = np.empty((oh, ow) + ((c,) if img.ndim == 3 else ()), np.uint8)
+    lib().orc_exif_transpose(_p(img), h, w, c, orientation, _p(out))
+    return out
+
+
+# --- A6 ---------------------------------------------------------------------
+def adaptive_gauss11(gray, cval: int = 2):
+    gray = _u8(gray)
+    out = np.empty_like(gray)
+    lib().orc_adaptive_gauss11(_p(gray), gray.shape[0], gray.shape[1], cval, _p(out))
+    return out
+
+
+# --- A7/A8/A9 ---------------------------------------------------------------
+def canny(gray, low: int = 50, high: int = 150):
+    gray = _u8(gray)
+    out = np.empty_like(gray)
+    lib().orc_canny(_p(gray), gray.shape[0], gray.shape[1], low, high, _p(out))
+    return out
+
+
+def ppht(edges, rho=1.0, theta=np.pi / 180, threshold=100, min_len=100, max_gap=10, max_lines=1 << 16):
+    edges = _u8(edges)
+    lines = np.zeros((max_lines, 4), np.int32)
+    n = lib().orc_ppht(_p(edges), edges.shape[0], edges.shape[1], C.c_double(rho), C.c_double(theta),
+                       threshold, min_len, max_gap, _p(lines), max_lines)
+    return lines[: min(n, max_lines)].copy()
+
+
+def median_angle(lines) -> float:
+    lines = np.ascontiguousarray(lines, np.int32)
+    return float(lib().orc_median_angle(_p(lines), len(lines)))
+
+
+def rotation_matrix(cx: float, cy: float, angle: float, scale: float = 1.0):
+    m = np.zeros(6, np.float64)
+    lib().orc_rotation_matrix(C.c_double(cx), C.c_double(cy), C.c_double(angle), C.c_double(scale), _p(m))
+    return m.reshape(2, 3)
+
+
+def cubic_table():
+    t = np.zeros((1024, 16), np.int16)
+    lib().orc_cubic_table(_p(t))
+    return t
+
+
+def warp_affine_cubic(img, M):
+    img, h, w, c = _hwc(img)
+    M = np.ascontiguousarray(M, np.float64).reshape(6)
+    out = np.empty_like(img)
+    lib().orc_warp_affine_cubic_u8(_p(img), h, w, c, _p(M), _p(out))
+    return out
+
+
+def deskew(img):
+    """image_preprocessing.py:372-460 composed from the restated stages.
+    Returns (image, angle, lines)."""
+    img = _u8(img)
+    gray = img if img.ndim == 2 else gray_cv(img)
+    edges = canny(gray, 50, 150)
+    lines = ppht(edges)
+    if len(lines) == 0:
+        return img, 0.0, lines
+    angle = median_angle(lines)
+    if abs(angle) < 0.5:
+        return img, angle, lines
+    if abs(angle) > 45:
+        return img, 0.0, lines
+    h, w = img.shape[:2]
+    M = rotation_matrix(w // 2, h // 2, angle)
+    return warp_affine_cubic(img, M), angle, lines
+
+
+# --- B3 / B2 ----------------------------------------------------------------
+DET_MEAN = np.array([0.485, 0.456, 0.406], np.float32)
+DET_STD = np.array([0.229, 0.224, 0.225], np.float32)
+
+
+def det_target_size(h: int, w: int, limit: int = 960):
+    rh, rw = C.c_int(), C.c_int()
+    lib().orc_det_target_size(h, w, limit, C.byref(rh), C.byref(rw))
+    return rh.value, rw.value
+
+
+def resize_linear(img, out_w: int, out_h: int):
+    img, h, w, c = _hwc(img)
+    out = np.empty((out_h, out_w) + ((c,) if img.ndim == 3 else ()), np.uint8)
+    lib().orc_resize_linear_u8(_p(img), h, w, c, _p(out), out_h, out_w)
+    return out
+
+
+def det_resize_normalize(img, limit: int = 960):
+    img = _u8(img)
+    h, w = img.shape[:2]
+    rh, rw = det_target_size(h, w, limit)
+    r = resize_linear(img, rw, rh)
+    out = np.empty((3, rh, rw), np.float32)
+    lib().orc_normalize_chw(_p(r), rh, rw, _p(DET_MEAN), _p(DET_STD), C.c_float(np.float32(1.0 / 255.0)), _p(out))
+    return out, (h, w, rh / h, rw / w)
+
+
+def ctc_greedy(probs):
+    probs = np.ascontiguousarray(probs, np.float32)
+    n, t, c = probs.shape
+    idx = np.empty((n, t), np.int32)
+    pos = np.empty((n, t), np.int32)
+    ln = np.empty(n, np.int32)
+    conf = np.empty(n, np.float32)
+    lib().orc_ctc_greedy(_p(probs), n, t, c, _p(idx), _p(pos), _p(ln), _p(conf))
+    return idx, pos, ln, conf
