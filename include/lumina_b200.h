@@ -1,0 +1,157 @@
+/*
+ * lumina_b200.h -- C-ABI of the B200-native page-image hot path.
+ *
+ * Drop-in boundary for GothiProCoder/OCR-System ("Lumina OCR").  Every entry
+ * point replaces the native routine that one reference call site reaches
+ * (reference paths are relative to backend/utils/image_preprocessing.py unless
+ * stated).  The reference is Python, so the reference-side binding is a ctypes
+ * stub; nothing here mentions torch.
+ *
+ * Conventions
+ *   - All pointers named d_* are DEVICE pointers valid on the current CUDA
+ *     device; h_* are HOST pointers.  The caller owns every buffer; kernels
+ *     never allocate.  Scratch is passed in and sized by *_workspace_bytes().
+ *   - Page batches are NHWC uint8, tightly packed: [n][h][w][c], c in {1,3}.
+ *     Planes (gray / masks / edges) are [n][h][w].
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls
+ *     only enqueue work unless documented as synchronising.
+ *   - Return value: 0 on success, negative LUMINA_E_* on failure.  Nothing
+ *     throws, nothing calls exit().  lumina_last_error_string() is
+ *     thread-local.
+ *   - Re-entrant per (device, stream); the only global state is an init-once
+ *     constant table cache (bicubic weights, Gaussian taps).
+ */
+#ifndef LUMINA_B200_H
+#define LUMINA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUMINA_OK 0
+#define LUMINA_E_INVALID (-1) /* bad argument                     */
+#define LUMINA_E_CUDA (-2)    /* CUDA runtime error (see string)  */
+#define LUMINA_E_NOMEM (-3)   /* workspace too small              */
+#define LUMINA_E_UNSUPPORTED (-4)
+
+int lumina_abi_version(void);
+const char *lumina_last_error_string(void);
+/* number of kernels this library has launched since load (bench gpu_launches) */
+uint64_t lumina_launch_count(void);
+
+/* ---- a2  auto_orient :171-173 (PIL ImageOps.exif_transpose) ------------- */
+/* orientation 1..8 (EXIF); dst is [n][w][h][c] for 5..8 else [n][h][w][c]. */
+int lumina_exif_transpose_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c,
+                             int orientation, void *stream);
+
+/* ---- a3  resize_if_needed :81-110 (PIL Image.resize LANCZOS) ------------ */
+/* Target size with the reference's int() truncation (:97-105). */
+void lumina_target_size(int width, int height, int max_dim, int *out_w, int *out_h);
+typedef struct lumina_resize_plan lumina_resize_plan; /* device coefficient tables */
+/* Synchronising (allocates + uploads the 22-bit fixed-point tables once). */
+int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_w, lumina_resize_plan **plan);
+void lumina_resize_plan_destroy(lumina_resize_plan *plan);
+size_t lumina_resize_workspace_bytes(const lumina_resize_plan *plan, int n, int c);
+/* Horizontal pass then vertical pass on a uint8 intermediate (Resample.c order). */
+int lumina_resize_lanczos_u8(const lumina_resize_plan *plan, const uint8_t *d_src, uint8_t *d_dst, int n,
+                             int c, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---- a4  convert_to_grayscale :167-169 ; deskew's cv gray :394-396 ------ */
+int lumina_rgb2gray_pil_u8(const uint8_t *d_rgb, uint8_t *d_gray, size_t npx, void *stream);
+int lumina_rgb2gray_cv_u8(const uint8_t *d_rgb, uint8_t *d_gray, size_t npx, void *stream);
+
+/* ---- a5  enhance_contrast :132-144 (ImageStat mean + Blend.c) ----------- */
+/* mean = int(sum(L)/count + 0.5) == ImageStat's sum(i*hist[i])/count, so the
+ * exact integer sum of PIL-L is reduced instead of a histogram.
+ * d_sum_scratch: [n] uint64 (zeroed by the call); d_mean: [n] int32. */
+int lumina_contrast_mean_u8(const uint8_t *d_src, int n, int h, int w, int c, uint64_t *d_sum_scratch,
+                            int32_t *d_mean, void *stream);
+int lumina_contrast_apply_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c,
+                             const int32_t *d_mean, float factor, void *stream);
+
+/* ---- a6  enhance_sharpness :146-158 (Filter.c SMOOTH 3x3 + Blend.c) ----- */
+int lumina_sharpness_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, float factor,
+                        void *stream);
+/* contrast-apply fused into the sharpness stencil (one read, one write):
+ * dst = sharpness(contrast(src, mean, contrast_factor), sharp_factor). */
+int lumina_contrast_sharpness_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c,
+                                 const int32_t *d_mean, float contrast_factor, float sharp_factor,
+                                 void *stream);
+
+/* ---- a7  denoise :160-165 (RankFilter.c median 3x3, edge replicate) ----- */
+int lumina_median3_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, void *stream);
+
+/* ---- a8  binarize :175-185 (convert L, point >thr -> mode "1") ---------- */
+/* c==3: fused PIL gray.  dst [n][h][w] in {0,255}. */
+int lumina_binarize_u8(const uint8_t *d_src, uint8_t *d_dst, size_t npx, int c, int threshold, void *stream);
+
+/* ---- a9  adaptive_binarize :462-494 (cv2.adaptiveThreshold GAUSSIAN 11,C) */
+/* c==3: fused PIL gray.  dst [n][h][w] in {0,255}. */
+int lumina_adaptive_gauss11_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, int cval,
+                               void *stream);
+
+/* ---- a10 deskew :372-460 ------------------------------------------------ */
+/* (i)+(ii) cv gray (c==3) + cv2.Canny(low, high, aperture 3, L1): edges [n][h][w] {0,255} */
+size_t lumina_canny_workspace_bytes(int n, int h, int w);
+int lumina_canny_u8(const uint8_t *d_src, uint8_t *d_edges, int n, int h, int w, int c, int low, int high,
+                    void *d_workspace, size_t workspace_bytes, void *stream);
+/* (iii) cv2.HoughLinesP (progressive probabilistic Hough, cv::RNG stream).
+ * d_lines [n][max_lines][4] int32 (x0,y0,x1,y1) in OpenCV's emission order;
+ * d_nlines [n] int32 (may exceed max_lines: truncated output). */
+size_t lumina_ppht_workspace_bytes(int n, int h, int w, double rho, double theta);
+int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double rho, double theta, int threshold,
+                int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
+                void *d_workspace, size_t workspace_bytes, void *stream);
+/* (iv)+(v) host: per-line degrees(arctan2) folded to +-45, np.median.  Host
+ * code on purpose (glibc atan2 == the reference's libm). nlines==0 -> 0.0 */
+double lumina_median_angle_host(const int32_t *h_lines, int nlines);
+/* cv2.getRotationMatrix2D (double, 2x3 row-major) */
+void lumina_rotation_matrix_host(double cx, double cy, double angle_deg, double scale, double *h_m6);
+/* (vii) cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE), same size.
+ * h_m6: [n][6] forward matrices on the HOST (copied as kernel arguments in
+ * chunks); pages with h_apply[i]==0 are copied unchanged (|angle|<0.5 etc). */
+int lumina_warp_affine_cubic_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c,
+                                const double *h_m6, const uint8_t *h_apply, void *stream);
+
+/* ---- a15 [upstream PaddleOCR] DetResizeForTest + NormalizeImage + ToCHW - */
+void lumina_det_target_size(int h, int w, int limit_side_len, int *out_h, int *out_w);
+/* src [n][h][w][3] u8 -> dst [n][3][oh][ow] f32; cv2.resize INTER_LINEAR
+ * (11-bit fixed point) then (x*scale - mean[c]) / std[c]. */
+int lumina_det_resize_normalize(const uint8_t *d_src, float *d_dst, int n, int h, int w, int oh, int ow,
+                                const float *h_mean3, const float *h_std3, float scale, void *stream);
+
+/* ---- a17 [upstream PaddleOCR] CTCLabelDecode ----------------------------- */
+/* probs [n][t][c] f32.  d_idx/d_pos [n][t] int32 kept class ids / time steps
+ * (-1 padded), d_len [n], d_conf [n] (mean of kept max-probs, 0 if none). */
+size_t lumina_ctc_workspace_bytes(int n, int t);
+int lumina_ctc_greedy(const float *d_probs, int n, int t, int c, int32_t *d_idx, int32_t *d_pos,
+                      int32_t *d_len, float *d_conf, void *d_workspace, size_t workspace_bytes,
+                      void *stream);
+
+/* ---- a16 [upstream PaddleOCR] DBPostProcess ------------------------------ */
+/* pred [n][h][w] f32 (channel 0 of the DB head).  Output per map: up to
+ * max_candidates quads d_boxes [n][max_candidates][4][2] int32 (scaled to
+ * (src_w, src_h), clipped, rounded), d_scores [n][max_candidates] f32,
+ * d_counts [n] int32; candidate order = OpenCV findContours order. */
+size_t lumina_db_workspace_bytes(int n, int h, int w, int max_candidates);
+int lumina_db_postprocess(const float *d_pred, int n, int h, int w, float thresh, float box_thresh,
+                          float unclip_ratio, int max_candidates, int min_size, const int32_t *h_src_hw,
+                          int32_t *d_boxes, float *d_scores, int32_t *d_counts, void *d_workspace,
+                          size_t workspace_bytes, void *stream);
+/* Stage outputs for parity tests: binary mask + 8-connected labels
+ * (label = min raster index of the component + 1, 0 = background). */
+int lumina_db_mask_ccl(const float *d_pred, int n, int h, int w, float thresh, uint8_t *d_mask,
+                       int32_t *d_labels, void *stream);
+
+/* ---- synthetic workloads (bench/test inputs generated in HBM) ------------ */
+/* A4-like text page, seeded by page index; identical bytes to the host
+ * generator in include/lumina_synth.h compiled for the CPU. */
+int lumina_synth_pages_u8(uint8_t *d_dst, int n, int h, int w, uint64_t seed0, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMINA_B200_H */

@@ -1,0 +1,442 @@
+// k_ppht.cu -- cv2.HoughLinesP (progressive probabilistic Hough transform),
+// identical line list in identical order.
+//
+// Replaces OpenCV hough.cpp HoughLinesProbabilistic reached from
+// backend/utils/image_preprocessing.py:402-407.  Arithmetic: SURVEY App. A8.
+//
+// The algorithm is a sequential randomised loop (cv::RNG seeded with (uint64)-1,
+// swap-remove of a raster-ordered point list, vote / arg-max / line walk per
+// point).  What is parallel is exploited without changing the result:
+//   ppht_collect_kernel : raster-order compaction of edge pixels (CTA-wide scan)
+//   ppht_order_kernel   : the visiting order depends only on N and the seed, not
+//                         on the votes, so the RNG + swap-remove permutation is
+//                         produced ahead of time, 32 draws per warp step with an
+//                         exact sequential fallback when two draws interact
+//   ppht_main_kernel    : one warp per page; the 180 theta votes of a point are
+//                         spread over the lanes (L2 atomics on packed 16-bit
+//                         counters), arg-max by one redux.sync, line walks test 32
+//                         positions per step with ballots, un-voting is fire-and-
+//                         forget RED traffic.  Pages are independent, so a batch
+//                         keeps up to one warp per page in flight.
+// This stage is latency-bound (dependent L2 round trips), not bandwidth-bound.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace lumina {
+
+struct PphtLayout {
+    size_t acc_off, mask_off, nz_off, order_off, count_off, trig_off, step_off, stats_off, total;
+    size_t acc_words_per_page;  // uint32 words (2 counters per word)
+    int numangle, numrho;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static PphtLayout ppht_layout(int n, int h, int w, double rho_d, double theta_d) {
+    PphtLayout L;
+    const float rho = (float)rho_d, theta = (float)theta_d;
+    L.numangle = (int)lrint(M_PI / theta);
+    L.numrho = (int)lrint(((w + h) * 2 + 1) / rho);
+    const size_t px = (size_t)h * w;
+    L.acc_words_per_page = ((size_t)L.numangle * L.numrho + 1) / 2;
+    size_t off = 0;
+    L.acc_off = off; off = align256(off + (size_t)n * L.acc_words_per_page * 4);
+    L.mask_off = off; off = align256(off + (size_t)n * px);
+    L.nz_off = off; off = align256(off + (size_t)n * px * 4);
+    L.order_off = off; off = align256(off + (size_t)n * px * 4);
+    L.count_off = off; off = align256(off + (size_t)n * 4);
+    L.trig_off = off; off = align256(off + (size_t)L.numangle * 2 * 4);
+    L.step_off = off; off = align256(off + (size_t)L.numangle * 3 * 4);
+    L.stats_off = off; off = align256(off + (size_t)n * 8 * 4);  // per page: N, votes, events, good, walk windows
+    L.total = off;
+    return L;
+}
+
+// ---- A: raster-order compaction ------------------------------------------------
+__global__ void __launch_bounds__(1024) ppht_collect_kernel(const uint8_t *__restrict__ edges, uint8_t *__restrict__ mask,
+                                                            uint32_t *__restrict__ nz, int *__restrict__ count, int h, int w) {
+    const int page = blockIdx.x;
+    const int px = h * w;
+    const uint8_t *e = edges + (size_t)page * px;
+    uint8_t *m = mask + (size_t)page * px;
+    uint32_t *out = nz + (size_t)page * px;
+    __shared__ int wsum[32];
+    __shared__ int chunk_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;  // uniform running count
+    for (int p0 = 0; p0 < px; p0 += 1024 * 4) {
+        const int p = p0 + threadIdx.x * 4;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (p + k < px && e[p + k]) bits |= 1u << k;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (p + k < px) m[p + k] = (uint8_t)((bits >> k) & 1u);
+        const int c = __popc(bits);
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = wsum[lane];
+            int s = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += t;
+            }
+            wsum[lane] = s - v;  // exclusive warp offsets
+            if (lane == 31) chunk_total = s;
+        }
+        __syncthreads();
+        int off = base + wsum[warp] + inc - c;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (bits & (1u << k)) {
+                const int q = p + k;
+                const int y = q / w, x = q - y * w;
+                out[off++] = ((uint32_t)y << 16) | (uint32_t)x;
+            }
+        base += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[page] = base;
+}
+
+// ---- B: visiting order (cv::RNG MWC + swap-remove), data independent ------------
+__global__ void __launch_bounds__(32) ppht_order_kernel(uint32_t *__restrict__ nz_all, uint32_t *__restrict__ order_all,
+                                                        const int *__restrict__ count, int px) {
+    const int page = blockIdx.x, lane = threadIdx.x;
+    uint32_t *nz = nz_all + (size_t)page * px;
+    uint32_t *order = order_all + (size_t)page * px;
+    unsigned long long state = ~0ull;
+    int cnt = count[page];
+    int i = 0;
+    while (cnt > 0) {
+        const int b = cnt < 32 ? cnt : 32;
+        unsigned long long s = state;
+        uint32_t my_r = 0;
+        for (int k = 0; k < b; k++) {
+            s = (unsigned long long)(uint32_t)s * 4164903690ull + (s >> 32);
+            if (k == lane) my_r = (uint32_t)s;
+        }
+        state = s;
+        const bool act = lane < b;
+        const int my_cnt = cnt - lane;
+        const int idx = act ? (int)(my_r % (uint32_t)my_cnt) : -1 - lane;
+        const unsigned same = __match_any_sync(0xffffffffu, idx);
+        const bool c1 = act && (same & ((1u << lane) - 1u)) != 0u;
+        const bool c2 = act && idx >= cnt - b;
+        if (__any_sync(0xffffffffu, c1 || c2)) {
+            // exact sequential replay of this batch
+            for (int k = 0; k < b; k++) {
+                const int ik = __shfl_sync(0xffffffffu, idx, k);
+                if (lane == 0) {
+                    const uint32_t pt = __ldcg(nz + ik);
+                    const uint32_t tl = __ldcg(nz + (cnt - k - 1));
+                    __stcg(nz + ik, tl);
+                    __stcg(order + i + k, pt);
+                }
+            }
+            __syncwarp();
+        } else {
+            uint32_t pt = 0, tl = 0;
+            if (act) { pt = __ldcg(nz + idx); tl = __ldcg(nz + (my_cnt - 1)); }
+            __syncwarp();
+            if (act) { __stcg(nz + idx, tl); __stcg(order + i + lane, pt); }
+            __syncwarp();
+        }
+        cnt -= b;
+        i += b;
+    }
+}
+
+// ---- C: main loop -----------------------------------------------------------------
+struct PphtParams {
+    uint32_t *acc;         // packed 2 x 16-bit counters
+    uint8_t *mask;
+    const uint32_t *order;
+    const int *count;
+    const float *trig;     // [numangle][2] cos, sin (pre-divided by rho)
+    const int *step;       // [numangle][3] xflag, dx0, dy0
+    int32_t *lines;        // [n][max_lines][4]
+    int32_t *nlines;       // [n]
+    int32_t *stats;        // [n][8] diagnostics: N, votes, events, good lines, walk windows
+    size_t acc_words_per_page;
+    int h, w, numangle, numrho, threshold, line_length, line_gap, max_lines;
+};
+
+__device__ __forceinline__ int cvround_f(float v) { return __float2int_rn(v); }
+
+// vote (+1) for point (x,y); returns packed key of this lane's best: (val << 16) | (65535 - n)
+template <int NPER>
+__device__ __forceinline__ uint32_t ppht_vote(uint32_t *acc, const float *tc, const float *ts, int lane, int numangle,
+                                              int numrho, int x, int y) {
+    const float fx = (float)x, fy = (float)y;
+    uint32_t old[NPER];
+    int half[NPER];
+#pragma unroll
+    for (int q = 0; q < NPER; q++) {
+        const int n = lane + 32 * q;
+        if (n < numangle) {
+            const int r = cvround_f(__fadd_rn(__fmul_rn(fx, tc[q]), __fmul_rn(fy, ts[q]))) + (numrho - 1) / 2;
+            const size_t cell = (size_t)n * numrho + r;
+            half[q] = (int)(cell & 1);
+            old[q] = atomicAdd(acc + (cell >> 1), half[q] ? 0x10000u : 1u);
+        }
+    }
+    uint32_t best = 0;
+#pragma unroll
+    for (int q = 0; q < NPER; q++) {
+        const int n = lane + 32 * q;
+        if (n < numangle) {
+            // counters are biased by PPHT_BIAS (OpenCV's int accumulator goes negative when a
+            // not-yet-visited pixel of a good line is un-voted); the biased value is monotonic
+            const uint32_t val = ((half[q] ? (old[q] >> 16) : (old[q] & 0xffffu)) + 1u) & 0xffffu;
+            const uint32_t key = (val << 16) | (uint32_t)(65535 - n);
+            best = max(best, key);
+        }
+    }
+    return best;
+}
+
+template <int NPER>
+__device__ __forceinline__ void ppht_unvote(uint32_t *acc, const float *tc, const float *ts, int lane, int numangle,
+                                            int numrho, int x, int y) {
+    const float fx = (float)x, fy = (float)y;
+#pragma unroll
+    for (int q = 0; q < NPER; q++) {
+        const int n = lane + 32 * q;
+        if (n < numangle) {
+            const int r = cvround_f(__fadd_rn(__fmul_rn(fx, tc[q]), __fmul_rn(fy, ts[q]))) + (numrho - 1) / 2;
+            const size_t cell = (size_t)n * numrho + r;
+            atomicAdd(acc + (cell >> 1), (cell & 1) ? 0xffff0000u : 0xffffffffu);  // -1 in the half (result unused -> RED)
+        }
+    }
+}
+
+constexpr int PPHT_MAXWIN = 256;   // 32-position windows per direction (covers 8192-pixel walks)
+constexpr int PPHT_BIAS = 0x4040;  // every accumulator byte is memset to 0x40
+
+template <int NPER>
+__global__ void __launch_bounds__(32) ppht_main_kernel(const PphtParams p) {
+    const int page = blockIdx.x, lane = threadIdx.x;
+    const int px = p.h * p.w;
+    uint32_t *acc = p.acc + (size_t)page * p.acc_words_per_page;
+    uint8_t *mask = p.mask + (size_t)page * px;
+    const uint32_t *order = p.order + (size_t)page * px;
+    int32_t *lines = p.lines + (size_t)page * p.max_lines * 4;
+    const int N = p.count[page];
+    __shared__ uint32_t setbits[2][PPHT_MAXWIN];
+
+    float tc[NPER], ts[NPER];
+#pragma unroll
+    for (int q = 0; q < NPER; q++) {
+        const int n = lane + 32 * q;
+        tc[q] = n < p.numangle ? p.trig[n * 2] : 0.f;
+        ts[q] = n < p.numangle ? p.trig[n * 2 + 1] : 0.f;
+    }
+    int nl = 0, n_votes = 0, n_events = 0, n_win = 0;
+    const int shift = 16;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+        const int nb = min(32, N - i0);
+        uint32_t pt = lane < nb ? __ldcg(order + i0 + lane) : 0u;
+        uint32_t mk = lane < nb ? (uint32_t)__ldcg(mask + (size_t)(pt >> 16) * p.w + (pt & 0xffffu)) : 0u;
+        for (int k = 0; k < nb; k++) {
+            const uint32_t m = __shfl_sync(0xffffffffu, mk, k);
+            if (!m) continue;
+            const uint32_t pk = __shfl_sync(0xffffffffu, pt, k);
+            const int j = (int)(pk & 0xffffu), i = (int)(pk >> 16);
+            n_votes++;
+            const uint32_t mykey = ppht_vote<NPER>(acc, tc, ts, lane, p.numangle, p.numrho, j, i);
+            const uint32_t key = __reduce_max_sync(0xffffffffu, mykey);
+            const int max_val = (int)(key >> 16) - PPHT_BIAS;
+            if (max_val < p.threshold) continue;
+            const int max_n = 65535 - (int)(key & 0xffffu);
+            // ---- line event ----
+            n_events++;
+            const int xflag = p.step[max_n * 3], dx0 = p.step[max_n * 3 + 1], dy0 = p.step[max_n * 3 + 2];
+            int x0 = j, y0 = i;
+            if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
+            else x0 = (x0 << shift) + (1 << (shift - 1));
+            int endk[2], ex[2], ey[2];
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
+                int gap = 0, ek = 0;  // position 0 is the (set) start point in walk 1
+                int base = 0, win = 0;
+                for (;; base += 32, win++) {
+                    n_win++;
+                    const int kp = base + lane;
+                    const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                    const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                    const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
+                    const bool st = inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0;
+                    const unsigned bset = __ballot_sync(0xffffffffu, st);
+                    if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset;
+                    // gap seen by this lane if it is unset: distance to the last set position
+                    const unsigned below = bset & ((2u << lane) - 1u);  // bits <= lane
+                    const int gk = below ? lane - (31 - __clz(below)) : gap + lane + 1;
+                    const bool brk = !inb || (!st && gk > p.line_gap);
+                    const unsigned bbrk = __ballot_sync(0xffffffffu, brk);
+                    if (bbrk) {
+                        const int fb = __ffs(bbrk) - 1;
+                        const unsigned sb = fb ? (bset & ((1u << fb) - 1u)) : 0u;
+                        if (sb) ek = base + 31 - __clz(sb);
+                        break;
+                    }
+                    if (bset) { ek = base + 31 - __clz(bset); gap = __clz(bset); }
+                    else gap += 32;
+                }
+                endk[d] = ek;
+                const int X = x0 + ek * dx, Y = y0 + ek * dy;
+                ex[d] = xflag ? X : (X >> shift);
+                ey[d] = xflag ? (Y >> shift) : Y;
+            }
+            const bool good = abs(ex[1] - ex[0]) >= p.line_length || abs(ey[1] - ey[0]) >= p.line_length;
+            __syncwarp();
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
+                for (int base = 0, win = 0; base <= endk[d]; base += 32, win++) {
+                    unsigned bset;
+                    if (win < PPHT_MAXWIN) bset = setbits[d][win];
+                    else {  // beyond the recorded windows (never for pages < 8192 px): re-read
+                        const int kp = base + lane;
+                        const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                        const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
+                        bset = __ballot_sync(0xffffffffu, inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0);
+                    }
+                    const int rem = endk[d] - base;  // positions base..endk
+                    if (rem < 31) bset &= (2u << rem) - 1u;
+                    if (d == 1 && base == 0) bset &= ~1u;  // start pixel already cleared by direction 0
+                    // clear the mask
+                    if (bset & (1u << lane)) {
+                        const int kp = base + lane;
+                        const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                        __stcg(mask + (size_t)i1 * p.w + j1, (uint8_t)0);
+                    }
+                    if (good) {
+                        unsigned bb = bset;
+                        while (bb) {
+                            const int b = __ffs(bb) - 1;
+                            bb &= bb - 1;
+                            const int kp = base + b;
+                            const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                            const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                            ppht_unvote<NPER>(acc, tc, ts, lane, p.numangle, p.numrho, j1, i1);
+                        }
+                    }
+                }
+            }
+            if (good) {
+                if (lane == 0 && nl < p.max_lines) {
+                    lines[nl * 4 + 0] = ex[0]; lines[nl * 4 + 1] = ey[0];
+                    lines[nl * 4 + 2] = ex[1]; lines[nl * 4 + 3] = ey[1];
+                }
+                nl++;
+            }
+            // the mask changed: refresh the not-yet-visited points of this chunk
+            __syncwarp();
+            if (lane > k && lane < nb) mk = (uint32_t)__ldcg(mask + (size_t)(pt >> 16) * p.w + (pt & 0xffffu));
+        }
+    }
+    if (lane == 0) {
+        p.nlines[page] = nl;
+        int32_t *st = p.stats + page * 8;
+        st[0] = N; st[1] = n_votes; st[2] = n_events; st[3] = nl; st[4] = n_win;
+    }
+}
+
+}  // namespace lumina
+
+using namespace lumina;
+
+LUMINA_API size_t lumina_ppht_workspace_bytes(int n, int h, int w, double rho, double theta) {
+    if (n <= 0 || h <= 0 || w <= 0 || !(rho > 0) || !(theta > 0)) return 0;
+    return ppht_layout(n, h, w, rho, theta).total;
+}
+
+LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double rho_d, double theta_d, int threshold,
+                           int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
+                           void *d_workspace, size_t workspace_bytes, void *stream) {
+    LUMINA_REQUIRE(d_edges && d_lines && d_nlines && d_workspace, "null pointer");
+    LUMINA_REQUIRE(n > 0 && h > 0 && w > 0 && max_lines > 0, "empty batch");
+    LUMINA_REQUIRE(h < 65536 && w < 65536, "page too large (16-bit packed coordinates)");
+    LUMINA_REQUIRE(rho_d > 0 && theta_d > 0, "rho/theta must be positive");
+    const PphtLayout L = ppht_layout(n, h, w, rho_d, theta_d);
+    if (workspace_bytes < L.total) return set_error(LUMINA_E_NOMEM, "ppht workspace too small: need %zu bytes", L.total);
+    LUMINA_REQUIRE((((uintptr_t)d_workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    LUMINA_REQUIRE(L.numangle >= 1 && L.numangle <= 192, "numangle must be <= 192 (theta >= pi/192)");
+    cudaStream_t st = as_stream(stream);
+    uint8_t *ws = (uint8_t *)d_workspace;
+
+    // host tables exactly as hough.cpp builds them (float theta, double cos/sin, float store)
+    const float rho = (float)rho_d, theta = (float)theta_d;
+    const float irho = 1 / rho;
+    std::vector<float> trig((size_t)L.numangle * 2);
+    std::vector<int> step((size_t)L.numangle * 3);
+    for (int a = 0; a < L.numangle; a++) {
+        trig[a * 2] = (float)(cos((double)a * theta) * irho);
+        trig[a * 2 + 1] = (float)(sin((double)a * theta) * irho);
+        const float fa = -trig[a * 2 + 1], fb = trig[a * 2];
+        int xflag, dx0, dy0;
+        if (fabsf(fa) > fabsf(fb)) {
+            xflag = 1; dx0 = fa > 0 ? 1 : -1;
+            dy0 = (int)lrintf(fb * (1 << 16) / fabsf(fa));
+        } else {
+            xflag = 0; dy0 = fb > 0 ? 1 : -1;
+            dx0 = (int)lrintf(fa * (1 << 16) / fabsf(fb));
+        }
+        step[a * 3] = xflag; step[a * 3 + 1] = dx0; step[a * 3 + 2] = dy0;
+    }
+    LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.trig_off, trig.data(), trig.size() * 4, cudaMemcpyHostToDevice, st));
+    LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.step_off, step.data(), step.size() * 4, cudaMemcpyHostToDevice, st));
+    // pageable-source async copies are staged before returning, so the vectors may die here
+    LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.acc_off, 0x40, (size_t)n * L.acc_words_per_page * 4, st));
+
+    ppht_collect_kernel<<<n, 1024, 0, st>>>(d_edges, ws + L.mask_off, (uint32_t *)(ws + L.nz_off), (int *)(ws + L.count_off), h, w);
+    LUMINA_KERNEL_CHECK("ppht_collect_kernel");
+    ppht_order_kernel<<<n, 32, 0, st>>>((uint32_t *)(ws + L.nz_off), (uint32_t *)(ws + L.order_off), (const int *)(ws + L.count_off), h * w);
+    LUMINA_KERNEL_CHECK("ppht_order_kernel");
+    PphtParams p;
+    p.acc = (uint32_t *)(ws + L.acc_off); p.mask = ws + L.mask_off;
+    p.order = (const uint32_t *)(ws + L.order_off); p.count = (const int *)(ws + L.count_off);
+    p.trig = (const float *)(ws + L.trig_off); p.step = (const int *)(ws + L.step_off);
+    p.lines = d_lines; p.nlines = d_nlines; p.stats = (int32_t *)(ws + L.stats_off); p.acc_words_per_page = L.acc_words_per_page;
+    p.h = h; p.w = w; p.numangle = L.numangle; p.numrho = L.numrho;
+    p.threshold = threshold; p.line_length = min_line_length; p.line_gap = max_line_gap; p.max_lines = max_lines;
+    ppht_main_kernel<6><<<n, 32, 0, st>>>(p);
+    LUMINA_KERNEL_CHECK("ppht_main_kernel");
+    return LUMINA_OK;
+}
+
+// (iv)+(v) image_preprocessing.py:414-428 -- host on purpose (libm atan2, as numpy)
+static int cmp_double(const void *a, const void *b) {
+    const double x = *(const double *)a, y = *(const double *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+LUMINA_API double lumina_median_angle_host(const int32_t *h_lines, int nlines) {
+    if (!h_lines || nlines <= 0) return 0.0;
+    std::vector<double> ang((size_t)nlines);
+    for (int i = 0; i < nlines; i++) {
+        const double dy = (double)(h_lines[i * 4 + 3] - h_lines[i * 4 + 1]);
+        const double dx = (double)(h_lines[i * 4 + 2] - h_lines[i * 4 + 0]);
+        double a = atan2(dy, dx) * (180.0 / M_PI);
+        if (a < -45) a += 90;
+        else if (a > 45) a -= 90;
+        ang[i] = a;
+    }
+    qsort(ang.data(), ang.size(), sizeof(double), cmp_double);
+    return (nlines & 1) ? ang[nlines / 2] : (ang[nlines / 2 - 1] + ang[nlines / 2]) / 2.0;
+}

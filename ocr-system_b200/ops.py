@@ -1,0 +1,332 @@
+"""Batched page-tensor operators over the C-ABI (``include/lumina_b200.h``).
+
+Every function takes CUDA ``torch.uint8`` page batches ``[N, H, W, C]`` (C in
+{1, 3}; planes are ``[N, H, W]``), allocates outputs / scratch as torch tensors
+(torch is only the allocator + stream provider) and enqueues the hand-written
+sm_100a kernels on the current torch stream.  No CPU fallback exists: a
+non-CUDA tensor is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi
+
+_L = _abi.lib
+_chk = _abi.check
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _pages(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int]:
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise TypeError("lumina_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if x.dtype != torch.uint8:
+        raise TypeError(f"expected uint8 pages, got {x.dtype}")
+    if x.dim() == 3:
+        x = x.unsqueeze(-1)
+    if x.dim() != 4 or x.shape[-1] not in (1, 3):
+        raise ValueError(f"expected [N,H,W,C] with C in (1,3) or [N,H,W]; got {tuple(x.shape)}")
+    x = x.contiguous()
+    n, h, w, c = x.shape
+    return x, n, h, w, c
+
+
+def _like(x: torch.Tensor, squeeze: bool) -> torch.Tensor:
+    return x.squeeze(-1) if squeeze else x
+
+
+def launch_count() -> int:
+    return int(_L().lumina_launch_count())
+
+
+# --------------------------------------------------------------------------- a2
+def exif_transpose(pages: torch.Tensor, orientation: int) -> torch.Tensor:
+    """PIL ImageOps.exif_transpose (image_preprocessing.py:173) for a fixed EXIF orientation."""
+    sq = pages.dim() == 3
+    x, n, h, w, c = _pages(pages)
+    oh, ow = (w, h) if 5 <= orientation <= 8 else (h, w)
+    out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+    _chk(_L().lumina_exif_transpose_u8(_ptr(x), _ptr(out), n, h, w, c, int(orientation), _stream()))
+    return _like(out, sq)
+
+
+# --------------------------------------------------------------------------- a3
+def target_size(width: int, height: int, max_dim: int) -> Tuple[int, int]:
+    ow, oh = C.c_int(), C.c_int()
+    _L().lumina_target_size(width, height, max_dim, C.byref(ow), C.byref(oh))
+    return ow.value, oh.value
+
+
+class _ResizePlans:
+    """Device coefficient tables per (device, in, out) geometry; created once."""
+
+    def __init__(self):
+        self._plans = {}
+        self._lock = threading.Lock()
+
+    def get(self, dev: int, in_h: int, in_w: int, out_h: int, out_w: int) -> C.c_void_p:
+        key = (dev, in_h, in_w, out_h, out_w)
+        with self._lock:
+            p = self._plans.get(key)
+            if p is None:
+                h = C.c_void_p()
+                with torch.cuda.device(dev):
+                    _chk(_L().lumina_resize_plan_create(in_h, in_w, out_h, out_w, C.byref(h)))
+                p = self._plans[key] = h
+            return p
+
+
+_plans = _ResizePlans()
+
+
+def resize_lanczos(pages: torch.Tensor, out_w: int, out_h: int) -> torch.Tensor:
+    """PIL Image.resize((out_w,out_h), LANCZOS) (image_preprocessing.py:110), byte-exact."""
+    sq = pages.dim() == 3
+    x, n, h, w, c = _pages(pages)
+    plan = _plans.get(x.device.index, h, w, out_h, out_w)
+    out = torch.empty((n, out_h, out_w, c), dtype=torch.uint8, device=x.device)
+    wsb = int(_L().lumina_resize_workspace_bytes(plan, n, c))
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=x.device) if wsb else None
+    _chk(_L().lumina_resize_lanczos_u8(plan, _ptr(x), _ptr(out), n, c, _ptr(ws), wsb, _stream()))
+    return _like(out, sq)
+
+
+def resize_if_needed(pages: torch.Tensor, max_dim: int) -> torch.Tensor:
+    h, w = pages.shape[1], pages.shape[2]
+    if max(w, h) <= max_dim:
+        return pages
+    ow, oh = target_size(w, h, max_dim)
+    return resize_lanczos(pages, ow, oh)
+
+
+# --------------------------------------------------------------------------- a4
+def gray_pil(pages: torch.Tensor) -> torch.Tensor:
+    x, n, h, w, c = _pages(pages)
+    if c == 1:
+        return x.squeeze(-1)
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    _chk(_L().lumina_rgb2gray_pil_u8(_ptr(x), _ptr(out), n * h * w, _stream()))
+    return out
+
+
+def gray_cv(pages: torch.Tensor) -> torch.Tensor:
+    x, n, h, w, c = _pages(pages)
+    if c == 1:
+        return x.squeeze(-1)
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    _chk(_L().lumina_rgb2gray_cv_u8(_ptr(x), _ptr(out), n * h * w, _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- a5 / a6
+def contrast_mean(pages: torch.Tensor) -> torch.Tensor:
+    x, n, h, w, c = _pages(pages)
+    scratch = torch.empty(n, dtype=torch.int64, device=x.device)
+    mean = torch.empty(n, dtype=torch.int32, device=x.device)
+    _chk(_L().lumina_contrast_mean_u8(_ptr(x), n, h, w, c, _ptr(scratch), _ptr(mean), _stream()))
+    return mean
+
+
+def enhance_contrast(pages: torch.Tensor, factor: float, mean: Optional[torch.Tensor] = None) -> torch.Tensor:
+    sq = pages.dim() == 3
+    x, n, h, w, c = _pages(pages)
+    if mean is None:
+        mean = contrast_mean(x)
+    out = torch.empty_like(x)
+    _chk(_L().lumina_contrast_apply_u8(_ptr(x), _ptr(out), n, h, w, c, _ptr(mean), float(factor), _stream()))
+    return _like(out, sq)
+
+
+def enhance_sharpness(pages: torch.Tensor, factor: float) -> torch.Tensor:
+    sq = pages.dim() == 3
+    x, n, h, w, c = _pages(pages)
+    out = torch.empty_like(x)
+    _chk(_L().lumina_sharpness_u8(_ptr(x), _ptr(out), n, h, w, c, float(factor), _stream()))
+    return _like(out, sq)
+
+
+def contrast_sharpness(pages: torch.Tensor, contrast: float, sharpness: float) -> torch.Tensor:
+    """enhance_sharpness(enhance_contrast(x, contrast), sharpness) with the contrast LUT fused
+    into the stencil (image_preprocessing.py:613-618)."""
+    sq = pages.dim() == 3
+    x, n, h, w, c = _pages(pages)
+    mean = contrast_mean(x)
+    out = torch.empty_like(x)
+    _chk(_L().lumina_contrast_sharpness_u8(_ptr(x), _ptr(out), n, h, w, c, _ptr(mean), float(contrast),
+                                           float(sharpness), _stream()))
+    return _like(out, sq)
+
+
+# --------------------------------------------------------------------------- a7 / a8 / a9
+def median3(pages: torch.Tensor) -> torch.Tensor:
+    sq = pages.dim() == 3
+    x, n, h, w, c = _pages(pages)
+    out = torch.empty_like(x)
+    _chk(_L().lumina_median3_u8(_ptr(x), _ptr(out), n, h, w, c, _stream()))
+    return _like(out, sq)
+
+
+def binarize(pages: torch.Tensor, threshold: int = 128) -> torch.Tensor:
+    x, n, h, w, c = _pages(pages)
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    _chk(_L().lumina_binarize_u8(_ptr(x), _ptr(out), n * h * w, c, int(threshold), _stream()))
+    return out
+
+
+def adaptive_binarize(pages: torch.Tensor, cval: int = 2) -> torch.Tensor:
+    x, n, h, w, c = _pages(pages)
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    _chk(_L().lumina_adaptive_gauss11_u8(_ptr(x), _ptr(out), n, h, w, c, int(cval), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- a10
+def _ws(nbytes: int, device) -> torch.Tensor:
+    # torch's caching allocator returns >=512-byte aligned blocks
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def canny(pages: torch.Tensor, low: int = 50, high: int = 150) -> torch.Tensor:
+    """cv gray (for RGB) + cv2.Canny(low, high, apertureSize=3) -> edges [N,H,W] {0,255}."""
+    x, n, h, w, c = _pages(pages)
+    edges = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    wsb = int(_L().lumina_canny_workspace_bytes(n, h, w))
+    ws = _ws(wsb, x.device)
+    _chk(_L().lumina_canny_u8(_ptr(x), _ptr(edges), n, h, w, c, int(low), int(high), _ptr(ws), wsb, _stream()))
+    return edges
+
+
+def hough_lines_p(edges: torch.Tensor, rho: float = 1.0, theta: float = float(np.pi / 180), threshold: int = 100,
+                  min_line_length: int = 100, max_line_gap: int = 10, max_lines: int = 4096):
+    """cv2.HoughLinesP on a batch of edge planes -> (lines [N,max_lines,4] int32, nlines [N] int32), device."""
+    x, n, h, w, c = _pages(edges)
+    if c != 1:
+        raise ValueError("edges must be [N,H,W]")
+    lines = torch.empty((n, max_lines, 4), dtype=torch.int32, device=x.device)
+    nlines = torch.empty(n, dtype=torch.int32, device=x.device)
+    wsb = int(_L().lumina_ppht_workspace_bytes(n, h, w, float(rho), float(theta)))
+    ws = _ws(wsb, x.device)
+    _chk(_L().lumina_ppht(_ptr(x), n, h, w, float(rho), float(theta), int(threshold), int(min_line_length),
+                          int(max_line_gap), _ptr(lines), _ptr(nlines), int(max_lines), _ptr(ws), wsb, _stream()))
+    return lines, nlines
+
+
+def median_angle(lines_host: np.ndarray) -> float:
+    """image_preprocessing.py:414-428 on the host (libm atan2, like numpy)."""
+    a = np.ascontiguousarray(lines_host, dtype=np.int32)
+    return float(_L().lumina_median_angle_host(a.ctypes.data_as(C.c_void_p), int(a.shape[0])))
+
+
+def rotation_matrix(cx: float, cy: float, angle: float, scale: float = 1.0) -> np.ndarray:
+    m = np.zeros(6, np.float64)
+    _L().lumina_rotation_matrix_host(float(cx), float(cy), float(angle), float(scale), m.ctypes.data_as(C.c_void_p))
+    return m.reshape(2, 3)
+
+
+def warp_affine_cubic(pages: torch.Tensor, mats: np.ndarray, apply: Optional[np.ndarray] = None) -> torch.Tensor:
+    """cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE) with per-page forward 2x3 matrices (host)."""
+    sq = pages.dim() == 3
+    x, n, h, w, c = _pages(pages)
+    m = np.ascontiguousarray(mats, dtype=np.float64).reshape(n, 6)
+    ap = np.ones(n, np.uint8) if apply is None else np.ascontiguousarray(apply, dtype=np.uint8)
+    out = torch.empty_like(x)
+    _chk(_L().lumina_warp_affine_cubic_u8(_ptr(x), _ptr(out), n, h, w, c, m.ctypes.data_as(C.c_void_p),
+                                          ap.ctypes.data_as(C.c_void_p), _stream()))
+    return _like(out, sq)
+
+
+def deskew(pages: torch.Tensor, max_lines: int = 4096):
+    """image_preprocessing.py:372-460 for a batch: returns (pages, angles[N] float64 numpy).
+
+    One host synchronisation (the line lists come back for the median / gating),
+    exactly where the reference computes ``np.median(angles)``."""
+    x, n, h, w, c = _pages(pages)
+    edges = canny(x, 50, 150)
+    lines, nlines = hough_lines_p(edges, max_lines=max_lines)
+    nl = nlines.cpu().numpy()
+    if int(nl.max(initial=0)) > max_lines:
+        return deskew(pages, max_lines=int(nl.max()))
+    keep = int(nl.max(initial=0))
+    lh = lines[:, :max(keep, 1)].cpu().numpy()
+    angles = np.zeros(n, np.float64)
+    mats = np.zeros((n, 6), np.float64)
+    apply = np.zeros(n, np.uint8)
+    for i in range(n):
+        if nl[i] == 0:
+            continue  # "No lines detected" -> image, 0.0
+        a = median_angle(lh[i, : nl[i]])
+        if abs(a) < 0.5:
+            angles[i] = a
+            continue
+        if abs(a) > 45:
+            continue  # angle too large -> image, 0.0
+        angles[i] = a
+        mats[i] = rotation_matrix(w // 2, h // 2, a).reshape(6)
+        apply[i] = 1
+    if not apply.any():
+        return pages, angles
+    out = warp_affine_cubic(x, mats, apply)
+    return (out.squeeze(-1) if pages.dim() == 3 else out), angles
+
+
+# --------------------------------------------------------------------------- a15 / a17
+DET_MEAN = (0.485, 0.456, 0.406)
+DET_STD = (0.229, 0.224, 0.225)
+
+
+def det_target_size(h: int, w: int, limit_side_len: int = 960) -> Tuple[int, int]:
+    oh, ow = C.c_int(), C.c_int()
+    _L().lumina_det_target_size(h, w, limit_side_len, C.byref(oh), C.byref(ow))
+    return oh.value, ow.value
+
+
+def det_resize_normalize(pages: torch.Tensor, limit_side_len: int = 960, mean=DET_MEAN, std=DET_STD,
+                         scale: float = 1.0 / 255.0):
+    """PaddleOCR DetResizeForTest('max') + NormalizeImage + ToCHWImage -> ([N,3,oh,ow] f32, shape_list)."""
+    x, n, h, w, c = _pages(pages)
+    if c != 3:
+        raise ValueError("det preprocess expects RGB/BGR pages")
+    oh, ow = det_target_size(h, w, limit_side_len)
+    out = torch.empty((n, 3, oh, ow), dtype=torch.float32, device=x.device)
+    m = np.asarray(mean, np.float32)
+    s = np.asarray(std, np.float32)
+    _chk(_L().lumina_det_resize_normalize(_ptr(x), _ptr(out), n, h, w, oh, ow, m.ctypes.data_as(C.c_void_p),
+                                          s.ctypes.data_as(C.c_void_p), float(np.float32(scale)), _stream()))
+    shape_list = np.tile(np.array([h, w, oh / h, ow / w], np.float64), (n, 1))
+    return out, shape_list
+
+
+def ctc_greedy(probs: torch.Tensor):
+    """CTC greedy decode of [N,T,C] float32 posteriors -> (idx, pos, length, conf) device tensors."""
+    if not probs.is_cuda or probs.dtype != torch.float32 or probs.dim() != 3:
+        raise TypeError("ctc_greedy expects a CUDA float32 [N,T,C] tensor")
+    p = probs.contiguous()
+    n, t, c = p.shape
+    idx = torch.empty((n, t), dtype=torch.int32, device=p.device)
+    pos = torch.empty((n, t), dtype=torch.int32, device=p.device)
+    ln = torch.empty(n, dtype=torch.int32, device=p.device)
+    conf = torch.empty(n, dtype=torch.float32, device=p.device)
+    wsb = int(_L().lumina_ctc_workspace_bytes(n, t))
+    ws = _ws(wsb, p.device)
+    _chk(_L().lumina_ctc_greedy(_ptr(p), n, t, c, _ptr(idx), _ptr(pos), _ptr(ln), _ptr(conf), _ptr(ws), wsb, _stream()))
+    return idx, pos, ln, conf
+
+
+def synth_pages(n: int, h: int = 3508, w: int = 2480, seed0: int = 0, device="cuda") -> torch.Tensor:
+    """Synthetic A4 text pages generated in HBM (identical bytes to oracle.synth_page)."""
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
+    with torch.cuda.device(out.device):
+        _chk(_L().lumina_synth_pages_u8(_ptr(out), n, h, w, C.c_uint64(seed0), _stream()))
+    return out

@@ -249,3 +249,15 @@ def ctc_greedy(probs):
     conf = np.empty(n, np.float32)
     lib().orc_ctc_greedy(_p(probs), n, t, c, _p(idx), _p(pos), _p(ln), _p(conf))
     return idx, pos, ln, conf
+
+
+# --- synthetic workload (host build of include/lumina_synth.h) ---------------
+def synth_page(h: int, w: int, seed: int):
+    out = np.empty((h, w, 3), np.uint8)
+    lib().orc_synth_page(_p(out), h, w, C.c_uint64(seed))
+    return out
+
+
+def synth_skew_deg(h: int, w: int, seed: int) -> float:
+    lib().orc_synth_skew_deg.restype = C.c_double
+    return float(lib().orc_synth_skew_deg(h, w, C.c_uint64(seed)))

@@ -686,6 +686,28 @@ ORC_API void orc_normalize_chw(const uint8_t *img, int h, int w, const float *me
  *     collapse repeats, drop blank 0, conf = float32 mean of kept max probs.
  *     idx_out: N x T int32 kept class ids (-1 padded); len_out: N; conf_out: N
  * ------------------------------------------------------------------------- */
+/* numpy float32 add.reduce: n<8 sequential; <=128: 8 accumulators, then
+ * ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), remainder sequential; else recurse. */
+static float orc_np_pairwise_sum(const float *a, int n) {
+    if (n < 8) {
+        float r = 0.0f;
+        for (int i = 0; i < n; i++) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int q = 0; q < 8; q++) r[q] = a[q];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int q = 0; q < 8; q++) r[q] += a[i + q];
+        float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return orc_np_pairwise_sum(a, n2) + orc_np_pairwise_sum(a + n2, n - n2);
+}
 ORC_API void orc_ctc_greedy(const float *probs, int n, int t, int c, int32_t *idx_out, int32_t *pos_out,
                             int32_t *len_out, float *conf_out) {
     for (int b = 0; b < n; b++) {
@@ -712,24 +734,29 @@ ORC_API void orc_ctc_greedy(const float *probs, int n, int t, int c, int32_t *id
         }
         for (int s = len; s < t; s++) { idx_out[(size_t)b * t + s] = -1; pos_out[(size_t)b * t + s] = -1; }
         len_out[b] = len;
-        /* np.mean over float32: pairwise summation for n>=8 blocks; T<=128 kept
-         * values -> numpy uses an unrolled 8-accumulator pairwise sum. */
+        /* np.mean(float32) = pairwise add.reduce / n */
         if (len == 0) conf_out[b] = 0.0f;
         else {
-            float sum;
-            if (len < 8) {
-                sum = 0.0f; /* numpy: res = 0.; for i: res += a[i]  (starts from -0.0 actually; same value) */
-                for (int i = 0; i < len; i++) sum += kept[i];
-            } else {
-                float r[8];
-                for (int i = 0; i < 8; i++) r[i] = kept[i];
-                int i;
-                for (i = 8; i < len - (len % 8); i += 8)
-                    for (int q = 0; q < 8; q++) r[q] += kept[i + q];
-                sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-                for (; i < len; i++) sum += kept[i];
-            }
+            float sum = orc_np_pairwise_sum(kept, len);
             conf_out[b] = sum / (float)len;
         }
     }
+}
+
+/* ------------------------------------------------------------------------- *
+ * Synthetic page generator (host build of include/lumina_synth.h; the CUDA
+ * build of the same header must produce identical bytes).
+ * ------------------------------------------------------------------------- */
+#include "../include/lumina_synth.h"
+ORC_API void orc_synth_page(uint8_t *dst, int h, int w, uint64_t seed) {
+    lsyn_page_t p;
+    lsyn_page_init(&p, h, w, seed);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int ch = 0; ch < 3; ch++) dst[((size_t)y * w + x) * 3 + ch] = lsyn_pixel(&p, x, y, ch);
+}
+ORC_API double orc_synth_skew_deg(int h, int w, uint64_t seed) {
+    lsyn_page_t p;
+    lsyn_page_init(&p, h, w, seed);
+    return atan2((double)p.sinq, (double)p.cosq) * 180.0 / M_PI;
 }

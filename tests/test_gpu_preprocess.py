@@ -1,0 +1,198 @@
+"""GPU parity: every preprocessing kernel (through the C-ABI) vs the CPU oracle.
+
+Bit-exact for all integer / byte work; the adaptive threshold is compared
+bit-exactly too (the oracle restates OpenCV's plain, non-SIMD summation order).
+Reference call sites: backend/utils/image_preprocessing.py (line numbers in the
+kernels' headers)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _page(O, h, w, seed):
+    return O.synth_page(h, w, seed)
+
+
+def _rand(h, w, c, seed):
+    rng = np.random.default_rng(seed)
+    shape = (h, w, c) if c > 1 else (h, w)
+    return rng.integers(0, 256, size=shape, dtype=np.uint8)
+
+
+def test_synth_device_equals_host(oracle, cuda):
+    from ocr_system_b200 import ops
+
+    dev = ops.synth_pages(3, 877, 620, seed0=5, device=cuda).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(dev[i], oracle.synth_page(877, 620, 5 + i))
+
+
+@pytest.mark.parametrize("h,w,md", [(3508, 2480, 960), (3508, 2480, 2000), (2480, 3508, 960), (1200, 850, 600),
+                                    (501, 333, 200), (2000, 1413, 1999), (700, 5000, 960)])
+def test_resize_lanczos_rgb(oracle, cuda, h, w, md):
+    from ocr_system_b200 import ops
+
+    img = _page(oracle, h, w, 1) if h * w > 10**6 else _rand(h, w, 3, 7)
+    tw, th = oracle.target_size(w, h, md)
+    assert ops.target_size(w, h, md) == (tw, th)
+    got = ops.resize_lanczos(_t(img[None], cuda), tw, th).cpu().numpy()[0]
+    assert np.array_equal(got, oracle.resize_lanczos(img, tw, th))
+
+
+def test_resize_lanczos_gray_batch_and_one_axis(oracle, cuda):
+    from ocr_system_b200 import ops
+
+    imgs = np.stack([_rand(640, 480, 1, s) for s in range(3)])
+    got = ops.resize_lanczos(_t(imgs, cuda), 201, 268).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], oracle.resize_lanczos(imgs[i], 201, 268))
+    rgb = _rand(300, 400, 3, 3)
+    for (ow, oh) in ((400, 123), (177, 300), (40, 30)):  # one-axis and 10x reductions (generic path)
+        got = ops.resize_lanczos(_t(rgb[None], cuda), ow, oh).cpu().numpy()[0]
+        assert np.array_equal(got, oracle.resize_lanczos(rgb, ow, oh)), (ow, oh)
+
+
+@pytest.mark.parametrize("h,w", [(960, 678), (101, 77), (33, 1000)])
+def test_gray_and_binarize(oracle, cuda, h, w):
+    from ocr_system_b200 import ops
+
+    img = np.stack([_rand(h, w, 3, s) for s in range(2)])
+    x = _t(img, cuda)
+    gp, gc, bz = ops.gray_pil(x).cpu().numpy(), ops.gray_cv(x).cpu().numpy(), ops.binarize(x, 128).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(gp[i], oracle.gray_pil(img[i]))
+        assert np.array_equal(gc[i], oracle.gray_cv(img[i]))
+        assert np.array_equal(bz[i], oracle.threshold(oracle.gray_pil(img[i]), 128))
+    g = _t(oracle.gray_pil(img[0])[None], cuda)
+    assert np.array_equal(ops.binarize(g, 100).cpu().numpy()[0], oracle.threshold(oracle.gray_pil(img[0]), 100))
+
+
+@pytest.mark.parametrize("h,w,c", [(960, 678, 3), (101, 77, 3), (101, 77, 1), (64, 3, 3), (3, 50, 1), (2000, 1413, 3)])
+def test_contrast_sharpness_median(oracle, cuda, h, w, c):
+    from ocr_system_b200 import ops
+
+    n = 2 if h < 1000 else 1
+    img = np.stack([(_page(oracle, h, w, s) if (c == 3 and h >= 900) else _rand(h, w, c, s)) for s in range(n)])
+    x = _t(img, cuda)
+    mean = ops.contrast_mean(x).cpu().numpy()
+    for f in (1.2, 1.3, 0.6):
+        got = ops.enhance_contrast(x, f).cpu().numpy()
+        for i in range(n):
+            assert mean[i] == oracle.contrast_mean(img[i])
+            assert np.array_equal(got[i], oracle.contrast(img[i], f)), ("contrast", f)
+    for f in (1.1, 1.2, 0.4, 2.5):
+        got = ops.enhance_sharpness(x, f).cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got[i], oracle.sharpness(img[i], f)), ("sharp", f)
+    got = ops.contrast_sharpness(x, 1.2, 1.1).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], oracle.sharpness(oracle.contrast(img[i], 1.2), 1.1))
+    got = ops.median3(x).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], oracle.median3(img[i]))
+
+
+@pytest.mark.parametrize("h,w,c", [(960, 678, 3), (101, 77, 1), (130, 67, 3), (11, 9, 1)])
+def test_adaptive_binarize(oracle, cuda, h, w, c):
+    from ocr_system_b200 import ops
+
+    img = np.stack([(_page(oracle, h, w, s) if h >= 900 else _rand(h, w, c, s)) for s in range(2)])
+    got = ops.adaptive_binarize(_t(img, cuda), 2).cpu().numpy()
+    for i in range(2):
+        g = oracle.gray_pil(img[i]) if c == 3 else img[i]
+        assert np.array_equal(got[i], oracle.adaptive_gauss11(g, 2))
+
+
+@pytest.mark.parametrize("orientation", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_exif_transpose(oracle, cuda, orientation):
+    from ocr_system_b200 import ops
+
+    img = _rand(37, 53, 3, orientation)
+    got = ops.exif_transpose(_t(img[None], cuda), orientation).cpu().numpy()[0]
+    assert np.array_equal(got, oracle.exif_transpose(img, orientation))
+
+
+def _resized_page(O, seed, md):
+    pg = O.synth_page(3508, 2480, seed)
+    tw, th = O.target_size(2480, 3508, md)
+    return O.resize_lanczos(pg, tw, th)
+
+
+@pytest.mark.parametrize("md", [960, 2000])
+def test_canny_ppht_deskew(oracle, cuda, md):
+    from ocr_system_b200 import ops
+
+    seeds = [0, 1, 2] if md == 960 else [0]
+    imgs = np.stack([_resized_page(oracle, s, md) for s in seeds])
+    x = _t(imgs, cuda)
+    edges = ops.canny(x, 50, 150)
+    e = edges.cpu().numpy()
+    ref_edges = [oracle.canny(oracle.gray_cv(im), 50, 150) for im in imgs]
+    for i in range(len(seeds)):
+        assert np.array_equal(e[i], ref_edges[i]), "canny edge map"
+    lines, nlines = ops.hough_lines_p(edges)
+    lines, nlines = lines.cpu().numpy(), nlines.cpu().numpy()
+    for i in range(len(seeds)):
+        ref = oracle.ppht(ref_edges[i])
+        assert nlines[i] == len(ref)
+        assert np.array_equal(lines[i, : nlines[i]], ref), "HoughLinesP line list / order"
+    out, angles = ops.deskew(x)
+    out = out.cpu().numpy()
+    for i in range(len(seeds)):
+        ref_img, ref_angle, _ = oracle.deskew(imgs[i])
+        assert angles[i] == ref_angle
+        assert np.array_equal(out[i], ref_img)
+
+
+@pytest.mark.parametrize("h,w,c", [(960, 678, 3), (211, 97, 1), (50, 300, 3)])
+def test_warp_affine_teacher_forced(oracle, cuda, h, w, c):
+    from ocr_system_b200 import ops
+
+    img = _page(oracle, h, w, 3) if c == 3 and h > 900 else _rand(h, w, c, 4)
+    angs = [0.5, -0.7, 2.9, -13.0, 44.9]
+    mats = np.stack([oracle.rotation_matrix(w // 2, h // 2, a).reshape(6) for a in angs])
+    for a, m in zip(angs, mats):
+        assert np.array_equal(ops.rotation_matrix(w // 2, h // 2, a).reshape(6), m)
+    x = _t(np.stack([img] * len(angs)), cuda)
+    apply = np.array([1, 1, 0, 1, 1], np.uint8)
+    got = ops.warp_affine_cubic(x, mats, apply).cpu().numpy()
+    for i, a in enumerate(angs):
+        ref = oracle.warp_affine_cubic(img, mats[i]) if apply[i] else img
+        assert np.array_equal(got[i], ref), a
+
+
+@pytest.mark.parametrize("h,w", [(960, 678), (3508, 2480), (300, 500), (20, 31)])
+def test_det_resize_normalize(oracle, cuda, h, w):
+    from ocr_system_b200 import ops
+
+    img = _rand(h, w, 3, 9)
+    got, shape_list = ops.det_resize_normalize(_t(img[None], cuda), 960)
+    ref, sl = oracle.det_resize_normalize(img, 960)
+    assert got.shape[1:] == ref.shape
+    assert tuple(shape_list[0]) == tuple(sl)
+    # float stage tolerance from north_star: <= 1e-4 abs (observed: exact)
+    assert np.max(np.abs(got.cpu().numpy()[0] - ref)) <= 1e-4
+
+
+@pytest.mark.parametrize("n,t,c", [(8, 40, 6625), (3, 7, 13), (2, 200, 97), (5, 1, 2)])
+def test_ctc_greedy(oracle, cuda, n, t, c):
+    from ocr_system_b200 import ops
+
+    rng = np.random.default_rng(n * 1000 + t)
+    p = rng.random((n, t, c)).astype(np.float32)
+    p[:, :, 0] += (rng.random((n, t)) < 0.3) * 2.0          # blanks
+    if t > 2:
+        p[:, 1::3] = p[:, 0:-1:3][:, : p[:, 1::3].shape[1]]   # repeats
+    if c > 8:
+        p[0, 0, 5] = p[0, 0, 3] = 9.0                         # exact tie -> first index
+    idx, pos, ln, conf = [a.cpu().numpy() for a in ops.ctc_greedy(_t(p, cuda))]
+    ridx, rpos, rln, rconf = oracle.ctc_greedy(p)
+    assert np.array_equal(ln, rln) and np.array_equal(idx, ridx) and np.array_equal(pos, rpos)
+    assert np.max(np.abs(conf - rconf)) <= 1e-4
