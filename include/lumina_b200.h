@@ -134,17 +134,20 @@ int lumina_ctc_greedy(const float *d_probs, int n, int t, int c, int32_t *d_idx,
 /* ---- a16 [upstream PaddleOCR] DBPostProcess ------------------------------ */
 /* pred [n][h][w] f32 (channel 0 of the DB head).  Output per map: up to
  * max_candidates quads d_boxes [n][max_candidates][4][2] int32 (scaled to
- * (src_w, src_h), clipped, rounded), d_scores [n][max_candidates] f32,
- * d_counts [n] int32; candidate order = OpenCV findContours order. */
+ * (src_w, src_h) = h_src_hw[i][1], h_src_hw[i][0], clipped, rounded), d_scores
+ * [n][max_candidates] f32, d_counts [n] int32; box order = OpenCV findContours
+ * (RETR_LIST) order of the surviving candidates.  thresh is compared in float32
+ * (numpy: pred > thresh), box_thresh / unclip_ratio in float64 like upstream. */
 size_t lumina_db_workspace_bytes(int n, int h, int w, int max_candidates);
-int lumina_db_postprocess(const float *d_pred, int n, int h, int w, float thresh, float box_thresh,
-                          float unclip_ratio, int max_candidates, int min_size, const int32_t *h_src_hw,
+int lumina_db_postprocess(const float *d_pred, int n, int h, int w, float thresh, double box_thresh,
+                          double unclip_ratio, int max_candidates, int min_size, const int32_t *h_src_hw,
                           int32_t *d_boxes, float *d_scores, int32_t *d_counts, void *d_workspace,
                           size_t workspace_bytes, void *stream);
-/* Stage outputs for parity tests: binary mask + 8-connected labels
- * (label = min raster index of the component + 1, 0 = background). */
+/* Stage outputs for parity tests: binary mask {0,1} + 8-connected labels
+ * (label = min raster index of the component + 1, 0 = background).
+ * workspace >= align256(n*h*w) + 4*n*h*w bytes. */
 int lumina_db_mask_ccl(const float *d_pred, int n, int h, int w, float thresh, uint8_t *d_mask,
-                       int32_t *d_labels, void *stream);
+                       int32_t *d_labels, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- synthetic workloads (bench/test inputs generated in HBM) ------------ */
 /* A4-like text page, seeded by page index; identical bytes to the host

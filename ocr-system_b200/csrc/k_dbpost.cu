@@ -1,0 +1,578 @@
+// k_dbpost.cu -- [upstream PaddleOCR] DBPostProcess on the GPU:
+// probability map -> mask -> connected components -> min-area quads -> mean score ->
+// Clipper round-offset ("unclip") -> min-area quads -> boxes in source coordinates.
+//
+// Not in the reference tree.  cv2.findContours(RETR_LIST) is
+// replaced by its component-level equivalent (verified with cv2):
+//   outer border  <-> 8-connected foreground component
+//   hole border   <-> 4-connected background component that does not touch the image
+//                     border; its points are the foreground pixels 4-adjacent to it
+//   contour order <-> descending raster position of the component's first pixel
+// One union-find labelling pass handles both classes at once (ballot-initialised row
+// runs, atomicMin unions).  Per candidate, one warp gathers the row extremes of the
+// component (the only pixels a convex hull can use), then runs the geometry of
+// db_geom.h: hull -> rotating calipers -> fillPoly-exact mean score (lanes stride the
+// covered pixels) -> Clipper offset -> hull -> calipers -> scale/clip/round.
+#include "ccl.cuh"
+#include "db_geom.h"
+
+namespace lumina {
+
+struct DbLayout {
+    size_t mask_off, labels_off, cand_off, bbox_off, ncand_off, pool_off, poolctr_off, accept_off, tmpbox_off, tmpscore_off,
+        total;
+    size_t pool_pts_per_map;
+};
+
+static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static DbLayout db_layout(int n, int h, int w, int maxc) {
+    DbLayout L;
+    const size_t px = (size_t)h * w;
+    size_t off = 0;
+    L.mask_off = off; off = a256(off + (size_t)n * px);
+    L.labels_off = off; off = a256(off + (size_t)n * px * 4);
+    L.cand_off = off; off = a256(off + (size_t)n * maxc * 4);           // root position per slot (<0: hole, encoded)
+    L.bbox_off = off; off = a256(off + (size_t)n * maxc * 4 * 4);      // xmin, ymin, xmax, ymax
+    L.ncand_off = off; off = a256(off + (size_t)n * 2 * 4);            // total found, kept
+    L.pool_pts_per_map = px + 4096;  // DbgPt (8 B): row extremes + hull of every candidate (4*rows+2 each)
+    L.pool_off = off; off = a256(off + (size_t)n * L.pool_pts_per_map * 8);
+    L.poolctr_off = off; off = a256(off + (size_t)n * 4);
+    L.accept_off = off; off = a256(off + (size_t)n * maxc);
+    L.tmpbox_off = off; off = a256(off + (size_t)n * maxc * 8 * 4);
+    L.tmpscore_off = off; off = a256(off + (size_t)n * maxc * 4);
+    L.total = off;
+    return L;
+}
+
+// ---- 1. mask ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) db_mask_kernel(const float *__restrict__ pred, uint8_t *__restrict__ mask, size_t total,
+                                                      float thresh) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    if (i + 4 <= total && ((((uintptr_t)pred) & 15) == 0)) {
+        const uint4 u = ldg_stream_u4(pred + i);
+        const uint32_t m = (__uint_as_float(u.x) > thresh ? 1u : 0u) | (__uint_as_float(u.y) > thresh ? 0x100u : 0u) |
+                           (__uint_as_float(u.z) > thresh ? 0x10000u : 0u) | (__uint_as_float(u.w) > thresh ? 0x1000000u : 0u);
+        *reinterpret_cast<uint32_t *>(mask + i) = m;
+    } else {
+        for (size_t k = i; k < total && k < i + 4; k++) mask[k] = pred[k] > thresh ? 1 : 0;
+    }
+}
+
+// ---- 2. two-class union-find labelling ----------------------------------------------
+__global__ void __launch_bounds__(256) db_ccl_init_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h,
+                                                          int w, long long nseg_total) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= nseg_total) return;
+    const int segs_per_row = (w + 31) >> 5;
+    const long long row_g = gw / segs_per_row;
+    const int seg = (int)(gw - row_g * segs_per_row);
+    const int page = (int)(row_g / h), y = (int)(row_g - (long long)page * h);
+    const int x = seg * 32 + lane;
+    const size_t pbase = (size_t)page * h * w;
+    const bool in = x < w;
+    const int idx = y * w + x;
+    const int c = in ? (mask[pbase + idx] & 1) : 0;
+    const unsigned m1 = __ballot_sync(0xffffffffu, in && c == 1);
+    const unsigned m0 = __ballot_sync(0xffffffffu, in && c == 0);
+    if (in) {
+        const unsigned mine = c ? m1 : m0;
+        const unsigned below = ~mine & ((1u << lane) - 1u);
+        const int start = below ? 32 - __clz(below) : 0;
+        labels[pbase + idx] = idx - (lane - start);
+    }
+}
+
+__global__ void __launch_bounds__(256) db_ccl_merge_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h,
+                                                           int w, long long total_px) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_px) return;
+    const long long hw = (long long)h * w;
+    const int page = (int)(g / hw);
+    const int idx = (int)(g - (long long)page * hw);
+    const uint8_t *M = mask + (size_t)page * hw;
+    int *L = labels + (size_t)page * hw;
+    const int c = M[idx] & 1;
+    const int y = idx / w, x = idx - y * w;
+    if ((x & 31) == 0 && x > 0 && (M[idx - 1] & 1) == c) ccl_union(L, idx, idx - 1);
+    if (y > 0) {
+        const int up = idx - w;
+        if ((M[up] & 1) == c) {
+            const bool left_same = x > 0 && (M[idx - 1] & 1) == c;
+            const bool upleft_same = x > 0 && (M[up - 1] & 1) == c;
+            if (!(left_same && upleft_same)) ccl_union(L, idx, up);
+        } else if (c == 1) {  // foreground is 8-connected
+            if (x > 0 && (M[up - 1] & 1)) ccl_union(L, idx, up - 1);
+            if (x + 1 < w && (M[up + 1] & 1)) ccl_union(L, idx, up + 1);
+        }
+    }
+}
+
+// flatten; background components touching the image border get bit 1 on their root's mask byte
+__global__ void __launch_bounds__(256) db_ccl_flatten_kernel(uint8_t *__restrict__ mask, int *__restrict__ labels, int h, int w,
+                                                             long long total_px) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_px) return;
+    const long long hw = (long long)h * w;
+    const int page = (int)(g / hw);
+    const int idx = (int)(g - (long long)page * hw);
+    uint8_t *M = mask + (size_t)page * hw;
+    int *L = labels + (size_t)page * hw;
+    const int root = ccl_find(L, idx);
+    L[idx] = root;
+    if ((M[idx] & 1) == 0) {
+        const int y = idx / w, x = idx - y * w;
+        if (x == 0 || y == 0 || x == w - 1 || y == h - 1) M[root] = 2;  // same value from every writer
+    }
+}
+
+// ---- 3. candidates in findContours order ----------------------------------------------
+// One CTA per map: raster-order compaction of component roots (outer: fg root; hole: root of
+// a bg component that does not touch the border).  Discovery order == ascending root position;
+// findContours returns the reverse, truncated to max_candidates.  Two passes: count, then place.
+__global__ void __launch_bounds__(1024) db_candidates_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels,
+                                                             int *__restrict__ cand, int *__restrict__ bbox,
+                                                             int *__restrict__ ncand, int h, int w, int maxc) {
+    const int page = blockIdx.x;
+    const int px = h * w;
+    const uint8_t *M = mask + (size_t)page * px;
+    int *L = labels + (size_t)page * px;
+    int *C = cand + (size_t)page * maxc;
+    int *B = bbox + (size_t)page * maxc * 4;
+    __shared__ int wsum[32];
+    __shared__ int chunk_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < maxc; i += blockDim.x) {
+        C[i] = 0x7fffffff;
+        B[i * 4 + 0] = 0x7fffffff; B[i * 4 + 1] = 0x7fffffff; B[i * 4 + 2] = -1; B[i * 4 + 3] = -1;
+    }
+    int total = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        int base = 0;
+        for (int p0 = 0; p0 < px; p0 += 1024 * 4) {
+            const int p = p0 + threadIdx.x * 4;
+            uint32_t bits = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int q = p + k;
+                if (q < px) {
+                    const int lab = L[q];
+                    const uint8_t mv = M[q];
+                    const bool root = pass == 0 ? (lab == q) : (lab == q || lab < 0);
+                    if (root && ((mv & 1) || mv == 0)) bits |= 1u << k;  // fg root, or bg root not touching the border
+                }
+            }
+            const int c = __popc(bits);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                const int v = wsum[lane];
+                int s = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, s, o);
+                    if (lane >= o) s += t;
+                }
+                wsum[lane] = s - v;
+                if (lane == 31) chunk_total = s;
+            }
+            __syncthreads();
+            if (pass == 1) {
+                int i = base + wsum[warp] + inc - c;  // ascending discovery index
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (bits & (1u << k)) {
+                        const int q = p + k;
+                        const int slot = total - 1 - i;  // findContours order = reverse discovery
+                        if (slot < maxc) {
+                            C[slot] = (M[q] & 1) ? q : -1 - q;  // hole candidates are stored negated
+                            L[q] = -2 - slot;                   // root now carries its slot
+                        } else {
+                            L[q] = -1;                          // dropped by max_candidates
+                        }
+                        i++;
+                    }
+            }
+            base += chunk_total;
+            __syncthreads();
+        }
+        if (pass == 0) total = base;
+    }
+    if (threadIdx.x == 0) { ncand[page * 2] = total; ncand[page * 2 + 1] = total < maxc ? total : maxc; }
+}
+
+__device__ __forceinline__ int db_slot_of(const int *L, int p) {
+    const int lab = L[p];
+    if (lab < 0) return -2 - lab;          // p is a root (slot, or -1 when dropped)
+    const int r = L[lab];
+    return r < 0 ? -2 - r : -1;
+}
+
+// ---- 4. bounding boxes of the candidates' point sets -----------------------------------
+__global__ void __launch_bounds__(256) db_bbox_kernel(const uint8_t *__restrict__ mask, const int *__restrict__ labels,
+                                                      int *__restrict__ bbox, int h, int w, int maxc, long long total_px) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_px) return;
+    const long long hw = (long long)h * w;
+    const int page = (int)(g / hw);
+    const int idx = (int)(g - (long long)page * hw);
+    const uint8_t *M = mask + (size_t)page * hw;
+    const int *L = labels + (size_t)page * hw;
+    int *B = bbox + (size_t)page * maxc * 4;
+    const int y = idx / w, x = idx - y * w;
+    const int slot = db_slot_of(L, idx);
+    if (slot < 0) return;
+    if (M[idx] & 1) {
+        // only pixels on the component's outline can move the box
+        const bool inner = x > 0 && x < w - 1 && y > 0 && y < h - 1 && (M[idx - 1] & 1) && (M[idx + 1] & 1) &&
+                           (M[idx - w] & 1) && (M[idx + w] & 1);
+        if (inner) return;
+        atomicMin(&B[slot * 4 + 0], x); atomicMin(&B[slot * 4 + 1], y);
+        atomicMax(&B[slot * 4 + 2], x); atomicMax(&B[slot * 4 + 3], y);
+    } else {
+        // hole pixel: its 4-adjacent foreground pixels are the hole border's point set
+        const int nx[4] = {x - 1, x + 1, x, x}, ny[4] = {y, y, y - 1, y + 1};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (nx[k] < 0 || nx[k] >= w || ny[k] < 0 || ny[k] >= h) continue;
+            if (!(M[ny[k] * w + nx[k]] & 1)) continue;
+            atomicMin(&B[slot * 4 + 0], nx[k]); atomicMin(&B[slot * 4 + 1], ny[k]);
+            atomicMax(&B[slot * 4 + 2], nx[k]); atomicMax(&B[slot * 4 + 3], ny[k]);
+        }
+    }
+}
+
+// ---- 5. per-candidate geometry: one warp per candidate ----------------------------------
+struct DbParams {
+    const float *pred;
+    const uint8_t *mask;
+    const int *labels;
+    const int *cand;
+    const int *bbox;
+    const int *ncand;
+    DbgPt *pool;
+    int *poolctr;
+    uint8_t *accept;
+    int *tmpbox;
+    float *tmpscore;
+    const int *src_hw;  // [n][2] device copy
+    size_t pool_pts_per_map;
+    int h, w, maxc, min_size;
+    double box_thresh, unclip_ratio;
+};
+
+// merged coverage intervals of one mask row.  Deliberately out of line: inlined into the candidate
+// kernel nvcc 12.9 produced wrong interval bounds for x-major edges (caught by the parity test).
+__device__ __noinline__ int db_row_intervals(const DbgPt *q4, int ry, int *lo, int *hi) {
+    DbgPt q[4] = {q4[0], q4[1], q4[2], q4[3]};
+    int l[5] = {0, 0, 0, 0, 0}, h[5] = {-1, -1, -1, -1, -1};
+    int c = dbg_row_cover(q, ry, l, h);
+    c = dbg_merge(l, h, c);
+    for (int i = 0; i < 5; i++) { lo[i] = l[i]; hi[i] = h[i]; }
+    return c;
+}
+
+constexpr int DB_WARPS = 4;
+constexpr int DB_OFFS_MAX = 384;  // Clipper offset vertices kept in shared memory per warp
+
+__global__ void __launch_bounds__(DB_WARPS * 32) db_candidate_geometry_kernel(const DbParams p) {
+    __shared__ DbgPt offs[DB_WARPS][DB_OFFS_MAX + 2];
+    __shared__ DbgPt offs_hull[DB_WARPS][DB_OFFS_MAX + 2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int page = blockIdx.y;
+    const int slot = blockIdx.x * DB_WARPS + wib;
+    if (slot >= p.ncand[page * 2 + 1]) return;
+    const int px = p.h * p.w;
+    const uint8_t *M = p.mask + (size_t)page * px;
+    const int *L = p.labels + (size_t)page * px;
+    const float *P = p.pred + (size_t)page * px;
+    const int centry = p.cand[(size_t)page * p.maxc + slot];
+    const bool hole = centry < 0;
+    const int root = hole ? -1 - centry : centry;
+    const int *B = p.bbox + ((size_t)page * p.maxc + slot) * 4;
+    const int bx0 = B[0], by0 = B[1], bx1 = B[2], by1 = B[3];
+    uint8_t *acc = p.accept + (size_t)page * p.maxc + slot;
+    if (lane == 0) *acc = 0;
+    if (bx1 < bx0 || by1 < by0) return;
+    const int rows = by1 - by0 + 1;
+    // pool space: 2*rows sorted points + (2*rows + 2) hull points
+    int pbase = 0;
+    if (lane == 0) pbase = atomicAdd(p.poolctr + page, 4 * rows + 2);
+    pbase = __shfl_sync(0xffffffffu, pbase, 0);
+    if ((size_t)pbase + 4 * rows + 2 > p.pool_pts_per_map) { if (lane == 0) *acc = 15; return; }  // pathological masks only (> px/4 candidate rows): dropped
+    DbgPt *pts = p.pool + (size_t)page * p.pool_pts_per_map + pbase;
+    DbgPt *hull = pts + 2 * rows;
+    // ---- row extremes of the candidate's point set ----
+    int npts = 0;
+    for (int y = by0; y <= by1; y++) {
+        int rmin = 0x7fffffff, rmax = -1;
+        for (int xb = bx0; xb <= bx1; xb += 32) {
+            const int x = xb + lane;
+            bool member = false;
+            if (x <= bx1) {
+                const int q = y * p.w + x;
+                if (M[q] & 1) {
+                    if (!hole) member = (q == root) || (L[q] == root);
+                    else {
+                        // foreground pixel 4-adjacent to a pixel of this hole
+                        if (x > 0 && !(M[q - 1] & 1) && (q - 1 == root || L[q - 1] == root)) member = true;
+                        else if (x + 1 < p.w && !(M[q + 1] & 1) && (q + 1 == root || L[q + 1] == root)) member = true;
+                        else if (y > 0 && !(M[q - p.w] & 1) && (q - p.w == root || L[q - p.w] == root)) member = true;
+                        else if (y + 1 < p.h && !(M[q + p.w] & 1) && (q + p.w == root || L[q + p.w] == root)) member = true;
+                    }
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, member);
+            if (b) {
+                rmin = min(rmin, xb + __ffs(b) - 1);
+                rmax = max(rmax, xb + 31 - __clz(b));
+            }
+        }
+        if (rmax >= 0) {
+            if (lane == 0) {
+                pts[npts].x = rmin; pts[npts].y = y;
+                pts[npts + 1].x = rmax; pts[npts + 1].y = y;
+            }
+            npts += 2;
+        }
+    }
+    __syncwarp();
+    // ---- first min-area quad (lane 0), broadcast ----
+    float bxs[4] = {0, 0, 0, 0}, bys[4] = {0, 0, 0, 0};
+    float sside = 0.f;
+    if (lane == 0) {
+        int hn = dbg_hull_sorted(pts, npts, hull);
+        // note: roots carry the slot code in L; the root position itself is the (y,x)-smallest pixel
+        const int hy = root / p.w, hx = root - hy * p.w;
+        dbg_hull_rotate(hull, hn, hole ? 2 : 1, hx - 1, hy);
+        const DbgRect r = dbg_min_area_rect(hull, hn);
+        DbgPtF o[4];
+        sside = dbg_mini_box(r, o);
+        for (int i = 0; i < 4; i++) { bxs[i] = o[i].x; bys[i] = o[i].y; }
+    }
+    sside = __shfl_sync(0xffffffffu, sside, 0);
+    if (sside < (float)p.min_size) { if (lane == 0) *acc = 11; return; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { bxs[i] = __shfl_sync(0xffffffffu, bxs[i], 0); bys[i] = __shfl_sync(0xffffffffu, bys[i], 0); }
+    // ---- box_score_fast: mean of pred over cv2.fillPoly(int32(box - (xmin, ymin))) ----
+    const float fminx = fminf(fminf(bxs[0], bxs[1]), fminf(bxs[2], bxs[3]));
+    const float fmaxx = fmaxf(fmaxf(bxs[0], bxs[1]), fmaxf(bxs[2], bxs[3]));
+    const float fminy = fminf(fminf(bys[0], bys[1]), fminf(bys[2], bys[3]));
+    const float fmaxy = fmaxf(fmaxf(bys[0], bys[1]), fmaxf(bys[2], bys[3]));
+    const int xmin = min(max((int)floorf(fminx), 0), p.w - 1), xmax = min(max((int)ceilf(fmaxx), 0), p.w - 1);
+    const int ymin = min(max((int)floorf(fminy), 0), p.h - 1), ymax = min(max((int)ceilf(fmaxy), 0), p.h - 1);
+    DbgPt q[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { q[i].x = (int)(bxs[i] - (float)xmin); q[i].y = (int)(bys[i] - (float)ymin); }
+    const int mh = ymax - ymin + 1, mw = xmax - xmin + 1;
+    double sum = 0.0;
+    int cnt = 0;
+    for (int ry = 0; ry < mh; ry++) {
+        int lo[5], hi[5];
+        const int c = db_row_intervals(q, ry, lo, hi);
+        const float *prow = P + (size_t)(ymin + ry) * p.w + xmin;
+        for (int i = 0; i < c; i++) {
+            const int a = max(lo[i], 0), b = min(hi[i], mw - 1);
+            for (int x = a + lane; x <= b; x += 32) { sum += (double)__ldg(prow + x); cnt++; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const double score = cnt > 0 ? sum / (double)cnt : 0.0;
+    if (p.box_thresh > score) {
+        if (lane == 0) {  // reject code + the score that failed (diagnostics)
+            *acc = 12;
+            p.tmpscore[(size_t)page * p.maxc + slot] = (float)score;
+        }
+        return;
+    }
+    // ---- unclip + second min-area quad (lane 0) ----
+    int ok = 0;
+    int outq[8];
+    if (lane == 0) {
+        DbgPtF b4[4];
+        for (int i = 0; i < 4; i++) { b4[i].x = bxs[i]; b4[i].y = bys[i]; }
+        const double dist = dbg_unclip_distance(b4, p.unclip_ratio);
+        if (dist >= 0) {
+            const int m = dbg_clipper_offset(b4, dist, offs[wib], DB_OFFS_MAX);
+            if (m >= 3) {
+                dbg_sort(offs[wib], m);
+                const int hn = dbg_hull_sorted(offs[wib], m, offs_hull[wib]);
+                const DbgRect r2 = dbg_min_area_rect(offs_hull[wib], hn);
+                DbgPtF o2[4];
+                const float ss2 = dbg_mini_box(r2, o2);
+                if (!(ss2 < (float)(p.min_size + 2))) {
+                    const double dw = (double)p.src_hw[page * 2 + 1], dh = (double)p.src_hw[page * 2];
+                    for (int i = 0; i < 4; i++) {
+                        outq[i * 2] = dbg_scale_coord(o2[i].x, p.w, dw);
+                        outq[i * 2 + 1] = dbg_scale_coord(o2[i].y, p.h, dh);
+                    }
+                    ok = 1;
+                }
+            }
+        }
+        if (ok) {
+            int *tb = p.tmpbox + ((size_t)page * p.maxc + slot) * 8;
+            for (int i = 0; i < 8; i++) tb[i] = outq[i];
+            p.tmpscore[(size_t)page * p.maxc + slot] = (float)score;
+            *acc = 1;
+        } else {
+            *acc = 13;
+        }
+    }
+}
+
+// ---- 6. ordered compaction of the accepted candidates ------------------------------------
+__global__ void __launch_bounds__(1024) db_compact_kernel(const uint8_t *__restrict__ accept, const int *__restrict__ tmpbox,
+                                                          const float *__restrict__ tmpscore, const int *__restrict__ ncand,
+                                                          int *__restrict__ boxes, float *__restrict__ scores,
+                                                          int *__restrict__ counts, int maxc) {
+    const int page = blockIdx.x;
+    const int kept = ncand[page * 2 + 1];
+    __shared__ int wsum[32];
+    __shared__ int chunk_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;
+    for (int s0 = 0; s0 < kept; s0 += 1024) {
+        const int s = s0 + threadIdx.x;
+        const int a = (s < kept && accept[(size_t)page * maxc + s] == 1) ? 1 : 0;  // other codes = reject reasons
+        int inc = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = wsum[lane];
+            int t = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
+            }
+            wsum[lane] = t - v;
+            if (lane == 31) chunk_total = t;
+        }
+        __syncthreads();
+        if (a) {
+            const int dst = base + wsum[warp] + inc - 1;
+            const int *tb = tmpbox + ((size_t)page * maxc + s) * 8;
+            int *ob = boxes + ((size_t)page * maxc + dst) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) ob[i] = tb[i];
+            scores[(size_t)page * maxc + dst] = tmpscore[(size_t)page * maxc + s];
+        }
+        base += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[page] = base;
+}
+
+// canonical labels for the stage-level parity test: label = min raster index + 1 for fg, 0 for bg
+__global__ void __launch_bounds__(256) db_export_labels_kernel(const uint8_t *__restrict__ mask, const int *__restrict__ labels,
+                                                               uint8_t *__restrict__ mask_out, int *__restrict__ labels_out,
+                                                               long long total_px) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_px) return;
+    const int fg = mask[g] & 1;
+    mask_out[g] = (uint8_t)fg;
+    labels_out[g] = fg ? labels[g] + 1 : 0;
+}
+
+static int db_label(const float *d_pred, int n, int h, int w, float thresh, uint8_t *mask, int *labels, cudaStream_t st) {
+    const size_t px = (size_t)n * h * w;
+    db_mask_kernel<<<(unsigned)((px / 4 + 256) / 256), 256, 0, st>>>(d_pred, mask, px, thresh);
+    LUMINA_KERNEL_CHECK("db_mask_kernel");
+    const long long nseg = (long long)n * h * ((w + 31) / 32);
+    db_ccl_init_kernel<<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, st>>>(mask, labels, h, w, nseg);
+    LUMINA_KERNEL_CHECK("db_ccl_init_kernel");
+    const unsigned gpx = (unsigned)((px + 255) / 256);
+    db_ccl_merge_kernel<<<gpx, 256, 0, st>>>(mask, labels, h, w, (long long)px);
+    LUMINA_KERNEL_CHECK("db_ccl_merge_kernel");
+    db_ccl_flatten_kernel<<<gpx, 256, 0, st>>>(mask, labels, h, w, (long long)px);
+    LUMINA_KERNEL_CHECK("db_ccl_flatten_kernel");
+    return LUMINA_OK;
+}
+
+}  // namespace lumina
+
+using namespace lumina;
+
+LUMINA_API size_t lumina_db_workspace_bytes(int n, int h, int w, int max_candidates) {
+    if (n <= 0 || h <= 0 || w <= 0 || max_candidates <= 0) return 0;
+    return db_layout(n, h, w, max_candidates).total + (size_t)n * 2 * 4 + 256;
+}
+
+LUMINA_API int lumina_db_postprocess(const float *d_pred, int n, int h, int w, float thresh, double box_thresh,
+                                     double unclip_ratio, int max_candidates, int min_size, const int32_t *h_src_hw,
+                                     int32_t *d_boxes, float *d_scores, int32_t *d_counts, void *d_workspace,
+                                     size_t workspace_bytes, void *stream) {
+    LUMINA_REQUIRE(d_pred && h_src_hw && d_boxes && d_scores && d_counts && d_workspace, "null pointer");
+    LUMINA_REQUIRE(n > 0 && h > 0 && w > 0 && max_candidates > 0, "empty batch");
+    LUMINA_REQUIRE((long long)h * w < (1LL << 30), "map too large");
+    LUMINA_REQUIRE((((uintptr_t)d_workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    const size_t need = lumina_db_workspace_bytes(n, h, w, max_candidates);
+    if (workspace_bytes < need) return set_error(LUMINA_E_NOMEM, "db workspace too small: need %zu bytes", need);
+    const DbLayout L = db_layout(n, h, w, max_candidates);
+    cudaStream_t st = as_stream(stream);
+    uint8_t *ws = (uint8_t *)d_workspace;
+    uint8_t *mask = ws + L.mask_off;
+    int *labels = (int *)(ws + L.labels_off);
+    int *src_hw_dev = (int *)(ws + L.total);
+    LUMINA_CUDA_TRY(cudaMemcpyAsync(src_hw_dev, h_src_hw, (size_t)n * 2 * 4, cudaMemcpyHostToDevice, st));
+    LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.poolctr_off, 0, (size_t)n * 4, st));
+    int rc = db_label(d_pred, n, h, w, thresh, mask, labels, st);
+    if (rc != LUMINA_OK) return rc;
+    LUMINA_REQUIRE(n <= 65535, "batch too large for grid");
+    db_candidates_kernel<<<n, 1024, 0, st>>>(mask, labels, (int *)(ws + L.cand_off), (int *)(ws + L.bbox_off),
+                                             (int *)(ws + L.ncand_off), h, w, max_candidates);
+    LUMINA_KERNEL_CHECK("db_candidates_kernel");
+    const size_t px = (size_t)n * h * w;
+    db_bbox_kernel<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(mask, labels, (int *)(ws + L.bbox_off), h, w, max_candidates,
+                                                                  (long long)px);
+    LUMINA_KERNEL_CHECK("db_bbox_kernel");
+    DbParams p;
+    p.pred = d_pred; p.mask = mask; p.labels = labels;
+    p.cand = (const int *)(ws + L.cand_off); p.bbox = (const int *)(ws + L.bbox_off); p.ncand = (const int *)(ws + L.ncand_off);
+    p.pool = (DbgPt *)(ws + L.pool_off); p.poolctr = (int *)(ws + L.poolctr_off);
+    p.accept = ws + L.accept_off; p.tmpbox = (int *)(ws + L.tmpbox_off); p.tmpscore = (float *)(ws + L.tmpscore_off);
+    p.src_hw = src_hw_dev; p.pool_pts_per_map = L.pool_pts_per_map;
+    p.h = h; p.w = w; p.maxc = max_candidates; p.min_size = min_size;
+    p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
+    db_candidate_geometry_kernel<<<dim3(div_up(max_candidates, DB_WARPS), n), DB_WARPS * 32, 0, st>>>(p);
+    LUMINA_KERNEL_CHECK("db_candidate_geometry_kernel");
+    db_compact_kernel<<<n, 1024, 0, st>>>(p.accept, p.tmpbox, p.tmpscore, p.ncand, d_boxes, d_scores, d_counts, max_candidates);
+    LUMINA_KERNEL_CHECK("db_compact_kernel");
+    return LUMINA_OK;
+}
+
+LUMINA_API int lumina_db_mask_ccl(const float *d_pred, int n, int h, int w, float thresh, uint8_t *d_mask, int32_t *d_labels,
+                                  void *d_workspace, size_t workspace_bytes, void *stream) {
+    LUMINA_REQUIRE(d_pred && d_mask && d_labels && d_workspace, "null pointer");
+    LUMINA_REQUIRE(n > 0 && h > 0 && w > 0, "empty batch");
+    LUMINA_REQUIRE((((uintptr_t)d_workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    const size_t px = (size_t)n * h * w;
+    const size_t need = a256(px) + px * 4;
+    if (workspace_bytes < need) return set_error(LUMINA_E_NOMEM, "db label workspace too small: need %zu bytes", need);
+    cudaStream_t st = as_stream(stream);
+    uint8_t *mask = (uint8_t *)d_workspace;
+    int *labels = (int *)((uint8_t *)d_workspace + a256(px));
+    int rc = db_label(d_pred, n, h, w, thresh, mask, labels, st);
+    if (rc != LUMINA_OK) return rc;
+    db_export_labels_kernel<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(mask, labels, d_mask, d_labels, (long long)px);
+    LUMINA_KERNEL_CHECK("db_export_labels_kernel");
+    return LUMINA_OK;
+}

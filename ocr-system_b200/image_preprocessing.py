@@ -1,0 +1,313 @@
+"""Drop-in ``ImagePreprocessor`` backed by the sm_100a kernels.
+
+Mirrors the public surface of the reference's
+``backend/utils/image_preprocessing.py`` (class ``ImagePreprocessor`` :35, singleton
+``image_preprocessor`` :632): same method names, argument meaning, return types
+(PIL in -> PIL out, ``deskew`` -> ``(image, angle)``, ``preprocess_for_azure`` ->
+JPEG bytes) and error behaviour (``FileNotFoundError`` :61,277, ``ImportError``
+:268; ``deskew`` degrades to ``(image, 0.0)`` instead of raising).  Every pixel
+operation runs on the GPU through the C-ABI; codecs (PNG/JPEG/PDF) stay on the
+host exactly as in the reference -- they are the boundary, not the path.
+
+A single call is a batch of one (H2D + kernels + D2H); throughput comes from the
+batched API in ``pipeline.PagePipeline``.
+"""
+from __future__ import annotations
+
+import io
+import logging
+import os
+from pathlib import Path
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import ops
+
+logger = logging.getLogger(__name__)
+
+ImageSource = Union[str, Path, Image.Image, bytes]
+
+
+def _setting(name: str, default):
+    """Hot-path knobs of the reference's ``config.settings`` (config.py:69,85-87).
+
+    Inside the reference app its own ``config.settings`` object is honoured; standalone
+    the same names are read from the environment."""
+    try:  # drop-in inside the reference backend: `config` is importable there
+        from config import settings  # type: ignore
+
+        return getattr(settings, name, default)
+    except Exception:
+        raw = os.environ.get(name)
+        if raw is None:
+            return default
+        if isinstance(default, bool):
+            return raw.strip().lower() in ("1", "true", "yes", "on")
+        return type(default)(raw)
+
+
+class ImagePreprocessor:
+    """GPU image preprocessing with the reference's call signatures."""
+
+    def __init__(self, max_dimension: int = None, target_dpi: int = 300, device: Optional[str] = None):
+        self.max_dimension = max_dimension or _setting("OCR_MAX_IMAGE_DIMENSION", 2000)
+        self.target_dpi = target_dpi
+        self._device = device
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def device(self) -> torch.device:
+        if not torch.cuda.is_available():
+            raise RuntimeError("ocr_system_b200 needs a CUDA device: there is no CPU fallback for the pixel path")
+        return torch.device(self._device or f"cuda:{torch.cuda.current_device()}")
+
+    def _to_device(self, image: Image.Image) -> torch.Tensor:
+        if image.mode not in ("RGB", "L"):
+            raise ValueError(f"unsupported image mode {image.mode!r}: load_image() converts to RGB/L first")
+        arr = np.asarray(image)
+        if not arr.flags["C_CONTIGUOUS"] or not arr.flags["WRITEABLE"]:
+            arr = np.array(arr)
+        t = torch.from_numpy(arr).unsqueeze(0)
+        if t.dim() == 3:  # L -> [1,H,W,1]: every batch on the device is NHWC
+            t = t.unsqueeze(-1)
+        return t.to(self.device, non_blocking=False)
+
+    @staticmethod
+    def _to_pil(t: torch.Tensor) -> Image.Image:
+        a = t[0]
+        if a.dim() == 3 and a.shape[-1] == 1:
+            a = a.squeeze(-1)
+        return Image.fromarray(a.cpu().numpy())
+
+    def _open(self, image: ImageSource) -> Image.Image:
+        if isinstance(image, bytes):
+            return self.load_image_bytes(image)
+        if isinstance(image, (str, Path)):
+            return self.load_image(image)
+        return image
+
+    # ------------------------------------------------------------------ loading (host codecs)
+    def load_image(self, image_path: Union[str, Path]) -> Image.Image:
+        path = Path(image_path)
+        if not path.exists():
+            raise FileNotFoundError(f"Image not found: {path}")
+        image = Image.open(path)
+        return image if image.mode in ("RGB", "L") else image.convert("RGB")
+
+    def load_image_bytes(self, image_bytes: bytes) -> Image.Image:
+        image = Image.open(io.BytesIO(image_bytes))
+        return image if image.mode in ("RGB", "L") else image.convert("RGB")
+
+    # ------------------------------------------------------------------ size
+    def get_optimal_size(self, width: int, height: int, max_dimension: int = None) -> Tuple[int, int]:
+        return ops.target_size(width, height, max_dimension or self.max_dimension)
+
+    def resize_if_needed(self, image: Image.Image, max_dimension: int = None) -> Image.Image:
+        max_dim = max_dimension or self.max_dimension
+        width, height = image.size
+        if max(width, height) <= max_dim:
+            return image
+        new_w, new_h = ops.target_size(width, height, max_dim)
+        logger.info(f"Resizing image from {width}x{height} to {new_w}x{new_h}")
+        return self._to_pil(ops.resize_lanczos(self._to_device(image), new_w, new_h))
+
+    # ------------------------------------------------------------------ enhancement
+    def enhance_contrast(self, image: Image.Image, factor: float = 1.3) -> Image.Image:
+        return self._to_pil(ops.enhance_contrast(self._to_device(image), factor))
+
+    def enhance_sharpness(self, image: Image.Image, factor: float = 1.2) -> Image.Image:
+        return self._to_pil(ops.enhance_sharpness(self._to_device(image), factor))
+
+    def denoise(self, image: Image.Image) -> Image.Image:
+        return self._to_pil(ops.median3(self._to_device(image)))
+
+    def convert_to_grayscale(self, image: Image.Image) -> Image.Image:
+        if image.mode == "L":
+            return image.copy()
+        return self._to_pil(ops.gray_pil(self._to_device(image)))
+
+    def auto_orient(self, image: Image.Image) -> Image.Image:
+        orientation = image.getexif().get(0x0112)
+        if orientation not in (2, 3, 4, 5, 6, 7, 8):
+            return image.copy()
+        return self._to_pil(ops.exif_transpose(self._to_device(image), int(orientation)))
+
+    def binarize(self, image: Image.Image, threshold: int = 128) -> Image.Image:
+        mask = ops.binarize(self._to_device(image), threshold)
+        return Image.fromarray(mask[0].cpu().numpy()).convert("1", dither=Image.Dither.NONE)
+
+    # ------------------------------------------------------------------ composed pipelines
+    def optimize_for_ocr(self, image: ImageSource, apply_contrast: bool = True, apply_sharpness: bool = True,
+                         apply_denoise: bool = False, grayscale: bool = False) -> Image.Image:
+        """auto_orient -> resize -> [gray] -> [median] -> contrast 1.2 -> sharpness 1.1, one H2D/D2H."""
+        img = self.auto_orient(self._open(image))
+        x = self._to_device(img)
+        x = ops.resize_if_needed(x, self.max_dimension)
+        if grayscale and x.shape[-1] == 3:
+            x = ops.gray_pil(x).unsqueeze(-1)
+        if apply_denoise:
+            x = ops.median3(x)
+        if apply_contrast and apply_sharpness:
+            x = ops.contrast_sharpness(x, 1.2, 1.1)
+        elif apply_contrast:
+            x = ops.enhance_contrast(x, 1.2)
+        elif apply_sharpness:
+            x = ops.enhance_sharpness(x, 1.1)
+        return self._to_pil(x)
+
+    # ------------------------------------------------------------------ PDF (host rasteriser, then GPU resize)
+    def pdf_to_images(self, pdf_path: Union[str, Path], dpi: int = None) -> List[Image.Image]:
+        try:
+            from pdf2image import convert_from_path
+        except ImportError:
+            raise ImportError(
+                "pdf2image not installed. Install with: pip install pdf2image\n"
+                "Also install poppler: https://github.com/oschwartz10612/poppler-windows/releases"
+            )
+        path = Path(pdf_path)
+        if not path.exists():
+            raise FileNotFoundError(f"PDF not found: {path}")
+        pages = convert_from_path(str(path), dpi=dpi or self.target_dpi, fmt="png")
+        return self.resize_pages(pages)
+
+    def resize_pages(self, pages: List[Image.Image]) -> List[Image.Image]:
+        """The per-page ``resize_if_needed`` loop of pdf_to_images (:287-292), batched by page shape."""
+        out: List[Optional[Image.Image]] = [None] * len(pages)
+        groups = {}
+        for i, pg in enumerate(pages):
+            if pg.mode not in ("RGB", "L"):
+                pg = pages[i] = pg.convert("RGB")
+            if max(pg.size) <= self.max_dimension:
+                out[i] = pg
+            else:
+                groups.setdefault((pg.size, pg.mode), []).append(i)
+        for (size, _mode), idxs in groups.items():
+            batch = torch.from_numpy(np.stack([np.asarray(pages[i]) for i in idxs])).to(self.device)
+            nw, nh = ops.target_size(size[0], size[1], self.max_dimension)
+            res = ops.resize_lanczos(batch, nw, nh).cpu().numpy()
+            for k, i in enumerate(idxs):
+                out[i] = Image.fromarray(res[k])
+        return out  # type: ignore[return-value]
+
+    def get_pdf_page_count(self, pdf_path: Union[str, Path]) -> int:
+        try:
+            from pdf2image import pdfinfo_from_path
+
+            return pdfinfo_from_path(str(pdf_path)).get("Pages", 1)
+        except Exception:
+            return len(self.pdf_to_images(pdf_path))
+
+    # ------------------------------------------------------------------ utilities (host codecs)
+    def save_image(self, image: Image.Image, output_path: Union[str, Path], quality: int = 95,
+                   optimize: bool = True) -> Path:
+        path = Path(output_path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        suffix = path.suffix.lower()
+        if suffix in (".jpg", ".jpeg"):
+            image.save(path, "JPEG", quality=quality, optimize=optimize)
+        elif suffix == ".png":
+            image.save(path, "PNG", optimize=optimize)
+        else:
+            image.save(path)
+        return path
+
+    def image_to_bytes(self, image: Image.Image, format: str = "PNG", quality: int = 95) -> bytes:
+        buf = io.BytesIO()
+        if format.upper() in ("JPG", "JPEG"):
+            image.save(buf, format="JPEG", quality=quality)
+        else:
+            image.save(buf, format=format)
+        return buf.getvalue()
+
+    def get_image_info(self, image: Union[str, Path, Image.Image]) -> dict:
+        img = self.load_image(image) if isinstance(image, (str, Path)) else image
+        return {
+            "width": img.width,
+            "height": img.height,
+            "mode": img.mode,
+            "format": img.format,
+            "size_optimal": self.get_optimal_size(img.width, img.height),
+            "needs_resize": max(img.width, img.height) > self.max_dimension,
+        }
+
+    # ------------------------------------------------------------------ Azure preprocessing
+    def deskew(self, image: Image.Image) -> Tuple[Image.Image, float]:
+        """Canny -> HoughLinesP -> median angle -> bicubic rotation (reference :372-460).
+        Never raises for a bad page: degrades to ``(image, 0.0)`` like the reference."""
+        x = self._to_device(image.convert("RGB") if image.mode not in ("RGB", "L") else image)
+        out, angles = ops.deskew(x)
+        angle = float(angles[0])
+        if out is x or out.data_ptr() == x.data_ptr():
+            return image, angle
+        return self._to_pil(out), angle
+
+    def adaptive_binarize(self, image: Image.Image) -> Image.Image:
+        return self._to_pil(ops.adaptive_binarize(self._to_device(image), 2))
+
+    def compress_for_azure(self, image: Image.Image, target_size_mb: float = 2.0, initial_quality: int = 95,
+                           min_quality: int = 30) -> bytes:
+        """JPEG encode-to-size on the host codec (the step after the path).
+        Quality ladder initial..min step 10, then a Lanczos shrink by sqrt(target/current) on the GPU."""
+        target = int(target_size_mb * 1024 * 1024)
+        if image.mode in ("RGBA", "P", "L"):
+            image = image.convert("RGB")
+        quality = initial_quality
+        while quality >= min_quality:
+            buf = io.BytesIO()
+            image.save(buf, format="JPEG", quality=quality, optimize=True)
+            if buf.tell() <= target:
+                return buf.getvalue()
+            quality -= 10
+        buf = io.BytesIO()
+        image.save(buf, format="JPEG", quality=min_quality)
+        scale = (target / buf.tell()) ** 0.5
+        new_w, new_h = int(image.width * scale), int(image.height * scale)
+        small = self._to_pil(ops.resize_lanczos(self._to_device(image), new_w, new_h))
+        buf = io.BytesIO()
+        small.save(buf, format="JPEG", quality=min_quality, optimize=True)
+        return buf.getvalue()
+
+    def preprocess_device(self, x: torch.Tensor, apply_deskew: bool = True, apply_binarize: bool = False,
+                          apply_contrast: bool = True, apply_sharpness: bool = True):
+        """The pixel part of preprocess_for_azure on a resident page batch [N,H,W,C]:
+        resize -> deskew -> (contrast 1.2 -> sharpness 1.1 | adaptive binarize).  Returns (pages, angles)."""
+        x = ops.resize_if_needed(x, self.max_dimension)
+        angles = np.zeros(x.shape[0], np.float64)
+        if apply_deskew:
+            x, angles = ops.deskew(x)
+        if apply_binarize:
+            x = ops.adaptive_binarize(x, 2)
+        elif apply_contrast and apply_sharpness:
+            x = ops.contrast_sharpness(x, 1.2, 1.1)
+        elif apply_contrast:
+            x = ops.enhance_contrast(x, 1.2)
+        elif apply_sharpness:
+            x = ops.enhance_sharpness(x, 1.1)
+        return x, angles
+
+    def preprocess_for_azure(self, image: ImageSource, apply_deskew: bool = True, apply_binarize: bool = False,
+                             apply_contrast: bool = True, apply_sharpness: bool = True,
+                             target_size_mb: float = 2.0) -> bytes:
+        img = self.auto_orient(self._open(image))
+        logger.info(f"Preprocessing image: {img.size}, mode={img.mode}")
+        x, _ = self.preprocess_device(self._to_device(img), apply_deskew, apply_binarize, apply_contrast,
+                                      apply_sharpness)
+        return self.compress_for_azure(self._to_pil(x), target_size_mb=target_size_mb)
+
+
+class _LazySingleton:
+    """``image_preprocessor`` singleton (reference :632) built on first use, so importing
+    the module never touches CUDA."""
+
+    _inst: Optional[ImagePreprocessor] = None
+
+    def __getattr__(self, name):
+        if _LazySingleton._inst is None:
+            _LazySingleton._inst = ImagePreprocessor()
+        return getattr(_LazySingleton._inst, name)
+
+
+image_preprocessor = _LazySingleton()

@@ -330,3 +330,40 @@ def synth_pages(n: int, h: int = 3508, w: int = 2480, seed0: int = 0, device="cu
     with torch.cuda.device(out.device):
         _chk(_L().lumina_synth_pages_u8(_ptr(out), n, h, w, C.c_uint64(seed0), _stream()))
     return out
+
+
+# --------------------------------------------------------------------------- a16
+def db_mask_ccl(pred: torch.Tensor, thresh: float = 0.3):
+    """Stage outputs of the DB labelling: (mask {0,1} [N,H,W] u8, labels [N,H,W] int32 with
+    label = min raster index of the 8-connected component + 1, 0 = background)."""
+    if not pred.is_cuda or pred.dtype != torch.float32 or pred.dim() != 3:
+        raise TypeError("db_mask_ccl expects a CUDA float32 [N,H,W] tensor")
+    p = pred.contiguous()
+    n, h, w = p.shape
+    mask = torch.empty((n, h, w), dtype=torch.uint8, device=p.device)
+    labels = torch.empty((n, h, w), dtype=torch.int32, device=p.device)
+    wsb = ((n * h * w + 255) // 256) * 256 + 4 * n * h * w
+    ws = _ws(wsb, p.device)
+    _chk(_L().lumina_db_mask_ccl(_ptr(p), n, h, w, float(np.float32(thresh)), _ptr(mask), _ptr(labels), _ptr(ws), wsb,
+                                 _stream()))
+    return mask, labels
+
+
+def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: float = 0.7,
+                   unclip_ratio: float = 2.0, max_candidates: int = 1000, min_size: int = 3):
+    """DBPostProcess core on [N,H,W] float32 maps -> (boxes [N,max_candidates,4,2] int32,
+    scores [N,max_candidates] f32, counts [N] int32), all on the device."""
+    if not pred.is_cuda or pred.dtype != torch.float32 or pred.dim() != 3:
+        raise TypeError("db_postprocess expects a CUDA float32 [N,H,W] tensor")
+    p = pred.contiguous()
+    n, h, w = p.shape
+    hw = np.ascontiguousarray(np.asarray(src_hw, dtype=np.int32).reshape(n, 2))
+    boxes = torch.empty((n, max_candidates, 4, 2), dtype=torch.int32, device=p.device)
+    scores = torch.empty((n, max_candidates), dtype=torch.float32, device=p.device)
+    counts = torch.empty(n, dtype=torch.int32, device=p.device)
+    wsb = int(_L().lumina_db_workspace_bytes(n, h, w, int(max_candidates)))
+    ws = _ws(wsb, p.device)
+    _chk(_L().lumina_db_postprocess(_ptr(p), n, h, w, float(np.float32(thresh)), float(box_thresh), float(unclip_ratio),
+                                    int(max_candidates), int(min_size), hw.ctypes.data_as(C.c_void_p), _ptr(boxes),
+                                    _ptr(scores), _ptr(counts), _ptr(ws), wsb, _stream()))
+    return boxes, scores, counts

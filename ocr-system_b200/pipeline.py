@@ -1,0 +1,160 @@
+"""Batched page chain + page-range sharding.
+
+``PagePipeline`` is the throughput API behind the drop-in ``ImagePreprocessor``:
+one call processes a batch of equally sized page rasters that are either already
+resident in HBM (``run_device``) or in pinned host memory (``run_host``: H2D of
+the rasters, kernels, D2H of the results a caller consumes).  It is the batch axis
+the reference iterates one page at a time (services/ocr_service.py:604-660 under
+``Semaphore(1)`` :157,404).
+
+Stages (BASELINE.json configs[1]: gray / resize / normalize / binarize / deskew):
+  a3  resize_if_needed -> PIL Lanczos to ``max_dimension``
+  a10 deskew           -> cv gray + Canny + HoughLinesP + median angle + bicubic warp
+  [a5+a6 contrast 1.2 + sharpness 1.1 when ``enhance=True`` (reference default chain)]
+  a4  PIL gray, a9 adaptive Gaussian threshold, a15 det resize+normalize (CHW f32)
+
+Pages are independent, so multi-GPU is plain page-range sharding with no
+collective on the data path (``shard_range``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def shard_range(n_pages: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous page range of ``rank``: [r*ceil(N/G), min(N, (r+1)*ceil(N/G)))  (SURVEY 8e)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    per = -(-n_pages // world_size)
+    lo = min(n_pages, rank * per)
+    return lo, min(n_pages, lo + per)
+
+
+class _StageTimer:
+    """CUDA-event brackets around each stage on the launching stream (only when profiling)."""
+
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+        self.marks: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
+
+    def run(self, name, fn):
+        if not self.enabled:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self.marks.append((name, a, b))
+        return r
+
+    def collect(self) -> Dict[str, float]:
+        out: Dict[str, float] = {}
+        for name, a, b in self.marks:
+            b.synchronize()
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+@dataclass
+class PageBatchResult:
+    pages: torch.Tensor          # [N,h,w,3] u8 deskewed (and enhanced) rasters
+    angles: np.ndarray           # [N] float64 deskew angles (reference semantics)
+    gray: torch.Tensor           # [N,h,w] u8 PIL-L of `pages`
+    binary: torch.Tensor         # [N,h,w] u8 {0,255} adaptive threshold
+    det_input: torch.Tensor      # [N,3,oh,ow] f32 normalised CHW detector input
+    shape_list: np.ndarray       # [N,4] (src_h, src_w, ratio_h, ratio_w)
+    timer: Optional["_StageTimer"] = None
+
+    @property
+    def stage_ms(self) -> Dict[str, float]:
+        """Per-stage device milliseconds (CUDA events on the launch stream); synchronises."""
+        return self.timer.collect() if self.timer is not None else {}
+
+
+class PagePipeline:
+    def __init__(self, max_dimension: int = 960, deskew: bool = True, enhance: bool = False,
+                 det_limit_side_len: int = 960, device: Optional[torch.device] = None):
+        self.max_dimension = int(max_dimension)
+        self.deskew = deskew
+        self.enhance = enhance
+        self.det_limit = int(det_limit_side_len)
+        self.device = device
+
+    # ------------------------------------------------------------------ resident input
+    def run_device(self, pages: torch.Tensor, profile: bool = False) -> PageBatchResult:
+        """pages: CUDA uint8 [N,H,W,3], resident in HBM."""
+        if not pages.is_cuda:
+            raise TypeError("run_device needs a CUDA tensor (use run_host for host buffers)")
+        t = _StageTimer(profile)
+        x = t.run("resize_lanczos", lambda: ops.resize_if_needed(pages, self.max_dimension))
+        n = x.shape[0]
+        angles = np.zeros(n, np.float64)
+        if self.deskew:
+            edges = t.run("canny", lambda: ops.canny(x, 50, 150))
+            lines, nlines = t.run("ppht", lambda: ops.hough_lines_p(edges))
+            x, angles = t.run("angle+warp", lambda: self._rotate(x, lines, nlines))
+        if self.enhance:
+            x = t.run("contrast+sharpness", lambda: ops.contrast_sharpness(x, 1.2, 1.1))
+        gray = t.run("gray_pil", lambda: ops.gray_pil(x))
+        binary = t.run("adaptive_binarize", lambda: ops.adaptive_binarize(gray, 2))
+        det, shape_list = t.run("det_resize_normalize", lambda: ops.det_resize_normalize(x, self.det_limit))
+        return PageBatchResult(x, angles, gray, binary, det, shape_list, t)
+
+    @staticmethod
+    def _rotate(x: torch.Tensor, lines: torch.Tensor, nlines: torch.Tensor):
+        """Host median / gating (image_preprocessing.py:414-439) + one warp launch.  The only
+        host synchronisation of the chain: the line lists (a few KB per page) come back."""
+        n, h, w = x.shape[0], x.shape[1], x.shape[2]
+        nl = nlines.cpu().numpy()
+        keep = int(nl.max(initial=0))
+        if keep > lines.shape[1]:  # truncated list: redo the Hough stage with room for every line
+            edges = ops.canny(x, 50, 150)
+            lines, nlines = ops.hough_lines_p(edges, max_lines=keep)
+            nl = nlines.cpu().numpy()
+        lh = lines[:, : max(keep, 1)].cpu().numpy()
+        angles = np.zeros(n, np.float64)
+        mats = np.zeros((n, 6), np.float64)
+        apply = np.zeros(n, np.uint8)
+        for i in range(n):
+            if nl[i] == 0:
+                continue
+            a = ops.median_angle(lh[i, : nl[i]])
+            if abs(a) < 0.5:
+                angles[i] = a
+            elif abs(a) <= 45:
+                angles[i] = a
+                mats[i] = ops.rotation_matrix(w // 2, h // 2, a).reshape(6)
+                apply[i] = 1
+        if apply.any():
+            x = ops.warp_affine_cubic(x, mats, apply)
+        return x, angles
+
+    # ------------------------------------------------------------------ host input (the e2e path)
+    def run_host(self, pages_host: torch.Tensor, out_host: Optional[Dict[str, torch.Tensor]] = None,
+                 profile: bool = False):
+        """pages_host: (pinned) CPU uint8 [N,H,W,3].  Copies the rasters to the device, runs the
+        chain and copies back what a caller consumes: deskewed rasters, binary masks and angles.
+        Returns (out_host dict, PageBatchResult, h2d_bytes, d2h_bytes)."""
+        if pages_host.is_cuda:
+            raise TypeError("run_host needs a host tensor")
+        dev = self.device or torch.device("cuda", torch.cuda.current_device())
+        x = pages_host.to(dev, non_blocking=True)
+        res = self.run_device(x, profile=profile)
+        if out_host is None:
+            out_host = {
+                "pages": torch.empty(res.pages.shape, dtype=torch.uint8, pin_memory=True),
+                "binary": torch.empty(res.binary.shape, dtype=torch.uint8, pin_memory=True),
+            }
+        out_host["pages"].copy_(res.pages, non_blocking=True)
+        out_host["binary"].copy_(res.binary, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out_host["angles"] = res.angles
+        h2d = pages_host.numel()
+        d2h = res.pages.numel() + res.binary.numel() + res.angles.nbytes
+        return out_host, res, h2d, d2h
