@@ -196,23 +196,24 @@ def main_ours(args):
     sampler = ClockSampler(_physical_index(local))
     sampler.start()
     launches0 = ops.launch_count()
-    results = []
+    timers = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(K):
-        results.append(pipe.run_device(pages, profile=True))
+        r = pipe.run_device(pages, profile=True)   # stage brackets = CUDA events on the launch stream
+        timers.append(r.timer)
+        angles = r.angles
+        del r                                      # outputs are released every step (no growing pool)
     e1.record()
     barrier()
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ops.launch_count() - launches0
     clocks = sampler.stop()
     stage_ms = {}
-    for r in results:
-        for k, v in r.stage_ms.items():
+    for t in timers:
+        for k, v in t.collect().items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / K
-    angles = results[-1].angles
-    del results
 
     # ---- e2e: pinned host rasters -> HBM -> chain -> host results ------------------
     host_in = torch.empty(pages.shape, dtype=torch.uint8, pin_memory=True)
@@ -269,7 +270,7 @@ def main_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = args.cpu_sample or 2 * (os.cpu_count() or 1)
-            rate, dt, cores = cpu_reference_rate(sample, args.max_dim)
+            rate, dt, cores = cpu_reference_rate(sample, args.max_dim, steps=3, warmup=1)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{sample} synthetic A4 pages ({dt:.1f} s), one page per task on "

@@ -1,0 +1,124 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/lumina_b200.h
+declares (no compute calls), host-only entry points agree with the oracle / reference rules,
+the product path never touches oracle/, and the drop-in keeps the reference's error behaviour."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def abi():
+    import __graft_entry__ as g
+
+    g._load_build_module().build()
+    from ocr_system_b200 import _abi
+
+    return _abi
+
+
+def test_library_exports_every_declared_symbol(abi):
+    hdr = open(os.path.join(ROOT, "include", "lumina_b200.h")).read()
+    declared = set(re.findall(r"\b(lumina_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = C.CDLL(abi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/lumina_b200.h but not exported"
+    assert declared == set(abi.PROTOTYPES), declared ^ set(abi.PROTOTYPES)
+    assert abi.lib().lumina_abi_version() == 1
+
+
+def test_target_size_matches_reference_rule(abi, oracle):
+    from ocr_system_b200 import ops
+
+    for (w, h, md) in [(2480, 3508, 2000), (2480, 3508, 960), (3508, 2480, 960), (1000, 1000, 2000), (4000, 3000, 2000),
+                       (2001, 17, 2000), (333, 5000, 1234)]:
+        assert ops.target_size(w, h, md) == oracle.target_size(w, h, md)
+    assert ops.det_target_size(960, 678) == oracle.det_target_size(960, 678) == (960, 672)
+    assert ops.det_target_size(3508, 2480) == oracle.det_target_size(3508, 2480)
+
+
+def test_host_angle_and_rotation_match_oracle(abi, oracle):
+    from ocr_system_b200 import ops
+
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 200):
+        lines = rng.integers(0, 1500, (n, 4)).astype(np.int32)
+        assert ops.median_angle(lines) == oracle.median_angle(lines)
+    assert ops.median_angle(np.zeros((0, 4), np.int32)) == 0.0
+    for a in (0.5, -1.3, 44.0):
+        assert np.array_equal(ops.rotation_matrix(706, 1000, a), oracle.rotation_matrix(706, 1000, a))
+
+
+def test_errors_are_codes_not_crashes(abi):
+    lib = abi.lib()
+    rc = lib.lumina_rgb2gray_pil_u8(None, None, 16, None)  # null pointers: rejected before any launch
+    assert rc == -1
+    assert b"null" in lib.lumina_last_error_string()
+    with pytest.raises(abi.LuminaError):
+        abi.check(rc)
+    assert lib.lumina_ppht_workspace_bytes(0, 10, 10, 1.0, 0.01) == 0
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ocr-system_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+                assert "liblumina_oracle" not in src and "reference_port" not in src, f
+
+
+def test_no_cpu_fallback(abi):
+    import torch
+
+    from ocr_system_b200 import ops
+
+    with pytest.raises(TypeError):
+        ops.gray_pil(torch.zeros((1, 4, 4, 3), dtype=torch.uint8))  # CPU tensor: refused, never computed on host
+
+
+def test_dropin_surface_and_error_behaviour(abi, tmp_path):
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor, image_preprocessor
+
+    ip = ImagePreprocessor()
+    assert ip.max_dimension == 2000 and ip.target_dpi == 300      # config.py:69, image_preprocessing.py:45-51
+    for name in ("load_image", "load_image_bytes", "resize_if_needed", "get_optimal_size", "enhance_contrast",
+                 "enhance_sharpness", "denoise", "convert_to_grayscale", "auto_orient", "binarize", "optimize_for_ocr",
+                 "pdf_to_images", "get_pdf_page_count", "save_image", "image_to_bytes", "get_image_info", "deskew",
+                 "adaptive_binarize", "compress_for_azure", "preprocess_for_azure"):
+        assert callable(getattr(ip, name)) and callable(getattr(image_preprocessor, name))
+    with pytest.raises(FileNotFoundError):
+        ip.load_image(tmp_path / "missing.png")
+    assert ip.get_optimal_size(2480, 3508) == (1413, 2000)
+    assert ip.get_optimal_size(100, 100) == (100, 100)
+    from PIL import Image
+
+    small = Image.new("RGB", (64, 48), (10, 20, 30))
+    assert ip.resize_if_needed(small) is small                     # no resize needed -> same object, no GPU
+    png = ip.image_to_bytes(small, "PNG")
+    assert ip.load_image_bytes(png).size == (64, 48)
+    p = ip.save_image(small, tmp_path / "a" / "b.jpg")
+    assert p.exists() and ip.load_image(p).mode == "RGB"
+    info = ip.get_image_info(small)
+    assert info["needs_resize"] is False and info["size_optimal"] == (64, 48)
+    try:
+        import pdf2image  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            ip.pdf_to_images(tmp_path / "x.pdf")
+
+
+def test_ctc_dictionary_handling(abi, tmp_path):
+    from ocr_system_b200.paddle_ops import CTCLabelDecode
+
+    d = tmp_path / "dict.txt"
+    d.write_text("a\nb\nक\n", encoding="utf-8")
+    dec = CTCLabelDecode(str(d), use_space_char=True)
+    assert dec.character == ["blank", "a", "b", "क", " "]
+    assert len(CTCLabelDecode().character) == 37

@@ -1,0 +1,182 @@
+"""CPU unit tests of ocr-system_b200/csrc/db_geom.h (the geometry the DB kernels run per
+candidate), compiled for the host by tests/geom_host.cpp and compared with cv2:
+fillPoly coverage, minAreaRect (incl. cv2's tie-breaking on findContours borders and holes),
+get_mini_boxes, the Clipper offset restatement, and the whole per-candidate chain."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def G():
+    os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
+    so = os.path.join(HERE, "_build", "libgeom_host.so")
+    src = os.path.join(HERE, "geom_host.cpp")
+    hdr = os.path.join(HERE, "..", "ocr-system_b200", "csrc", "db_geom.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.geom_mini_box.restype = C.c_float
+    lib.geom_unclip_distance.restype = C.c_double
+    return lib
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_fillpoly_cover_matches_cv2(G):
+    rng = np.random.default_rng(1)
+    n = 0
+    for it in range(4000):
+        h, w = int(rng.integers(3, 60)), int(rng.integers(3, 90))
+        ww, hh = rng.uniform(0, w * 0.55), rng.uniform(0, h * 0.55)
+        if it % 4 == 0:
+            hh = rng.uniform(0, 2)
+        ang = rng.uniform(-90, 90) if it % 3 else 0.0
+        rect = cv2.boxPoints(((rng.uniform(0.3 * w, 0.7 * w), rng.uniform(0.3 * h, 0.7 * h)), (ww, hh), ang))
+        quad = np.ascontiguousarray(rect.astype(np.int32))
+        if not (quad[:, 0].min() >= 0 and quad[:, 0].max() < w and quad[:, 1].min() >= 0 and quad[:, 1].max() < h):
+            continue
+        ref = np.zeros((h, w), np.uint8)
+        cv2.fillPoly(ref, quad.reshape(1, -1, 2), 1)
+        got = np.zeros((h, w), np.uint8)
+        G.geom_fill_quad(P(quad), h, w, P(got))
+        assert np.array_equal(ref, got), quad.tolist()
+        n += 1
+    assert n > 2000
+
+
+def _random_mask(rng, h=120, w=160):
+    m = np.zeros((h, w), np.uint8)
+    for _ in range(int(rng.integers(3, 14))):
+        c = (int(rng.integers(10, w - 10)), int(rng.integers(10, h - 10)))
+        t = rng.integers(0, 3)
+        if t == 0:
+            cv2.ellipse(m, c, (int(rng.integers(1, 25)), int(rng.integers(1, 12))), float(rng.uniform(0, 180)), 0, 360, 1, -1)
+        elif t == 1:
+            r = cv2.boxPoints((c, (float(rng.uniform(1, 50)), float(rng.uniform(1, 16))), float(rng.uniform(-30, 30))))
+            cv2.fillPoly(m, [r.astype(np.int32)], 1)
+        else:
+            cv2.fillPoly(m, [(rng.integers(-15, 15, (3, 2)) + np.array(c)).astype(np.int32)], 1)
+    for _ in range(int(rng.integers(0, 6))):
+        c = (int(rng.integers(10, w - 10)), int(rng.integers(10, h - 10)))
+        cv2.ellipse(m, c, (int(rng.integers(1, 6)), int(rng.integers(1, 4))), float(rng.uniform(0, 180)), 0, 360, 0, -1)
+    return m
+
+
+def test_min_area_rect_matches_cv2_on_contours_and_holes(G):
+    """Component pixel set -> row extremes -> hull -> calipers == cv2.minAreaRect(contour), including
+    which of several equal-area rectangles cv2 returns (hull start convention)."""
+    rng = np.random.default_rng(3)
+    seen = {0: 0, 1: 0}
+    for _ in range(60):
+        m = _random_mask(rng)
+        h, w = m.shape
+        cs, hier = cv2.findContours(m * 255, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_SIMPLE)
+        if hier is None:
+            continue
+        _, labf = cv2.connectedComponents(m, connectivity=8)
+        _, labb = cv2.connectedComponents(1 - m, connectivity=4)
+        border = set(np.unique(np.concatenate([labb[0], labb[-1], labb[:, 0], labb[:, -1]])).tolist())
+        for ci, c in enumerate(cs):
+            hole = hier[0][ci][3] != -1
+            x0, y0 = c[0, 0]
+            if not hole:
+                ys, xs = np.nonzero(labf == labf[y0, x0])
+                mode, sx, sy = 1, 0, 0
+            else:
+                cand = None
+                for (px, py) in c[:, 0, :]:
+                    nb = {int(labb[py + dy, px + dx]) for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1))
+                          if 0 <= py + dy < h and 0 <= px + dx < w and m[py + dy, px + dx] == 0}
+                    cand = nb if cand is None else cand & nb
+                cand -= border
+                if len(cand) != 1:
+                    continue
+                hm = labb == cand.pop()
+                adj = np.zeros_like(hm)
+                adj[1:] |= hm[:-1]; adj[:-1] |= hm[1:]; adj[:, 1:] |= hm[:, :-1]; adj[:, :-1] |= hm[:, 1:]
+                ys, xs = np.nonzero(adj & (m > 0))
+                hy, hx = np.argwhere(hm)[0]
+                mode, sx, sy = 2, int(hx) - 1, int(hy)
+            pts = np.ascontiguousarray(np.stack([xs, ys], 1).astype(np.int32))
+            ref = cv2.minAreaRect(c)
+            out = np.zeros(5, np.float32)
+            G.geom_min_area_rect_ex(P(pts), len(pts), mode, sx, sy, P(out))
+            rb = cv2.boxPoints(ref)
+            ob = cv2.boxPoints(((float(out[0]), float(out[1])), (float(out[2]), float(out[3])), float(out[4])))
+            dm = np.abs(rb[:, None, :] - ob[None, :, :]).max(2)
+            assert max(dm.min(1).max(), dm.min(0).max()) < 1e-3, (ref, out.tolist())
+            seen[int(hole)] += 1
+    assert seen[0] > 200 and seen[1] > 10
+
+
+def test_clipper_offset_matches_oracle_restatement(G):
+    from oracle import db_post as D
+
+    rng = np.random.default_rng(2)
+    for _ in range(500):
+        rect = cv2.boxPoints(((rng.uniform(50, 900), rng.uniform(50, 900)), (rng.uniform(3, 300), rng.uniform(3, 60)),
+                              rng.uniform(-90, 90)))
+        box, _ = D.get_mini_boxes(rect.reshape(-1, 1, 2))
+        box = np.ascontiguousarray(np.array(box, np.float32))
+        ratio = float(rng.choice([1.5, 1.6, 2.0]))
+        dist = G.geom_unclip_distance(P(box), C.c_double(ratio))
+        ref = D.clipper_offset_round([(float(p[0]), float(p[1])) for p in box], dist)
+        o = np.zeros((512, 2), np.int32)
+        m = G.geom_clipper_offset(P(box), C.c_double(dist), P(o), 512)
+        assert m == len(ref) and np.array_equal(o[:m], np.array(ref, np.int32).reshape(-1, 2))
+        ex = D.unclip(box, ratio)
+        assert ex is not None and len(ex) == m
+
+
+def test_candidate_chain_matches_oracle(G):
+    """pixel set -> final int32 box + score, vs the cv2-based upstream restatement, per contour."""
+    from oracle import db_post as D
+
+    pred = D.synth_prob_map(480, 640, 7, n_boxes=150)
+    h, w = pred.shape
+    mask = (pred > np.float32(0.3)).astype(np.uint8)
+    cs, hier = cv2.findContours(mask * 255, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_SIMPLE)
+    _, labf = cv2.connectedComponents(mask, connectivity=8)
+    tot = bad = 0
+    for ci, c in enumerate(cs):
+        if hier[0][ci][3] != -1:
+            continue
+        x0, y0 = c[0, 0]
+        ys, xs = np.nonzero(labf == labf[y0, x0])
+        pts = np.ascontiguousarray(np.stack([xs, ys], 1).astype(np.int32))
+        # upstream steps for THIS contour (boxes_from_bitmap's loop body)
+        boxes, scores = [], []
+        points, sside = D.get_mini_boxes(c)
+        if sside >= 3:
+            points = np.array(points)
+            score = D.box_score_fast(pred, points.reshape(-1, 2))
+            if not (0.6 > score):
+                ex = D.unclip(points, 1.5)
+                if ex is not None:
+                    box, ss = D.get_mini_boxes(ex.reshape(-1, 1, 2))
+                    if ss >= 5:
+                        box = np.array(box)
+                        box[:, 0] = np.clip(np.round(box[:, 0] / w * np.float64(w)), 0, w)
+                        box[:, 1] = np.clip(np.round(box[:, 1] / h * np.float64(h)), 0, h)
+                        boxes.append(box.astype("int32")); scores.append(score)
+        out8 = np.zeros(8, np.int32); sc = C.c_double(); b8 = np.zeros(8, np.float32); why = C.c_int()
+        ok = G.geom_candidate(P(pts), len(pts), 0, 0, 0, P(np.ascontiguousarray(pred)), h, w, C.c_double(0.6),
+                              C.c_double(1.5), 3, C.c_double(w), C.c_double(h), P(out8), C.byref(sc), P(b8), C.byref(why))
+        tot += 1
+        assert ok == (len(boxes) == 1), (ci, ok, len(boxes), why.value)
+        if ok:
+            assert abs(sc.value - scores[0]) <= 1e-6
+            a = np.sort(boxes[0].reshape(-1, 2), axis=0); b = np.sort(out8.reshape(-1, 2), axis=0)
+            d = np.abs(a - b).max()
+            assert d <= 1
+            bad += int(d != 0)
+    assert tot > 100 and bad <= max(1, tot // 100)
