@@ -20,6 +20,7 @@
 //                         keeps up to one warp per page in flight.
 // This stage is latency-bound (dependent L2 round trips), not bandwidth-bound.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -28,7 +29,8 @@
 namespace lumina {
 
 struct PphtLayout {
-    size_t acc_off, mask_off, nz_off, order_off, count_off, trig_off, step_off, stats_off, total;
+    size_t acc_off, mask_off, nz_off, order_off, count_off, trig_off, step_off, stats_off, rholo_off, celloff_off, evbuf_off, total;
+    size_t evbuf_words;
     size_t acc_words_per_page;  // uint32 words (2 counters per word)
     int numangle, numrho;
 };
@@ -50,7 +52,11 @@ static PphtLayout ppht_layout(int n, int h, int w, double rho_d, double theta_d)
     L.count_off = off; off = align256(off + (size_t)n * 4);
     L.trig_off = off; off = align256(off + (size_t)L.numangle * 2 * 4);
     L.step_off = off; off = align256(off + (size_t)L.numangle * 3 * 4);
-    L.stats_off = off; off = align256(off + (size_t)n * 8 * 4);  // per page: N, votes, events, good, walk windows
+    L.stats_off = off; off = align256(off + (size_t)n * 8 * 4 + (size_t)n * 10 * 8);  // per page: N, votes, events, good, walk windows
+    L.rholo_off = off; off = align256(off + (size_t)L.numangle * 4);
+    L.celloff_off = off; off = align256(off + (size_t)L.numangle * 4);
+    L.evbuf_words = (size_t)(w > h ? w : h) * 2 + 64;  // a line walk visits at most max(w,h) pixels per direction
+    L.evbuf_off = off; off = align256(off + (size_t)n * L.evbuf_words * 4);
     L.total = off;
     return L;
 }
@@ -225,10 +231,116 @@ __device__ __forceinline__ void ppht_unvote(uint32_t *acc, const float *tc, cons
 
 constexpr int PPHT_MAXWIN = 256;   // 32-position windows per direction (covers 8192-pixel walks)
 constexpr int PPHT_BIAS = 0x4040;  // every accumulator byte is memset to 0x40
+constexpr int PPHT_WARPS = 16;      // points of the visiting order in flight per page
 
+// One line event (hough.cpp: walk both ways from the point along theta = max_n, decide good /
+// not good, clear the mask along the segment, un-vote when good, emit the line).  Runs on ONE
+// warp: 32 walk positions per step, ballots find the stop position, RED un-votes.
 template <int NPER>
-__global__ void __launch_bounds__(32) ppht_main_kernel(const PphtParams p) {
-    const int page = blockIdx.x, lane = threadIdx.x;
+__device__ __forceinline__ void ppht_line_event(const PphtParams &p, uint32_t *acc, uint8_t *mask, int32_t *lines,
+                                                const float *tc, const float *ts, uint32_t (*setbits)[PPHT_MAXWIN], int lane,
+                                                int j, int i, int max_n, int &nl, int &n_win) {
+    const int shift = 16;
+    const int xflag = p.step[max_n * 3], dx0 = p.step[max_n * 3 + 1], dy0 = p.step[max_n * 3 + 2];
+    int x0 = j, y0 = i;
+    if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
+    else x0 = (x0 << shift) + (1 << (shift - 1));
+    int endk[2], ex[2], ey[2];
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
+        int gap = 0, ek = 0;  // position 0 is the (set) start point in walk 1
+        int base = 0, win = 0;
+        for (;; base += 32, win++) {
+            n_win++;
+            const int kp = base + lane;
+            const int X = x0 + kp * dx, Y = y0 + kp * dy;
+            const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+            const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
+            const bool st = inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0;
+            const unsigned bset = __ballot_sync(0xffffffffu, st);
+            if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset;
+            // gap seen by this lane if it is unset: distance to the last set position
+            const unsigned below = bset & ((2u << lane) - 1u);  // bits <= lane
+            const int gk = below ? lane - (31 - __clz(below)) : gap + lane + 1;
+            const bool brk = !inb || (!st && gk > p.line_gap);
+            const unsigned bbrk = __ballot_sync(0xffffffffu, brk);
+            if (bbrk) {
+                const int fb = __ffs(bbrk) - 1;
+                const unsigned sb = fb ? (bset & ((1u << fb) - 1u)) : 0u;
+                if (sb) ek = base + 31 - __clz(sb);
+                break;
+            }
+            if (bset) { ek = base + 31 - __clz(bset); gap = __clz(bset); }
+            else gap += 32;
+        }
+        endk[d] = ek;
+        const int X = x0 + ek * dx, Y = y0 + ek * dy;
+        ex[d] = xflag ? X : (X >> shift);
+        ey[d] = xflag ? (Y >> shift) : Y;
+    }
+    const bool good = abs(ex[1] - ex[0]) >= p.line_length || abs(ey[1] - ey[0]) >= p.line_length;
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
+        for (int base = 0, win = 0; base <= endk[d]; base += 32, win++) {
+            unsigned bset;
+            if (win < PPHT_MAXWIN) bset = setbits[d][win];
+            else {  // beyond the recorded windows (never for pages < 8192 px): re-read
+                const int kp = base + lane;
+                const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
+                bset = __ballot_sync(0xffffffffu, inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0);
+            }
+            const int rem = endk[d] - base;  // positions base..endk
+            if (rem < 31) bset &= (2u << rem) - 1u;
+            if (d == 1 && base == 0) bset &= ~1u;  // start pixel already cleared by direction 0
+            if (bset & (1u << lane)) {
+                const int kp = base + lane;
+                const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                __stcg(mask + (size_t)i1 * p.w + j1, (uint8_t)0);
+            }
+            if (good) {
+                unsigned bb = bset;
+                while (bb) {
+                    const int b = __ffs(bb) - 1;
+                    bb &= bb - 1;
+                    const int kp = base + b;
+                    const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                    const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                    ppht_unvote<NPER>(acc, tc, ts, lane, p.numangle, p.numrho, j1, i1);
+                }
+            }
+        }
+    }
+    if (good) {
+        if (lane == 0 && nl < p.max_lines) {
+            lines[nl * 4 + 0] = ex[0]; lines[nl * 4 + 1] = ey[0];
+            lines[nl * 4 + 2] = ex[1]; lines[nl * 4 + 3] = ey[1];
+        }
+        nl++;
+    }
+}
+
+// Batched main loop: one CTA per page, NW warps = NW consecutive points of the visiting order in
+// flight.  Votes commute, so a batch is voted speculatively (every atomic of NW points in flight at
+// once: one L2 round trip per batch instead of one per point).  The atomics return the cell values in
+// an arbitrary order, but per cell the multiset of returned values equals the multiset of the values
+// the sequential loop would see; hence
+//   * if no returned value reaches the threshold, no point of the batch triggers a line: commit;
+//   * otherwise the exact sequential value of (point k, theta) is  min(returned values of the
+//     batch points hitting that cell) + #(batch points <= k hitting that cell), resolved through
+//     shared memory.  The first point k* whose exact maximum reaches the threshold runs its line
+//     event; points after k* take their votes back (RED -1) and are replayed in the next batch,
+//     because the event changes the mask / accumulator they must see.
+// The result is identical to the sequential algorithm (same lines, same order).
+template <int NPER, int NW>
+__global__ void __launch_bounds__(NW * 32) ppht_main_kernel(const PphtParams p) {
+    constexpr int ORD_CHUNK = 1024;
+    const int page = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int px = p.h * p.w;
     uint32_t *acc = p.acc + (size_t)page * p.acc_words_per_page;
     uint8_t *mask = p.mask + (size_t)page * px;
@@ -236,6 +348,12 @@ __global__ void __launch_bounds__(32) ppht_main_kernel(const PphtParams p) {
     int32_t *lines = p.lines + (size_t)page * p.max_lines * 4;
     const int N = p.count[page];
     __shared__ uint32_t setbits[2][PPHT_MAXWIN];
+    __shared__ uint32_t ordbuf[ORD_CHUNK];
+    __shared__ short rr[NW][NPER * 32];
+    __shared__ unsigned short oo[NW][NPER * 32];
+    __shared__ uint32_t wkey[NW];
+    __shared__ uint32_t wspec[2][NW];  // double-buffered by batch parity: a warp is at most one batch ahead
+    __shared__ int s_nl, s_stats[4];
 
     float tc[NPER], ts[NPER];
 #pragma unroll
@@ -244,121 +362,124 @@ __global__ void __launch_bounds__(32) ppht_main_kernel(const PphtParams p) {
         tc[q] = n < p.numangle ? p.trig[n * 2] : 0.f;
         ts[q] = n < p.numangle ? p.trig[n * 2 + 1] : 0.f;
     }
-    int nl = 0, n_votes = 0, n_events = 0, n_win = 0;
-    const int shift = 16;
-    for (int i0 = 0; i0 < N; i0 += 32) {
-        const int nb = min(32, N - i0);
-        uint32_t pt = lane < nb ? __ldcg(order + i0 + lane) : 0u;
-        uint32_t mk = lane < nb ? (uint32_t)__ldcg(mask + (size_t)(pt >> 16) * p.w + (pt & 0xffffu)) : 0u;
-        for (int k = 0; k < nb; k++) {
-            const uint32_t m = __shfl_sync(0xffffffffu, mk, k);
-            if (!m) continue;
-            const uint32_t pk = __shfl_sync(0xffffffffu, pt, k);
-            const int j = (int)(pk & 0xffffu), i = (int)(pk >> 16);
-            n_votes++;
-            const uint32_t mykey = ppht_vote<NPER>(acc, tc, ts, lane, p.numangle, p.numrho, j, i);
-            const uint32_t key = __reduce_max_sync(0xffffffffu, mykey);
-            const int max_val = (int)(key >> 16) - PPHT_BIAS;
-            if (max_val < p.threshold) continue;
-            const int max_n = 65535 - (int)(key & 0xffffu);
-            // ---- line event ----
-            n_events++;
-            const int xflag = p.step[max_n * 3], dx0 = p.step[max_n * 3 + 1], dy0 = p.step[max_n * 3 + 2];
-            int x0 = j, y0 = i;
-            if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
-            else x0 = (x0 << shift) + (1 << (shift - 1));
-            int endk[2], ex[2], ey[2];
+    if (threadIdx.x == 0) { s_nl = 0; s_stats[0] = s_stats[1] = s_stats[2] = s_stats[3] = 0; }
+    int pos = 0, buf_lo = 0, buf_hi = 0;
+    int n_votes = 0, n_events = 0, n_win = 0, n_batches = 0;
+    __syncthreads();
+    while (pos < N) {
+        if (pos + NW > buf_hi && buf_hi < N) {  // refill the visiting-order window (uniform branch)
+            __syncthreads();
+            buf_lo = pos;
+            buf_hi = min(N, pos + ORD_CHUNK);
+            for (int t = threadIdx.x; t < buf_hi - buf_lo; t += NW * 32) ordbuf[t] = __ldcg(order + buf_lo + t);
+            __syncthreads();
+        }
+        n_batches++;
+        const int e = pos + w;
+        const bool live = e < N;
+        const uint32_t pt = live ? ordbuf[e - buf_lo] : 0u;
+        const int j = (int)(pt & 0xffffu), i = (int)(pt >> 16);
+        const bool m = live && __ldcg(mask + (size_t)i * p.w + j) != 0;
+        // ---- speculative vote ----
+        int rq[NPER];
+        uint32_t oq[NPER];
+        uint32_t spec = 0;
+        if (m) {
+            const float fx = (float)j, fy = (float)i;
+            int half[NPER];
 #pragma unroll
-            for (int d = 0; d < 2; d++) {
-                const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
-                int gap = 0, ek = 0;  // position 0 is the (set) start point in walk 1
-                int base = 0, win = 0;
-                for (;; base += 32, win++) {
-                    n_win++;
-                    const int kp = base + lane;
-                    const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                    const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                    const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
-                    const bool st = inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0;
-                    const unsigned bset = __ballot_sync(0xffffffffu, st);
-                    if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset;
-                    // gap seen by this lane if it is unset: distance to the last set position
-                    const unsigned below = bset & ((2u << lane) - 1u);  // bits <= lane
-                    const int gk = below ? lane - (31 - __clz(below)) : gap + lane + 1;
-                    const bool brk = !inb || (!st && gk > p.line_gap);
-                    const unsigned bbrk = __ballot_sync(0xffffffffu, brk);
-                    if (bbrk) {
-                        const int fb = __ffs(bbrk) - 1;
-                        const unsigned sb = fb ? (bset & ((1u << fb) - 1u)) : 0u;
-                        if (sb) ek = base + 31 - __clz(sb);
-                        break;
-                    }
-                    if (bset) { ek = base + 31 - __clz(bset); gap = __clz(bset); }
-                    else gap += 32;
+            for (int q = 0; q < NPER; q++) {
+                const int n = lane + 32 * q;
+                if (n < p.numangle) {
+                    rq[q] = cvround_f(__fadd_rn(__fmul_rn(fx, tc[q]), __fmul_rn(fy, ts[q]))) + (p.numrho - 1) / 2;
+                    const size_t cell = (size_t)n * p.numrho + rq[q];
+                    half[q] = (int)(cell & 1);
+                    oq[q] = atomicAdd(acc + (cell >> 1), half[q] ? 0x10000u : 1u);
                 }
-                endk[d] = ek;
-                const int X = x0 + ek * dx, Y = y0 + ek * dy;
-                ex[d] = xflag ? X : (X >> shift);
-                ey[d] = xflag ? (Y >> shift) : Y;
             }
-            const bool good = abs(ex[1] - ex[0]) >= p.line_length || abs(ey[1] - ey[0]) >= p.line_length;
-            __syncwarp();
 #pragma unroll
-            for (int d = 0; d < 2; d++) {
-                const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
-                for (int base = 0, win = 0; base <= endk[d]; base += 32, win++) {
-                    unsigned bset;
-                    if (win < PPHT_MAXWIN) bset = setbits[d][win];
-                    else {  // beyond the recorded windows (never for pages < 8192 px): re-read
-                        const int kp = base + lane;
-                        const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                        const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
-                        bset = __ballot_sync(0xffffffffu, inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0);
-                    }
-                    const int rem = endk[d] - base;  // positions base..endk
-                    if (rem < 31) bset &= (2u << rem) - 1u;
-                    if (d == 1 && base == 0) bset &= ~1u;  // start pixel already cleared by direction 0
-                    // clear the mask
-                    if (bset & (1u << lane)) {
-                        const int kp = base + lane;
-                        const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                        __stcg(mask + (size_t)i1 * p.w + j1, (uint8_t)0);
-                    }
-                    if (good) {
-                        unsigned bb = bset;
-                        while (bb) {
-                            const int b = __ffs(bb) - 1;
-                            bb &= bb - 1;
-                            const int kp = base + b;
-                            const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                            const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                            ppht_unvote<NPER>(acc, tc, ts, lane, p.numangle, p.numrho, j1, i1);
+            for (int q = 0; q < NPER; q++) {
+                const int n = lane + 32 * q;
+                if (n < p.numangle) {
+                    oq[q] = half[q] ? (oq[q] >> 16) : (oq[q] & 0xffffu);
+                    rr[w][n] = (short)rq[q];
+                    oo[w][n] = (unsigned short)oq[q];
+                    spec = max(spec, oq[q] + 1u);
+                }
+            }
+            n_votes++;
+        } else {
+#pragma unroll
+            for (int q = 0; q < NPER; q++) rr[w][lane + 32 * q] = (short)-1;
+        }
+        spec = __reduce_max_sync(0xffffffffu, spec);
+        if (lane == 0) wspec[n_batches & 1][w] = spec;
+        __syncthreads();  // (A) every vote of the batch has been performed; rr/oo/wspec visible
+        {
+            const uint32_t v = lane < NW ? wspec[n_batches & 1][lane] : 0u;
+            const bool any_hit = __any_sync(0xffffffffu, (int)v - PPHT_BIAS >= p.threshold);
+            if (!any_hit) {  // nothing in this batch can trigger: commit all votes (one barrier per batch)
+                pos += NW;
+                continue;
+            }
+        }
+        // ---- exact sequential values of this warp's point ----
+        uint32_t key = 0;
+        if (m) {
+#pragma unroll
+            for (int q = 0; q < NPER; q++) {
+                const int n = lane + 32 * q;
+                if (n < p.numangle) {
+                    uint32_t base = oq[q], rank = 1;
+                    const short r = (short)rq[q];
+                    for (int k = 0; k < NW; k++) {
+                        if (k == w) continue;
+                        if (rr[k][n] == r) {
+                            base = min(base, (uint32_t)oo[k][n]);
+                            rank += (k < w) ? 1u : 0u;
                         }
                     }
+                    key = max(key, ((base + rank) << 16) | (uint32_t)(65535 - n));
                 }
             }
-            if (good) {
-                if (lane == 0 && nl < p.max_lines) {
-                    lines[nl * 4 + 0] = ex[0]; lines[nl * 4 + 1] = ey[0];
-                    lines[nl * 4 + 2] = ex[1]; lines[nl * 4 + 3] = ey[1];
-                }
-                nl++;
-            }
-            // the mask changed: refresh the not-yet-visited points of this chunk
-            __syncwarp();
-            if (lane > k && lane < nb) mk = (uint32_t)__ldcg(mask + (size_t)(pt >> 16) * p.w + (pt & 0xffffu));
         }
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0) wkey[w] = key;
+        __syncthreads();  // (B) exact keys visible
+        int ks;
+        {
+            const uint32_t v = lane < NW ? wkey[lane] : 0u;
+            const unsigned hits = __ballot_sync(0xffffffffu, v != 0u && (int)(v >> 16) - PPHT_BIAS >= p.threshold);
+            ks = hits ? __ffs(hits) - 1 : NW;  // the multiset bound is not tight per point: may be none
+        }
+        if (ks < NW) {
+            if (w > ks && m) ppht_unvote<NPER>(acc, tc, ts, lane, p.numangle, p.numrho, j, i);  // replayed next batch
+            if (w == ks) {
+                int nl = s_nl;
+                const int max_n = 65535 - (int)(wkey[ks] & 0xffffu);
+                ppht_line_event<NPER>(p, acc, mask, lines, tc, ts, setbits, lane, j, i, max_n, nl, n_win);
+                if (lane == 0) s_nl = nl;
+                n_events++;
+            }
+            pos += ks + 1;
+        } else {
+            pos += NW;
+        }
+        __syncthreads();  // (C) event stores / rollbacks ordered before the next batch
     }
-    if (lane == 0) {
-        p.nlines[page] = nl;
+    // statistics (per-thread counters: votes per warp, events on the event warps)
+    if (lane == 0) { atomicAdd(&s_stats[1], n_votes); atomicAdd(&s_stats[2], n_events); atomicAdd(&s_stats[3], n_win); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.nlines[page] = s_nl;
         int32_t *st = p.stats + page * 8;
-        st[0] = N; st[1] = n_votes; st[2] = n_events; st[3] = nl; st[4] = n_win;
+        st[0] = N; st[1] = s_stats[1]; st[2] = s_stats[2]; st[3] = s_nl; st[4] = s_stats[3]; st[5] = n_batches;
     }
 }
 
 }  // namespace lumina
+
+#include "k_ppht_cluster.cuh"
 
 using namespace lumina;
 
@@ -403,12 +524,136 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
     LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.trig_off, trig.data(), trig.size() * 4, cudaMemcpyHostToDevice, st));
     LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.step_off, step.data(), step.size() * 4, cudaMemcpyHostToDevice, st));
     // pageable-source async copies are staged before returning, so the vectors may die here
-    LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.acc_off, 0x40, (size_t)n * L.acc_words_per_page * 4, st));
 
     ppht_collect_kernel<<<n, 1024, 0, st>>>(d_edges, ws + L.mask_off, (uint32_t *)(ws + L.nz_off), (int *)(ws + L.count_off), h, w);
     LUMINA_KERNEL_CHECK("ppht_collect_kernel");
     ppht_order_kernel<<<n, 32, 0, st>>>((uint32_t *)(ws + L.nz_off), (uint32_t *)(ws + L.order_off), (const int *)(ws + L.count_off), h * w);
     LUMINA_KERNEL_CHECK("ppht_order_kernel");
+    // ---- shared-memory (cluster) path: per-theta rho range the page can reach ----
+    std::vector<int> rho_lo(L.numangle), cell_off(L.numangle), row_cells(L.numangle);
+    int cs = 0, theta_per_cta = 0, slice_cells = 0;
+    {
+        const int half = (L.numrho - 1) / 2;
+        std::vector<int> &cells = row_cells;
+        for (int a = 0; a < L.numangle; a++) {
+            int lo = 1 << 30, hi = -(1 << 30);
+            for (int c = 0; c < 4; c++) {
+                const float fx = (float)((c & 1) ? w - 1 : 0), fy = (float)((c & 2) ? h - 1 : 0);
+                const int r = (int)lrintf(fx * trig[a * 2] + fy * trig[a * 2 + 1]);
+                lo = r < lo ? r : lo; hi = r > hi ? r : hi;
+            }
+            lo -= 1; hi += 1;  // rounding slack
+            if (lo + half < 0) lo = -half;
+            if (hi + half > L.numrho - 1) hi = L.numrho - 1 - half;
+            rho_lo[a] = lo + half;
+            cells[a] = hi - lo + 1;
+        }
+        int max_optin = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, ppht_cluster_kernel) == cudaSuccess) {
+            const long long budget = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024;
+            for (int c = 1; c <= 8; c *= 2) {
+                const int T = (L.numangle + c - 1) / c;
+                if (T > PCL_THREADS) continue;
+                int worst = 0;
+                for (int r0 = 0; r0 < L.numangle; r0 += T) {
+                    int sum = 0;
+                    for (int a = r0; a < L.numangle && a < r0 + T; a++) { cell_off[a] = sum; sum += cells[a]; }
+                    worst = sum > worst ? sum : worst;
+                }
+                if ((long long)worst * 2 <= budget) { cs = c; theta_per_cta = T; slice_cells = worst; break; }
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
+    const char *force = getenv("LUMINA_PPHT");  // diagnostics: "l2" | "cluster" force a slower variant
+    // (1) local-mask cluster kernel: accumulator slice + the page's edge bitmask in each CTA's shared memory
+    if (!force) {
+        int max_optin = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel) == cudaSuccess) {
+            const long long mask_bytes = (((long long)h * w + 31) / 32) * 4;
+            const long long budget = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024 - mask_bytes;
+            for (int c = 1; c <= 8 && budget > 0; c++) {
+                const int T = (L.numangle + c - 1) / c;
+                if (T > PCL_THREADS) continue;
+                int worst = 0;
+                std::vector<int> offs(L.numangle);
+                for (int r0 = 0; r0 < L.numangle; r0 += T) {
+                    int sum = 0;
+                    for (int a = r0; a < L.numangle && a < r0 + T; a++) { offs[a] = sum; sum += row_cells[a]; }
+                    worst = sum > worst ? sum : worst;
+                }
+                if ((long long)worst * 2 + 16 <= budget) {
+                    LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.rholo_off, rho_lo.data(), rho_lo.size() * 4, cudaMemcpyHostToDevice, st));
+                    LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.celloff_off, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, st));
+                    PphtLmParams q;
+                    q.edges = d_edges; q.order = (const uint32_t *)(ws + L.order_off); q.count = (const int *)(ws + L.count_off);
+                    q.trig = (const float *)(ws + L.trig_off); q.step = (const int *)(ws + L.step_off);
+                    q.rho_lo = (const int *)(ws + L.rholo_off); q.cell_off = (const int *)(ws + L.celloff_off);
+                    q.lines = d_lines; q.nlines = d_nlines; q.stats = (int32_t *)(ws + L.stats_off);
+                    q.stats_ll = (long long *)(ws + L.stats_off + (((size_t)n * 8 * 4 + 7) & ~(size_t)7));
+                    q.h = h; q.w = w; q.numangle = L.numangle; q.numrho = L.numrho; q.theta_per_cta = T;
+                    q.slice_cells = worst; q.threshold = threshold; q.line_length = min_line_length;
+                    q.line_gap = max_line_gap; q.max_lines = max_lines;
+                    const size_t dyn = (((size_t)worst * 2 + 15) & ~(size_t)15) + (size_t)mask_bytes;
+                    LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)(n * c));
+                    cfg.blockDim = dim3(PCL_THREADS);
+                    cfg.dynamicSmemBytes = dyn;
+                    cfg.stream = st;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = 1;
+                    LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel, q));
+                    LUMINA_KERNEL_CHECK("ppht_cluster_lm_kernel");
+                    return LUMINA_OK;
+                }
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
+    // (2) cluster kernel with the mask in L2 (pages whose bitmask does not fit next to the accumulator)
+    if (cs > 0 && !(force && force[0] == 'l')) {
+        LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.rholo_off, rho_lo.data(), rho_lo.size() * 4, cudaMemcpyHostToDevice, st));
+        LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.celloff_off, cell_off.data(), cell_off.size() * 4, cudaMemcpyHostToDevice, st));
+        PphtClParams q;
+        q.mask = ws + L.mask_off; q.order = (const uint32_t *)(ws + L.order_off); q.count = (const int *)(ws + L.count_off);
+        q.trig = (const float *)(ws + L.trig_off); q.step = (const int *)(ws + L.step_off);
+        q.rho_lo = (const int *)(ws + L.rholo_off); q.cell_off = (const int *)(ws + L.celloff_off);
+        q.evbuf = (uint32_t *)(ws + L.evbuf_off); q.evbuf_words = (int)L.evbuf_words;
+        q.lines = d_lines; q.nlines = d_nlines; q.stats = (int32_t *)(ws + L.stats_off);
+        q.stats_ll = (long long *)(ws + L.stats_off + (((size_t)n * 8 * 4 + 7) & ~(size_t)7));
+        q.h = h; q.w = w; q.numangle = L.numangle; q.numrho = L.numrho; q.theta_per_cta = theta_per_cta;
+        q.slice_cells = slice_cells; q.threshold = threshold; q.line_length = min_line_length;
+        q.line_gap = max_line_gap; q.max_lines = max_lines;
+        const size_t dyn = (size_t)slice_cells * 2;
+        LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n * cs));
+        cfg.blockDim = dim3(PCL_THREADS);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_kernel, q));
+        LUMINA_KERNEL_CHECK("ppht_cluster_kernel");
+        return LUMINA_OK;
+    }
+    // ---- (3) fallback: accumulator in L2 (pages whose rows do not fit 8 CTAs of shared memory) ----
+    LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.acc_off, 0x40, (size_t)n * L.acc_words_per_page * 4, st));
     PphtParams p;
     p.acc = (uint32_t *)(ws + L.acc_off); p.mask = ws + L.mask_off;
     p.order = (const uint32_t *)(ws + L.order_off); p.count = (const int *)(ws + L.count_off);
@@ -416,7 +661,7 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
     p.lines = d_lines; p.nlines = d_nlines; p.stats = (int32_t *)(ws + L.stats_off); p.acc_words_per_page = L.acc_words_per_page;
     p.h = h; p.w = w; p.numangle = L.numangle; p.numrho = L.numrho;
     p.threshold = threshold; p.line_length = min_line_length; p.line_gap = max_line_gap; p.max_lines = max_lines;
-    ppht_main_kernel<6><<<n, 32, 0, st>>>(p);
+    ppht_main_kernel<6, PPHT_WARPS><<<n, PPHT_WARPS * 32, 0, st>>>(p);
     LUMINA_KERNEL_CHECK("ppht_main_kernel");
     return LUMINA_OK;
 }

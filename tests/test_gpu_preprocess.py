@@ -196,3 +196,37 @@ def test_ctc_greedy(oracle, cuda, n, t, c):
     ridx, rpos, rln, rconf = oracle.ctc_greedy(p)
     assert np.array_equal(ln, rln) and np.array_equal(idx, ridx) and np.array_equal(pos, rpos)
     assert np.max(np.abs(conf - rconf)) <= 1e-4
+
+
+@pytest.mark.parametrize("variant", ["l2", "cluster"])
+def test_ppht_fallback_variants_are_exact_too(oracle, cuda, variant, monkeypatch):
+    """The default HoughLinesP kernel keeps accumulator + edge bitmask in (distributed) shared memory;
+    larger pages fall back to a cluster kernel with the mask in L2, then to L2 atomics.  All three
+    must give cv2's exact line list."""
+    from ocr_system_b200 import ops
+
+    monkeypatch.setenv("LUMINA_PPHT", variant)
+    imgs = np.stack([_resized_page(oracle, s, 960) for s in (0, 3)])
+    edges_ref = [oracle.canny(oracle.gray_cv(im), 50, 150) for im in imgs]
+    lines, nlines = ops.hough_lines_p(_t(np.stack(edges_ref), cuda))
+    lines, nlines = lines.cpu().numpy(), nlines.cpu().numpy()
+    for i in range(2):
+        ref = oracle.ppht(edges_ref[i])
+        assert nlines[i] == len(ref) and np.array_equal(lines[i, : nlines[i]], ref)
+
+
+def test_ppht_degenerate_inputs(oracle, cuda):
+    from ocr_system_b200 import ops
+
+    h, w = 300, 420
+    empty = np.zeros((h, w), np.uint8)
+    one_line = empty.copy(); one_line[150, 30:400] = 255
+    cross = empty.copy(); cross[40:260, 210] = 255; cross[150, 20:400] = 255
+    full = np.full((64, 64), 255, np.uint8)
+    for e in (empty, one_line, cross):
+        lines, nl = ops.hough_lines_p(_t(e[None], cuda))
+        ref = oracle.ppht(e)
+        assert int(nl[0]) == len(ref) and np.array_equal(lines[0, : int(nl[0])].cpu().numpy(), ref)
+    lines, nl = ops.hough_lines_p(_t(full[None], cuda), threshold=20, min_line_length=10, max_line_gap=2)
+    ref = oracle.ppht(full, threshold=20, min_len=10, max_gap=2)
+    assert int(nl[0]) == len(ref) and np.array_equal(lines[0, : int(nl[0])].cpu().numpy(), ref)

@@ -49,7 +49,8 @@ print("first differing line idx", d[:5])
 if len(d):
     k = d[0]; print("gpu", g[max(0,k-1):k+3]); print("ref", ref[max(0,k-1):k+3])
 
-print("stats N,votes,events,good,windows:", wsn[stats_off:stats_off+32].view(np.int32))
+print("stats N,votes,events,good,windows,batches,CS:", wsn[stats_off:stats_off+32].view(np.int32))
+print("phase cycles fill,vote,reduce,sync1,rollback,walk,sync2,unvote,sync3,init:", wsn[stats_off+32:stats_off+32+80].view(np.int64))
 import time
 for nn in (1, 8, 64):
     xs_ = x.expand(nn, h, w).contiguous()
