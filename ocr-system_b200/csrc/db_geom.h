@@ -202,7 +202,10 @@ DBG_HD DbgRect dbg_min_area_rect(const DbgPt *hp, int n) {
     box.cy = py + (o1y + o2y) * 0.5f;
     box.w = (float)sqrt((double)o1x * o1x + (double)o1y * o1y);
     box.h = (float)sqrt((double)o2x * o2x + (double)o2y * o2y);
-    box.angle = (float)((double)(float)atan2((double)o1y, (double)o1x) * 180 / DBG_PI);
+    {
+        const float arad = (float)atan2((double)o1y, (double)o1x);
+        box.angle = (float)((double)(arad * 180.0f) / DBG_PI);  // cv: (float)(box.angle*180/CV_PI)
+    }
     return box;
 }
 

@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(256) resize_strip_kernel(const ResizeParams p)
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) {
                         const int bi = t * C + ch;
-                        acc[ch] += (int)byte_of(a[bi >> 2], bi & 3) * coef[t];
+                        // one PRMT per tap (byte -> zero-extended int) instead of SHF+LOP3: the kernel is ALU-pipe bound
+                        acc[ch] += (int)__byte_perm(a[bi >> 2], 0u, 0x4440u | (unsigned)(bi & 3)) * coef[t];
                     }
                 uint8_t *o = ring + (size_t)((r0 + r - ys) & (RING - 1)) * ROWB + (cg * 32 + lane) * C;
 #pragma unroll
@@ -206,10 +207,10 @@ __global__ void __launch_bounds__(256) resize_strip_kernel(const ResizeParams p)
                 const uint32_t w =
                     *reinterpret_cast<const uint32_t *>(ring + (size_t)((ymin + j - ys) & (RING - 1)) * ROWB + wj * 4);
                 const int kk = __ldg(k + j);
-                a0 += (int)byte_of(w, 0) * kk;
-                a1 += (int)byte_of(w, 1) * kk;
-                a2 += (int)byte_of(w, 2) * kk;
-                a3 += (int)byte_of(w, 3) * kk;
+                a0 += (int)__byte_perm(w, 0u, 0x4440u) * kk;
+                a1 += (int)__byte_perm(w, 0u, 0x4441u) * kk;
+                a2 += (int)__byte_perm(w, 0u, 0x4442u) * kk;
+                a3 += (int)__byte_perm(w, 0u, 0x4443u) * kk;
             }
             const int bcol = ox0 * C + wj * 4;  // byte column in the output row
             const int row_bytes = p.out_w * C;

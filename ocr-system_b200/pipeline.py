@@ -158,3 +158,52 @@ class PagePipeline:
         h2d = pages_host.numel()
         d2h = res.pages.numel() + res.binary.numel() + res.angles.nbytes
         return out_host, res, h2d, d2h
+
+    def run_host_stream(self, host_batches, profile: bool = False):
+        """Streaming form of ``run_host`` for a sequence of (pinned) host batches: the H2D copy of
+        batch i+1 is enqueued on a copy stream before batch i is processed, so raster upload overlaps
+        the kernels of the previous batch (double-buffered device input).  Yields
+        ``(out_host, PageBatchResult, h2d_bytes, d2h_bytes)`` per batch, results complete in host memory."""
+        dev = self.device or torch.device("cuda", torch.cuda.current_device())
+        comp = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(dev)
+        it = iter(host_batches)
+        slots = [None, None]
+
+        def issue(k, hb):
+            if hb.is_cuda:
+                raise TypeError("run_host_stream needs host tensors")
+            with torch.cuda.stream(copy_stream):
+                x = hb.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            slots[k] = (x, ev, hb)
+
+        cur_hb = next(it, None)
+        if cur_hb is None:
+            return
+        issue(0, cur_hb)
+        i = 0
+        out_host = None
+        while cur_hb is not None:
+            k = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                issue(k ^ 1, nxt)  # upload of the next batch overlaps this batch's kernels
+            x, ev, hb = slots[k]
+            comp.wait_event(ev)
+            x.record_stream(comp)
+            res = self.run_device(x, profile=profile)
+            if out_host is None or out_host["pages"].shape != res.pages.shape:
+                out_host = {
+                    "pages": torch.empty(res.pages.shape, dtype=torch.uint8, pin_memory=True),
+                    "binary": torch.empty(res.binary.shape, dtype=torch.uint8, pin_memory=True),
+                }
+            out_host["pages"].copy_(res.pages, non_blocking=True)
+            out_host["binary"].copy_(res.binary, non_blocking=True)
+            comp.synchronize()
+            out_host["angles"] = res.angles
+            slots[k] = None
+            yield out_host, res, hb.numel(), res.pages.numel() + res.binary.numel() + res.angles.nbytes
+            cur_hb = nxt
+            i += 1
