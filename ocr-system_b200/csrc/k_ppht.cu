@@ -55,8 +55,8 @@ static PphtLayout ppht_layout(int n, int h, int w, double rho_d, double theta_d)
     L.stats_off = off; off = align256(off + (size_t)n * 8 * 4 + (size_t)n * 10 * 8);  // per page: N, votes, events, good, walk windows
     L.rholo_off = off; off = align256(off + (size_t)L.numangle * 4);
     L.celloff_off = off; off = align256(off + (size_t)L.numangle * 4);
-    L.evbuf_words = (size_t)(w > h ? w : h) * 2 + 64;  // a line walk visits at most max(w,h) pixels per direction
-    L.evbuf_off = off; off = align256(off + (size_t)n * L.evbuf_words * 4);
+    L.evbuf_words = 0;
+    L.evbuf_off = off;
     L.total = off;
     return L;
 }
@@ -126,8 +126,9 @@ __global__ void __launch_bounds__(32) ppht_order_kernel(uint32_t *__restrict__ n
     unsigned long long state = ~0ull;
     int cnt = count[page];
     int i = 0;
-    while (cnt > 0) {
-        const int b = cnt < 32 ? cnt : 32;
+    // the 32 draws of a step; computed one step ahead so the MWC chain overlaps the L2 round trips
+    auto draw = [&](int c) -> int {
+        const int b = c < 32 ? c : 32;
         unsigned long long s = state;
         uint32_t my_r = 0;
         for (int k = 0; k < b; k++) {
@@ -135,33 +136,40 @@ __global__ void __launch_bounds__(32) ppht_order_kernel(uint32_t *__restrict__ n
             if (k == lane) my_r = (uint32_t)s;
         }
         state = s;
+        return lane < b ? (int)(my_r % (uint32_t)(c - lane)) : -1 - lane;
+    };
+    int idx = cnt > 0 ? draw(cnt) : 0;
+    while (cnt > 0) {
+        const int b = cnt < 32 ? cnt : 32;
         const bool act = lane < b;
         const int my_cnt = cnt - lane;
-        const int idx = act ? (int)(my_r % (uint32_t)my_cnt) : -1 - lane;
         const unsigned same = __match_any_sync(0xffffffffu, idx);
         const bool c1 = act && (same & ((1u << lane) - 1u)) != 0u;
         const bool c2 = act && idx >= cnt - b;
-        if (__any_sync(0xffffffffu, c1 || c2)) {
-            // exact sequential replay of this batch
+        const bool slow = __any_sync(0xffffffffu, c1 || c2);
+        uint32_t pt = 0, tl = 0;
+        if (!slow && act) { pt = __ldcg(nz + idx); tl = __ldcg(nz + (my_cnt - 1)); }  // in flight ...
+        const int idx_next = cnt - b > 0 ? draw(cnt - b) : 0;                        // ... while the next draws are computed
+        if (slow) {
+            // exact sequential replay of this step
             for (int k = 0; k < b; k++) {
                 const int ik = __shfl_sync(0xffffffffu, idx, k);
                 if (lane == 0) {
-                    const uint32_t pt = __ldcg(nz + ik);
-                    const uint32_t tl = __ldcg(nz + (cnt - k - 1));
-                    __stcg(nz + ik, tl);
-                    __stcg(order + i + k, pt);
+                    const uint32_t p1 = __ldcg(nz + ik);
+                    const uint32_t t1 = __ldcg(nz + (cnt - k - 1));
+                    __stcg(nz + ik, t1);
+                    __stcg(order + i + k, p1);
                 }
             }
             __syncwarp();
         } else {
-            uint32_t pt = 0, tl = 0;
-            if (act) { pt = __ldcg(nz + idx); tl = __ldcg(nz + (my_cnt - 1)); }
             __syncwarp();
             if (act) { __stcg(nz + idx, tl); __stcg(order + i + lane, pt); }
             __syncwarp();
         }
         cnt -= b;
         i += b;
+        idx = idx_next;
     }
 }
 
@@ -529,12 +537,10 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
     LUMINA_KERNEL_CHECK("ppht_collect_kernel");
     ppht_order_kernel<<<n, 32, 0, st>>>((uint32_t *)(ws + L.nz_off), (uint32_t *)(ws + L.order_off), (const int *)(ws + L.count_off), h * w);
     LUMINA_KERNEL_CHECK("ppht_order_kernel");
-    // ---- shared-memory (cluster) path: per-theta rho range the page can reach ----
-    std::vector<int> rho_lo(L.numangle), cell_off(L.numangle), row_cells(L.numangle);
-    int cs = 0, theta_per_cta = 0, slice_cells = 0;
+    // ---- shared-memory (cluster) paths: per-theta rho range the page can reach ----
+    std::vector<int> rho_lo(L.numangle), row_cells(L.numangle);
     {
         const int half = (L.numrho - 1) / 2;
-        std::vector<int> &cells = row_cells;
         for (int a = 0; a < L.numangle; a++) {
             int lo = 1 << 30, hi = -(1 << 30);
             for (int c = 0; c < 4; c++) {
@@ -546,111 +552,64 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
             if (lo + half < 0) lo = -half;
             if (hi + half > L.numrho - 1) hi = L.numrho - 1 - half;
             rho_lo[a] = lo + half;
-            cells[a] = hi - lo + 1;
-        }
-        int max_optin = 0, dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, ppht_cluster_kernel) == cudaSuccess) {
-            const long long budget = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024;
-            for (int c = 1; c <= 8; c *= 2) {
-                const int T = (L.numangle + c - 1) / c;
-                if (T > PCL_THREADS) continue;
-                int worst = 0;
-                for (int r0 = 0; r0 < L.numangle; r0 += T) {
-                    int sum = 0;
-                    for (int a = r0; a < L.numangle && a < r0 + T; a++) { cell_off[a] = sum; sum += cells[a]; }
-                    worst = sum > worst ? sum : worst;
-                }
-                if ((long long)worst * 2 <= budget) { cs = c; theta_per_cta = T; slice_cells = worst; break; }
-            }
-        } else {
-            cudaGetLastError();
+            row_cells[a] = hi - lo + 1;
         }
     }
     const char *force = getenv("LUMINA_PPHT");  // diagnostics: "l2" | "cluster" force a slower variant
-    // (1) local-mask cluster kernel: accumulator slice + the page's edge bitmask in each CTA's shared memory
-    if (!force) {
+    // variant 0: accumulator slice + the page's edge bitmask in each CTA's shared memory (events CTA-local)
+    // variant 1: accumulator slices in shared memory, mask in L2 (two cluster barriers per event)
+    for (int variant = (force ? 1 : 0); variant < 2 && !(force && force[0] == 'l'); variant++) {
+        const bool lm = variant == 0;
         int max_optin = 0, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel) == cudaSuccess) {
-            const long long mask_bytes = (((long long)h * w + 31) / 32) * 4;
-            const long long budget = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024 - mask_bytes;
-            for (int c = 1; c <= 8 && budget > 0; c++) {
-                const int T = (L.numangle + c - 1) / c;
-                if (T > PCL_THREADS) continue;
-                int worst = 0;
-                std::vector<int> offs(L.numangle);
-                for (int r0 = 0; r0 < L.numangle; r0 += T) {
-                    int sum = 0;
-                    for (int a = r0; a < L.numangle && a < r0 + T; a++) { offs[a] = sum; sum += row_cells[a]; }
-                    worst = sum > worst ? sum : worst;
-                }
-                if ((long long)worst * 2 + 16 <= budget) {
-                    LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.rholo_off, rho_lo.data(), rho_lo.size() * 4, cudaMemcpyHostToDevice, st));
-                    LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.celloff_off, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, st));
-                    PphtLmParams q;
-                    q.edges = d_edges; q.order = (const uint32_t *)(ws + L.order_off); q.count = (const int *)(ws + L.count_off);
-                    q.trig = (const float *)(ws + L.trig_off); q.step = (const int *)(ws + L.step_off);
-                    q.rho_lo = (const int *)(ws + L.rholo_off); q.cell_off = (const int *)(ws + L.celloff_off);
-                    q.lines = d_lines; q.nlines = d_nlines; q.stats = (int32_t *)(ws + L.stats_off);
-                    q.stats_ll = (long long *)(ws + L.stats_off + (((size_t)n * 8 * 4 + 7) & ~(size_t)7));
-                    q.h = h; q.w = w; q.numangle = L.numangle; q.numrho = L.numrho; q.theta_per_cta = T;
-                    q.slice_cells = worst; q.threshold = threshold; q.line_length = min_line_length;
-                    q.line_gap = max_line_gap; q.max_lines = max_lines;
-                    const size_t dyn = (((size_t)worst * 2 + 15) & ~(size_t)15) + (size_t)mask_bytes;
-                    LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3((unsigned)(n * c));
-                    cfg.blockDim = dim3(PCL_THREADS);
-                    cfg.dynamicSmemBytes = dyn;
-                    cfg.stream = st;
-                    cudaLaunchAttribute attr[1];
-                    attr[0].id = cudaLaunchAttributeClusterDimension;
-                    attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                    cfg.attrs = attr;
-                    cfg.numAttrs = 1;
-                    LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel, q));
-                    LUMINA_KERNEL_CHECK("ppht_cluster_lm_kernel");
-                    return LUMINA_OK;
-                }
+        const cudaError_t fe = lm ? cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<true>)
+                                  : cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<false>);
+        if (fe != cudaSuccess) { cudaGetLastError(); continue; }
+        const long long mask_bytes = lm ? (((long long)h * w + 31) / 32) * 4 : 0;
+        const long long budget = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024 - mask_bytes;
+        for (int c = 1; c <= 8 && budget > 0; c++) {
+            const int T = (L.numangle + c - 1) / c;
+            if (T > PCL_THREADS) continue;
+            int worst = 0;
+            std::vector<int> offs(L.numangle);
+            for (int r0 = 0; r0 < L.numangle; r0 += T) {
+                int sum = 0;
+                for (int a = r0; a < L.numangle && a < r0 + T; a++) { offs[a] = sum; sum += row_cells[a]; }
+                worst = sum > worst ? sum : worst;
             }
-        } else {
-            cudaGetLastError();
+            if ((long long)worst * 2 + 16 > budget) continue;
+            LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.rholo_off, rho_lo.data(), rho_lo.size() * 4, cudaMemcpyHostToDevice, st));
+            LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.celloff_off, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, st));
+            PphtLmParams q;
+            q.edges = d_edges; q.gmask = ws + L.mask_off;
+            q.order = (const uint32_t *)(ws + L.order_off); q.count = (const int *)(ws + L.count_off);
+            q.trig = (const float *)(ws + L.trig_off); q.step = (const int *)(ws + L.step_off);
+            q.rho_lo = (const int *)(ws + L.rholo_off); q.cell_off = (const int *)(ws + L.celloff_off);
+            q.lines = d_lines; q.nlines = d_nlines; q.stats = (int32_t *)(ws + L.stats_off);
+            q.stats_ll = (long long *)(ws + L.stats_off + (((size_t)n * 8 * 4 + 7) & ~(size_t)7));
+            q.h = h; q.w = w; q.numangle = L.numangle; q.numrho = L.numrho; q.theta_per_cta = T;
+            q.slice_cells = worst; q.threshold = threshold; q.line_length = min_line_length;
+            q.line_gap = max_line_gap; q.max_lines = max_lines;
+            const size_t dyn = (((size_t)worst * 2 + 15) & ~(size_t)15) + (size_t)mask_bytes;
+            if (lm) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            else LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(n * c));
+            cfg.blockDim = dim3(PCL_THREADS);
+            cfg.dynamicSmemBytes = dyn;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (lm) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel<true>, q));
+            else LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel<false>, q));
+            LUMINA_KERNEL_CHECK("ppht_cluster_lm_kernel");
+            return LUMINA_OK;
         }
-    }
-    // (2) cluster kernel with the mask in L2 (pages whose bitmask does not fit next to the accumulator)
-    if (cs > 0 && !(force && force[0] == 'l')) {
-        LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.rholo_off, rho_lo.data(), rho_lo.size() * 4, cudaMemcpyHostToDevice, st));
-        LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.celloff_off, cell_off.data(), cell_off.size() * 4, cudaMemcpyHostToDevice, st));
-        PphtClParams q;
-        q.mask = ws + L.mask_off; q.order = (const uint32_t *)(ws + L.order_off); q.count = (const int *)(ws + L.count_off);
-        q.trig = (const float *)(ws + L.trig_off); q.step = (const int *)(ws + L.step_off);
-        q.rho_lo = (const int *)(ws + L.rholo_off); q.cell_off = (const int *)(ws + L.celloff_off);
-        q.evbuf = (uint32_t *)(ws + L.evbuf_off); q.evbuf_words = (int)L.evbuf_words;
-        q.lines = d_lines; q.nlines = d_nlines; q.stats = (int32_t *)(ws + L.stats_off);
-        q.stats_ll = (long long *)(ws + L.stats_off + (((size_t)n * 8 * 4 + 7) & ~(size_t)7));
-        q.h = h; q.w = w; q.numangle = L.numangle; q.numrho = L.numrho; q.theta_per_cta = theta_per_cta;
-        q.slice_cells = slice_cells; q.threshold = threshold; q.line_length = min_line_length;
-        q.line_gap = max_line_gap; q.max_lines = max_lines;
-        const size_t dyn = (size_t)slice_cells * 2;
-        LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(n * cs));
-        cfg.blockDim = dim3(PCL_THREADS);
-        cfg.dynamicSmemBytes = dyn;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_kernel, q));
-        LUMINA_KERNEL_CHECK("ppht_cluster_kernel");
-        return LUMINA_OK;
     }
     // ---- (3) fallback: accumulator in L2 (pages whose rows do not fit 8 CTAs of shared memory) ----
     LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.acc_off, 0x40, (size_t)n * L.acc_words_per_page * 4, st));

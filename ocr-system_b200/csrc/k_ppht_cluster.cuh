@@ -3,15 +3,17 @@
 // The L2-atomic kernel in k_ppht.cu is bound by the ~180 scattered L2 accesses every vote costs
 // (measured: ~7 cycles per returning atomic per SM).  Here a page is owned by a thread-block CLUSTER
 // of CS CTAs: CTA c keeps the accumulator rows of theta in [c*T, (c+1)*T) in its own shared memory
-// (16-bit counters, only the rho range the page can reach: ~0.64*(w+h) cells per theta), so a vote is
-// a shared-memory read-modify-write by the thread that owns the theta row -- no atomics, no L2.
+// (16-bit biased counters, only the rho range the page can reach: ~0.64*(w+h) cells per theta), so a
+// vote is a shared-memory read-modify-write by the thread that owns the theta row: no atomics, no L2.
 //   * 32 points of the (precomputed) visiting order per batch; the theta-thread applies them in
-//     order, so every per-(point,theta) value is the exact sequential value;
-//   * per point the block reduces max/first-theta, CTAs exchange their 32 keys through DSMEM
-//     (st.shared::cluster) and one cluster barrier, then all CTAs take the same decision;
-//   * the first point that reaches the threshold runs its line event on rank 0 (mask walks as in
-//     k_ppht.cu); later points of the batch take their votes back and are replayed;
-//   * pixels of a good line are published through an L2 buffer and every CTA un-votes its rows.
+//     order (groups of 4, duplicates resolved in registers), so every per-(point,theta) value is the
+//     exact sequential value;
+//   * per point the row warps reduce max/first-theta (redux.sync), CTAs exchange their 32 keys through
+//     DSMEM (st.shared::cluster) and one cluster barrier, then all CTAs take the same decision;
+//   * the first point that reaches the threshold runs its line event, replayed by every CTA (the walk
+//     is deterministic given the mask); a line that is not "good" only clears mask pixels, so the scan
+//     continues inside the batch; a good line (un-votes) or a cleared batch point makes the later
+//     points take their votes back and replay.
 // Identical result to cv2.HoughLinesP (same lines, same order).
 #pragma once
 #include <cooperative_groups.h>
@@ -26,268 +28,21 @@ constexpr int PCL_ORD = 1024;      // visiting-order window in shared memory
 constexpr int PCL_MKWIN = 256;     // mask values refreshed per L2 trip
 constexpr int PCL_BIAS = 0x4000;
 constexpr int PCL_EVMAX = 512;     // un-vote pixel list entries per chunk
-
-struct PphtClParams {
-    uint8_t *mask;
-    const uint32_t *order;
-    const int *count;
-    const float *trig;   // [numangle][2]
-    const int *step;     // [numangle][3]
-    const int *rho_lo;   // [numangle] smallest rho index (already offset by (numrho-1)/2) the page can reach
-    const int *cell_off; // [numangle] offset of the row inside its CTA's slice
-    uint32_t *evbuf;     // [n][evbuf_words] un-vote pixel list of the current good line
-    int32_t *lines, *nlines, *stats;
-    long long *stats_ll;  // [n][10] phase cycle counters (diagnostics)
-    int evbuf_words;
-    int h, w, numangle, numrho, theta_per_cta, slice_cells;
-    int threshold, line_length, line_gap, max_lines;
-};
-
-__device__ __forceinline__ int pcl_rho(float fx, float fy, float c, float s, int half_rho) {
-    return __float2int_rn(__fadd_rn(__fmul_rn(fx, c), __fmul_rn(fy, s))) + half_rho;
-}
-
-__global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_kernel(const PphtClParams p) {
-    cg::cluster_group cl = cg::this_cluster();
-    const int CS = (int)cl.num_blocks();
-    const int rank = (int)cl.block_rank();
-    const int page = blockIdx.x / CS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int px = p.h * p.w;
-    uint8_t *mask = p.mask + (size_t)page * px;
-    const uint32_t *order = p.order + (size_t)page * px;
-    int32_t *lines = p.lines + (size_t)page * p.max_lines * 4;
-    uint32_t *evbuf = p.evbuf + (size_t)page * p.evbuf_words;
-    const int N = p.count[page];
-    const int half_rho = (p.numrho - 1) / 2;
-
-    extern __shared__ __align__(16) unsigned short acc[];  // [slice_cells]
-    __shared__ uint32_t ordbuf[PCL_ORD];
-    __shared__ uint8_t mkbuf[PCL_ORD];
-    __shared__ unsigned short tt[PCL_B][PCL_THREADS];   // value after the vote of (point, theta)
-    __shared__ unsigned short rr[PCL_B][PCL_THREADS];   // rho - rho_lo of (point, theta)
-    __shared__ uint32_t keys[2][8][PCL_B];              // [batch parity][cluster rank][point]
-    __shared__ uint32_t setbits[2][PPHT_MAXWIN];
-
-    // this thread's theta row
-    const int th0 = rank * p.theta_per_cta;
-    const int nth = max(0, min(p.theta_per_cta, p.numangle - th0));
-    const bool has_row = tid < nth;
-    const int theta = th0 + tid;
-    float cth = 0.f, sth = 0.f;
-    int rlo = 0, coff = 0;
-    if (has_row) { cth = p.trig[theta * 2]; sth = p.trig[theta * 2 + 1]; rlo = p.rho_lo[theta]; coff = p.cell_off[theta]; }
-    for (int i = tid; i < p.slice_cells; i += PCL_THREADS) acc[i] = (unsigned short)PCL_BIAS;
-
-    int pos = 0, buf_lo = 0, buf_hi = 0, mk_hi = 0;
-    int nl = 0, n_votes = 0, n_events = 0, n_batches = 0;
-    long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long tc0 = clock64();
 #define PCL_TICK(i) do { const long long t__ = clock64(); tph[i] += t__ - tc0; tc0 = t__; } while (0)
-    __syncthreads();
-    cl.sync();
-    PCL_TICK(9);
-
-    while (pos < N) {  // every CTA of the cluster runs the same control flow
-        if (pos + PCL_B > buf_hi && buf_hi < N) {
-            __syncthreads();
-            buf_lo = pos;
-            buf_hi = min(N, pos + PCL_ORD);
-            for (int t = tid; t < buf_hi - buf_lo; t += PCL_THREADS) ordbuf[t] = __ldcg(order + buf_lo + t);
-            mk_hi = pos;
-            __syncthreads();
-        }
-        if (pos + PCL_B > mk_hi && mk_hi < buf_hi) {  // (re)load mask values for the next window
-            __syncthreads();
-            const int hi = min(buf_hi, pos + PCL_MKWIN);
-            for (int e = pos + tid; e < hi; e += PCL_THREADS) {
-                const uint32_t pt = ordbuf[e - buf_lo];
-                mkbuf[e - buf_lo] = __ldcg(mask + (size_t)(pt >> 16) * p.w + (pt & 0xffffu));
-            }
-            mk_hi = hi;
-            __syncthreads();
-        }
-        PCL_TICK(0);
-        const int par = n_batches & 1;
-        n_batches++;
-        const int nb = min(PCL_B, N - pos);
-        // ---- votes: the owner thread of a theta row applies the batch in order ----
-        if (has_row) {
-#pragma unroll 4
-            for (int k = 0; k < nb; k++) {
-                const int bi = pos + k - buf_lo;
-                if (mkbuf[bi]) {
-                    const uint32_t pt = ordbuf[bi];
-                    const int r = pcl_rho((float)(pt & 0xffffu), (float)(pt >> 16), cth, sth, half_rho) - rlo;
-                    const unsigned short v = (unsigned short)(acc[coff + r] + 1);
-                    acc[coff + r] = v;
-                    tt[k][tid] = v;
-                    rr[k][tid] = (unsigned short)r;
-                } else {
-                    tt[k][tid] = 0;
-                }
-            }
-        }
-        __syncthreads();
-        PCL_TICK(1);
-        // ---- per point: max over this CTA's rows, first theta on ties; publish to every CTA ----
-        for (int k = warp; k < nb; k += PCL_THREADS / 32) {
-            uint32_t key = 0;
-            for (int t = lane; t < nth; t += 32) {
-                const uint32_t v = tt[k][t];
-                if (v) key = max(key, (v << 16) | (uint32_t)(65535 - (th0 + t)));
-            }
-            key = __reduce_max_sync(0xffffffffu, key);
-            if (lane < CS) *cl.map_shared_rank(&keys[par][rank][k], lane) = key;
-        }
-        PCL_TICK(2);
-        cl.sync();
-        PCL_TICK(3);
-        int ks = nb;
-        uint32_t gkey = 0;
-        {
-            uint32_t g = 0;
-            if (lane < nb)
-                for (int c = 0; c < CS; c++) g = max(g, keys[par][c][lane]);
-            const unsigned hits = __ballot_sync(0xffffffffu, g != 0u && (int)(g >> 16) - PCL_BIAS >= p.threshold);
-            if (hits) {
-                ks = __ffs(hits) - 1;
-                gkey = __shfl_sync(0xffffffffu, g, ks);
-            }
-        }
-        if (ks == nb) {  // no point of the batch reaches the threshold: everything stays
-            if (has_row)
-                for (int k = 0; k < nb; k++) n_votes += mkbuf[pos + k - buf_lo] ? 1 : 0;
-            pos += nb;
-            continue;
-        }
-        // ---- point ks triggers: later points of the batch take their votes back ----
-        if (has_row) {
-            for (int k = ks + 1; k < nb; k++)
-                if (mkbuf[pos + k - buf_lo]) acc[coff + rr[k][tid]] = (unsigned short)(acc[coff + rr[k][tid]] - 1);
-            for (int k = 0; k <= ks; k++) n_votes += mkbuf[pos + k - buf_lo] ? 1 : 0;
-        }
-        PCL_TICK(4);
-        n_events++;
-        const uint32_t ept = ordbuf[pos + ks - buf_lo];
-        const int ej = (int)(ept & 0xffffu), ei = (int)(ept >> 16);
-        const int max_n = 65535 - (int)(gkey & 0xffffu);
-        // ---- line event: rank 0 / warp 0 walks the mask, clears it, publishes the un-vote list ----
-        if (rank == 0 && warp == 0) {
-            const int shift = 16;
-            const int xflag = p.step[max_n * 3], dx0 = p.step[max_n * 3 + 1], dy0 = p.step[max_n * 3 + 2];
-            int x0 = ej, y0 = ei;
-            if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
-            else x0 = (x0 << shift) + (1 << (shift - 1));
-            int endk[2], ex[2], ey[2];
-#pragma unroll
-            for (int d = 0; d < 2; d++) {
-                const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
-                int gap = 0, ek = 0, base = 0, win = 0;
-                for (;; base += 32, win++) {
-                    const int kp = base + lane;
-                    const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                    const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                    const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
-                    const bool st = inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0;
-                    const unsigned bset = __ballot_sync(0xffffffffu, st);
-                    if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset;
-                    const unsigned below = bset & ((2u << lane) - 1u);
-                    const int gk = below ? lane - (31 - __clz(below)) : gap + lane + 1;
-                    const bool brk = !inb || (!st && gk > p.line_gap);
-                    const unsigned bbrk = __ballot_sync(0xffffffffu, brk);
-                    if (bbrk) {
-                        const int fb = __ffs(bbrk) - 1;
-                        const unsigned sb = fb ? (bset & ((1u << fb) - 1u)) : 0u;
-                        if (sb) ek = base + 31 - __clz(sb);
-                        break;
-                    }
-                    if (bset) { ek = base + 31 - __clz(bset); gap = __clz(bset); }
-                    else gap += 32;
-                }
-                endk[d] = ek;
-                const int X = x0 + ek * dx, Y = y0 + ek * dy;
-                ex[d] = xflag ? X : (X >> shift);
-                ey[d] = xflag ? (Y >> shift) : Y;
-            }
-            const bool good = abs(ex[1] - ex[0]) >= p.line_length || abs(ey[1] - ey[0]) >= p.line_length;
-            __syncwarp();
-            int npx = 0;  // pixels to un-vote (uniform across the warp)
-#pragma unroll
-            for (int d = 0; d < 2; d++) {
-                const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
-                for (int base = 0, win = 0; base <= endk[d]; base += 32, win++) {
-                    unsigned bset;
-                    if (win < PPHT_MAXWIN) bset = setbits[d][win];
-                    else {
-                        const int kp = base + lane;
-                        const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                        const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
-                        bset = __ballot_sync(0xffffffffu, inb && __ldcg(mask + (size_t)i1 * p.w + j1) != 0);
-                    }
-                    const int rem = endk[d] - base;
-                    if (rem < 31) bset &= (2u << rem) - 1u;
-                    if (d == 1 && base == 0) bset &= ~1u;
-                    if (bset & (1u << lane)) {
-                        const int kp = base + lane;
-                        const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                        __stcg(mask + (size_t)i1 * p.w + j1, (uint8_t)0);
-                        if (good) {
-                            const int slot = npx + __popc(bset & ((1u << lane) - 1u));
-                            if (slot + 1 < p.evbuf_words) __stcg(evbuf + 1 + slot, ((uint32_t)i1 << 16) | (uint32_t)j1);
-                        }
-                    }
-                    if (good) npx += __popc(bset);
-                }
-            }
-            if (lane == 0) {
-                __stcg(evbuf, (uint32_t)(good ? npx : 0));
-                if (good && nl < p.max_lines) {
-                    lines[nl * 4 + 0] = ex[0]; lines[nl * 4 + 1] = ey[0];
-                    lines[nl * 4 + 2] = ex[1]; lines[nl * 4 + 3] = ey[1];
-                }
-            }
-            if (good) nl++;
-            __threadfence();
-        }
-        PCL_TICK(5);
-        cl.sync();  // mask clears + un-vote list visible to the whole cluster
-        PCL_TICK(6);
-        {
-            const int npx = (int)__ldcg(evbuf);
-            if (npx > 0 && has_row) {
-                for (int q = 0; q < npx; q++) {
-                    const uint32_t pt = __ldcg(evbuf + 1 + q);
-                    const int r = pcl_rho((float)(pt & 0xffffu), (float)(pt >> 16), cth, sth, half_rho) - rlo;
-                    acc[coff + r] = (unsigned short)(acc[coff + r] - 1);
-                }
-            }
-        }
-        pos += ks + 1;
-        mk_hi = pos;  // the mask changed: reload before the next batch
-        PCL_TICK(7);
-        cl.sync();    // every CTA has consumed evbuf before rank 0 may overwrite it
-        PCL_TICK(8);
-    }
-    if (rank == 0 && tid == 0) {
-        p.nlines[page] = nl;
-        int32_t *st = p.stats + page * 8;
-        st[0] = N; st[1] = n_votes; st[2] = n_events; st[3] = nl; st[4] = 0; st[5] = n_batches; st[6] = CS;
-        for (int i = 0; i < 10; i++) p.stats_ll[page * 10 + i] = tph[i];
-    }
-}
-
 
 // ---------------------------------------------------------------------------------------------
-// Local-mask variant: when a CTA can also hold the page's edge mask as a bitmask (h*w/8 bytes) next
+// When a CTA can also hold the page's edge mask as a bitmask (h*w/8 bytes) next
 // to its accumulator slice, every CTA of the cluster keeps its own copy and replays each line event
 // locally (the walk is deterministic given the mask), so events need no cluster barrier, no L2 round
 // trips and no published pixel list.  The only cross-CTA traffic is 32 keys per batch over DSMEM.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pcl_rho(float fx, float fy, float c, float s, int half_rho) {
+    return __float2int_rn(__fadd_rn(__fmul_rn(fx, c), __fmul_rn(fy, s))) + half_rho;
+}
+
 struct PphtLmParams {
     const uint8_t *edges;    // [n][h][w] the Canny output (nonzero = edge)
+    uint8_t *gmask;          // [n][h][w] mutable 0/1 mask in L2 (only used by the LM=false variant)
     const uint32_t *order;
     const int *count;
     const float *trig;
@@ -316,6 +71,11 @@ __device__ __forceinline__ void pcl_group_update(unsigned short *row, const int 
         if (g < cnt) row[r[g]] = (unsigned short)v[g];  // in order: a later duplicate carries the larger count
 }
 
+// LM = true : every CTA holds its own copy of the edge bitmask in shared memory (events are CTA-local).
+// LM = false: the mask stays in L2 (pages whose bitmask does not fit); every CTA still replays the walk,
+//             but reads must finish cluster-wide before rank 0 clears, and clears must be visible before
+//             the next liveness test: two cluster barriers per line event.
+template <bool LM>
 __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const PphtLmParams p) {
     cg::cluster_group cl = cg::this_cluster();
     const int CS = (int)cl.num_blocks();
@@ -324,6 +84,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = p.h * p.w;
     const uint8_t *edges = p.edges + (size_t)page * px;
+    uint8_t *gmask = LM ? nullptr : p.gmask + (size_t)page * px;
     const uint32_t *order = p.order + (size_t)page * px;
     int32_t *lines = p.lines + (size_t)page * p.max_lines * 4;
     const int N = p.count[page];
@@ -332,8 +93,17 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     extern __shared__ __align__(16) unsigned char dynsm[];
     unsigned short *acc = reinterpret_cast<unsigned short *>(dynsm);                              // [slice_cells]
     uint32_t *mbits = reinterpret_cast<uint32_t *>(dynsm + (((size_t)p.slice_cells * 2 + 15) & ~(size_t)15));  // [(px+31)/32]
+    auto mask_set = [&](int bidx) -> bool {
+        if (LM) return (mbits[bidx >> 5] >> (bidx & 31)) & 1u;
+        return __ldcg(gmask + bidx) != 0;
+    };
+    auto mask_clear = [&](int bidx) {
+        if (LM) atomicAnd(&mbits[bidx >> 5], ~(1u << (bidx & 31)));
+        else if (rank == 0) __stcg(gmask + bidx, (uint8_t)0);
+    };
     __shared__ uint32_t ordbuf[PCL_ORD];
-    __shared__ uint32_t wkeys[PCL_THREADS / 32][PCL_B];
+    __shared__ uint32_t wkeys[PCL_THREADS / 32][PCL_B];   // [row warp][compact slot of the live point]
+    __shared__ float2 lpt[PCL_THREADS / 32][PCL_B];      // per-warp compact table of the batch's live points (x, y)
     __shared__ uint32_t keys[2][8][PCL_B];
     __shared__ uint32_t setbits[2][PPHT_MAXWIN];
     __shared__ uint32_t evpx[PCL_EVMAX];
@@ -355,7 +125,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     for (int i = tid; i < p.slice_cells; i += PCL_THREADS) acc[i] = (unsigned short)PCL_BIAS;
     for (int i = tid; i < p.numangle * 3; i += PCL_THREADS) s_step[i] = p.step[i];
     // bitmask of the edge map (raster bit order), built from global memory once
-    const int nwords = (px + 31) >> 5;
+    const int nwords = LM ? (px + 31) >> 5 : 0;
     for (int wd = warp; wd < nwords; wd += PCL_THREADS / 32) {
         const int q = wd * 32 + lane;
         const bool e = q < px && __ldg(edges + q) != 0;
@@ -387,34 +157,34 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
         const uint32_t mypt = lane < nb ? ordbuf[pos + lane - buf_lo] : 0u;
         const int myx = (int)(mypt & 0xffffu), myy = (int)(mypt >> 16);
         const int mybit = myy * p.w + myx;
-        const bool mylive = lane < nb && ((mbits[mybit >> 5] >> (mybit & 31)) & 1u);
+        const bool mylive = lane < nb && mask_set(mybit);
         const unsigned livebits = __ballot_sync(0xffffffffu, mylive);
         const float myfx = (float)myx, myfy = (float)myy;
         // ---- votes: groups of 4 live points, all rows of this warp in lock step ----
+        const int nlive = __popc(livebits);
+        const int myslot = __popc(livebits & ((1u << lane) - 1u));
         if (warp < row_warps) {
-            unsigned todo = livebits;
-            while (todo) {
-                int kk[4], r[4], v[4], cnt = 0;
+            if (mylive) lpt[warp][myslot] = make_float2(myfx, myfy);
+            __syncwarp();
+            for (int j0 = 0; j0 < nlive; j0 += 4) {
+                const int cnt = min(4, nlive - j0);
+                int r[4], v[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    kk[g] = 0; r[g] = -1 - g;
-                    if (todo) {
-                        kk[g] = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        cnt = g + 1;
+                    r[g] = -1 - g;
+                    if (g < cnt) {
+                        const float2 q = lpt[warp][j0 + g];
+                        r[g] = pcl_rho(q.x, q.y, cth, sth, half_rho) - rlo;
                     }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const float fx = __shfl_sync(0xffffffffu, myfx, kk[g]), fy = __shfl_sync(0xffffffffu, myfy, kk[g]);
-                    if (g < cnt) r[g] = pcl_rho(fx, fy, cth, sth, half_rho) - rlo;
                 }
                 if (has_row) pcl_group_update(row, r, cnt, +1, v);
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    uint32_t key = (has_row && g < cnt) ? (((uint32_t)v[g] << 16) | (uint32_t)(65535 - theta)) : 0u;
-                    key = __reduce_max_sync(0xffffffffu, key);
-                    if (lane == 0 && g < cnt) wkeys[warp][kk[g]] = key;
+                    if (g < cnt) {
+                        uint32_t key = has_row ? (((uint32_t)v[g] << 16) | (uint32_t)(65535 - theta)) : 0u;
+                        key = __reduce_max_sync(0xffffffffu, key);
+                        if (lane == 0) wkeys[warp][j0 + g] = key;
+                    }
                 }
             }
         }
@@ -424,7 +194,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
         if (warp == 0) {
             uint32_t key = 0;
             if ((livebits >> lane) & 1u)
-                for (int wv = 0; wv < row_warps; wv++) key = max(key, wkeys[wv][lane]);
+                for (int wv = 0; wv < row_warps; wv++) key = max(key, wkeys[wv][myslot]);
             for (int c = 0; c < CS; c++) *cl.map_shared_rank(&keys[par][rank][lane], c) = key;
         }
         PCL_TICK(2);
@@ -464,7 +234,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                     const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
                     const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
                     const int bidx = i1 * p.w + j1;
-                    const bool st = inb && ((mbits[bidx >> 5] >> (bidx & 31)) & 1u);
+                    const bool st = inb && mask_set(bidx);
                     const unsigned bset = __ballot_sync(0xffffffffu, st);
                     if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset;
                     const unsigned below = bset & ((2u << lane) - 1u);
@@ -488,6 +258,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 }
             }
             __syncthreads();
+            if (!LM) cl.sync();  // every CTA has finished reading the shared mask before rank 0 clears it
             const bool good = abs(ev_ex[1] - ev_ex[0]) >= p.line_length || abs(ev_ey[1] - ev_ey[0]) >= p.line_length;
             if (!good) {
                 if (warp < 2) {  // clear the segment (start pixel included by direction 0)
@@ -503,7 +274,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                             const int X = x0 + kp * dx, Y = y0 + kp * dy;
                             const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
                             const int bidx = i1 * p.w + j1;
-                            atomicAnd(&mbits[bidx >> 5], ~(1u << (bidx & 31)));
+                            mask_clear(bidx);
                         }
                     }
                 }
@@ -537,7 +308,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                                 const int X = x0 + kp * dx, Y = y0 + kp * dy;
                                 const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
                                 const int bidx = i1 * p.w + j1;
-                                atomicAnd(&mbits[bidx >> 5], ~(1u << (bidx & 31)));
+                                mask_clear(bidx);
                                 evpx[slot0 + __popc(bset & ((1u << lane) - 1u))] = ((uint32_t)i1 << 16) | (uint32_t)j1;
                             }
                         }
@@ -566,26 +337,26 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 }
                 nl++;
             }
+            if (!LM) { __threadfence(); cl.sync(); }  // rank 0's clears are visible to the whole cluster
             __syncthreads();  // mask clears visible; ev_* / setbits may be reused
             // did the cleared segment take one of the later batch points?
-            const bool stilllive = lane < nb && ((mbits[mybit >> 5] >> (mybit & 31)) & 1u);
+            const bool stilllive = lane < nb && mask_set(mybit);
             const unsigned later = ks < 31 ? ~((2u << ks) - 1u) : 0u;
             const unsigned nowlive = __ballot_sync(0xffffffffu, stilllive);
             if (good || ((livebits ^ nowlive) & later)) {
                 // ---- later live points of the batch take their votes back and are replayed ----
                 if (warp < row_warps) {
-                    unsigned todo = livebits & later;
-                    while (todo) {
-                        int kk[4], r[4], v[4], cnt = 0;
+                    const int first = __popc(livebits & ((2u << ks) - 1u));  // compact slot of the first later point
+                    for (int j0 = first; j0 < nlive; j0 += 4) {
+                        const int cnt = min(4, nlive - j0);
+                        int r[4], v[4];
 #pragma unroll
                         for (int gq = 0; gq < 4; gq++) {
-                            kk[gq] = 0; r[gq] = -1 - gq;
-                            if (todo) { kk[gq] = __ffs(todo) - 1; todo &= todo - 1; cnt = gq + 1; }
-                        }
-#pragma unroll
-                        for (int gq = 0; gq < 4; gq++) {
-                            const float fx = __shfl_sync(0xffffffffu, myfx, kk[gq]), fy = __shfl_sync(0xffffffffu, myfy, kk[gq]);
-                            if (gq < cnt) r[gq] = pcl_rho(fx, fy, cth, sth, half_rho) - rlo;
+                            r[gq] = -1 - gq;
+                            if (gq < cnt) {
+                                const float2 q = lpt[warp][j0 + gq];
+                                r[gq] = pcl_rho(q.x, q.y, cth, sth, half_rho) - rlo;
+                            }
                         }
                         if (has_row) pcl_group_update(row, r, cnt, -1, v);
                     }

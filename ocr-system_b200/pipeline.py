@@ -166,18 +166,30 @@ class PagePipeline:
         ``(out_host, PageBatchResult, h2d_bytes, d2h_bytes)`` per batch, results complete in host memory."""
         dev = self.device or torch.device("cuda", torch.cuda.current_device())
         comp = torch.cuda.current_stream(dev)
-        copy_stream = torch.cuda.Stream(dev)
+        st = getattr(self, "_stream_state", None)
+        if st is None or st["dev"] != dev:  # copy stream + double buffer live as long as the pipeline object
+            st = self._stream_state = {"dev": dev, "copy": torch.cuda.Stream(dev), "buf": [None, None], "free": [None, None]}
+        copy_stream = st["copy"]
         it = iter(host_batches)
-        slots = [None, None]
+        dev_buf = st["buf"]         # persistent double buffer for the rasters (no allocator traffic per batch)
+        ready = [None, None]        # H2D of slot k finished (recorded on the copy stream)
+        free = st["free"]           # kernels that read slot k finished (recorded on the compute stream)
+        host_of = [None, None]
 
         def issue(k, hb):
             if hb.is_cuda:
                 raise TypeError("run_host_stream needs host tensors")
+            if dev_buf[k] is None or dev_buf[k].shape != hb.shape:
+                dev_buf[k] = torch.empty(hb.shape, dtype=torch.uint8, device=dev)
+                free[k] = None
             with torch.cuda.stream(copy_stream):
-                x = hb.to(dev, non_blocking=True)
+                if free[k] is not None:
+                    copy_stream.wait_event(free[k])
+                dev_buf[k].copy_(hb, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            slots[k] = (x, ev, hb)
+            ready[k] = ev
+            host_of[k] = hb
 
         cur_hb = next(it, None)
         if cur_hb is None:
@@ -190,10 +202,11 @@ class PagePipeline:
             nxt = next(it, None)
             if nxt is not None:
                 issue(k ^ 1, nxt)  # upload of the next batch overlaps this batch's kernels
-            x, ev, hb = slots[k]
-            comp.wait_event(ev)
-            x.record_stream(comp)
-            res = self.run_device(x, profile=profile)
+            comp.wait_event(ready[k])
+            res = self.run_device(dev_buf[k], profile=profile)
+            fe = torch.cuda.Event()
+            fe.record(comp)
+            free[k] = fe
             if out_host is None or out_host["pages"].shape != res.pages.shape:
                 out_host = {
                     "pages": torch.empty(res.pages.shape, dtype=torch.uint8, pin_memory=True),
@@ -203,7 +216,7 @@ class PagePipeline:
             out_host["binary"].copy_(res.binary, non_blocking=True)
             comp.synchronize()
             out_host["angles"] = res.angles
-            slots[k] = None
+            hb = host_of[k]
             yield out_host, res, hb.numel(), res.pages.numel() + res.binary.numel() + res.angles.nbytes
             cur_hb = nxt
             i += 1
