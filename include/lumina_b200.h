@@ -108,6 +108,10 @@ int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double rho, double 
 /* (iv)+(v) host: per-line degrees(arctan2) folded to +-45, np.median.  Host
  * code on purpose (glibc atan2 == the reference's libm). nlines==0 -> 0.0 */
 double lumina_median_angle_host(const int32_t *h_lines, int nlines);
+/* (iv)-(vi) for a batch in one call: per page the reference's gating (:409-439) and, when the page
+ * is to be rotated, getRotationMatrix2D((w//2, h//2), angle, 1).  h_lines [n][lines_stride][4]. */
+void lumina_deskew_decide_host(const int32_t *h_lines, const int32_t *h_nlines, int n, int lines_stride,
+                               int h, int w, double *h_angles, double *h_m6, uint8_t *h_apply);
 /* cv2.getRotationMatrix2D (double, 2x3 row-major) */
 void lumina_rotation_matrix_host(double cx, double cy, double angle_deg, double scale, double *h_m6);
 /* (vii) cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE), same size.

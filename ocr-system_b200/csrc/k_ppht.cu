@@ -55,8 +55,8 @@ static PphtLayout ppht_layout(int n, int h, int w, double rho_d, double theta_d)
     L.stats_off = off; off = align256(off + (size_t)n * 8 * 4 + (size_t)n * 10 * 8);  // per page: N, votes, events, good, walk windows
     L.rholo_off = off; off = align256(off + (size_t)L.numangle * 4);
     L.celloff_off = off; off = align256(off + (size_t)L.numangle * 4);
-    L.evbuf_words = 0;
-    L.evbuf_off = off;
+    L.evbuf_words = ((size_t)h * w + 31) / 32;  // words of one private bitmask copy
+    L.evbuf_off = off; off = align256(off + (size_t)n * 8 * L.evbuf_words * 4);
     L.total = off;
     return L;
 }
@@ -556,8 +556,8 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
         }
     }
     const char *force = getenv("LUMINA_PPHT");  // diagnostics: "l2" | "cluster" force a slower variant
-    // variant 0: accumulator slice + the page's edge bitmask in each CTA's shared memory (events CTA-local)
-    // variant 1: accumulator slices in shared memory, mask in L2 (two cluster barriers per event)
+    // variant 0: accumulator slice + a private copy of the edge bitmask in each CTA's shared memory
+    // variant 1: accumulator slices in shared memory, the private bitmask copies in L2
     for (int variant = (force ? 1 : 0); variant < 2 && !(force && force[0] == 'l'); variant++) {
         const bool lm = variant == 0;
         int max_optin = 0, dev = 0;
@@ -583,7 +583,7 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
             LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.rholo_off, rho_lo.data(), rho_lo.size() * 4, cudaMemcpyHostToDevice, st));
             LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.celloff_off, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, st));
             PphtLmParams q;
-            q.edges = d_edges; q.gmask = ws + L.mask_off;
+            q.edges = d_edges; q.gbits = (uint32_t *)(ws + L.evbuf_off);
             q.order = (const uint32_t *)(ws + L.order_off); q.count = (const int *)(ws + L.count_off);
             q.trig = (const float *)(ws + L.trig_off); q.step = (const int *)(ws + L.step_off);
             q.rho_lo = (const int *)(ws + L.rholo_off); q.cell_off = (const int *)(ws + L.celloff_off);
@@ -643,4 +643,24 @@ LUMINA_API double lumina_median_angle_host(const int32_t *h_lines, int nlines) {
     }
     qsort(ang.data(), ang.size(), sizeof(double), cmp_double);
     return (nlines & 1) ? ang[nlines / 2] : (ang[nlines / 2 - 1] + ang[nlines / 2]) / 2.0;
+}
+
+// The per-page decision of deskew (image_preprocessing.py:409-444) for a whole batch in one host call:
+// no lines -> (0.0, keep); |median| < 0.5 -> (median, keep); |median| > 45 -> (0.0, keep); else rotate by
+// getRotationMatrix2D((w//2, h//2), median, 1.0).
+LUMINA_API void lumina_deskew_decide_host(const int32_t *h_lines, const int32_t *h_nlines, int n, int lines_stride,
+                                          int h, int w, double *h_angles, double *h_m6, uint8_t *h_apply) {
+    for (int i = 0; i < n; i++) {
+        h_angles[i] = 0.0;
+        h_apply[i] = 0;
+        for (int k = 0; k < 6; k++) h_m6[(size_t)i * 6 + k] = 0.0;
+        const int nl = h_nlines[i] < lines_stride ? h_nlines[i] : lines_stride;
+        if (nl <= 0) continue;
+        const double a = lumina_median_angle_host(h_lines + (size_t)i * lines_stride * 4, nl);
+        if (fabs(a) < 0.5) { h_angles[i] = a; continue; }
+        if (fabs(a) > 45) continue;
+        h_angles[i] = a;
+        h_apply[i] = 1;
+        lumina_rotation_matrix_host((double)(w / 2), (double)(h / 2), a, 1.0, h_m6 + (size_t)i * 6);
+    }
 }

@@ -42,7 +42,7 @@ __device__ __forceinline__ int pcl_rho(float fx, float fy, float c, float s, int
 
 struct PphtLmParams {
     const uint8_t *edges;    // [n][h][w] the Canny output (nonzero = edge)
-    uint8_t *gmask;          // [n][h][w] mutable 0/1 mask in L2 (only used by the LM=false variant)
+    uint32_t *gbits;         // [n][8][(h*w+31)/32] per-CTA private edge bitmasks in L2 (LM=false variant only)
     const uint32_t *order;
     const int *count;
     const float *trig;
@@ -71,10 +71,13 @@ __device__ __forceinline__ void pcl_group_update(unsigned short *row, const int 
         if (g < cnt) row[r[g]] = (unsigned short)v[g];  // in order: a later duplicate carries the larger count
 }
 
-// LM = true : every CTA holds its own copy of the edge bitmask in shared memory (events are CTA-local).
-// LM = false: the mask stays in L2 (pages whose bitmask does not fit); every CTA still replays the walk,
-//             but reads must finish cluster-wide before rank 0 clears, and clears must be visible before
-//             the next liveness test: two cluster barriers per line event.
+// Every CTA of the cluster owns a private copy of the page's edge bitmask and replays each line event on
+// it, so events never need cluster-wide synchronisation.
+// LM = true : the copy lives in shared memory next to the accumulator slice (fastest per page, but at
+//             678x960 it needs 3 CTAs per page: 49 pages resident on 148 SMs).
+// LM = false: the copy lives in L2 (81 KB per CTA at 678x960, 10 MB per 64-page batch); mask reads cost an
+//             L2 round trip, but large pages (bitmask > shared memory) are covered and the slices of a
+//             678x960 page fit 2 CTAs.
 template <bool LM>
 __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const PphtLmParams p) {
     cg::cluster_group cl = cg::this_cluster();
@@ -84,7 +87,8 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = p.h * p.w;
     const uint8_t *edges = p.edges + (size_t)page * px;
-    uint8_t *gmask = LM ? nullptr : p.gmask + (size_t)page * px;
+    const int nwords_all = (px + 31) >> 5;
+    uint32_t *gbits = LM ? nullptr : p.gbits + ((size_t)page * 8 + rank) * nwords_all;
     const uint32_t *order = p.order + (size_t)page * px;
     int32_t *lines = p.lines + (size_t)page * p.max_lines * 4;
     const int N = p.count[page];
@@ -95,11 +99,11 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     uint32_t *mbits = reinterpret_cast<uint32_t *>(dynsm + (((size_t)p.slice_cells * 2 + 15) & ~(size_t)15));  // [(px+31)/32]
     auto mask_set = [&](int bidx) -> bool {
         if (LM) return (mbits[bidx >> 5] >> (bidx & 31)) & 1u;
-        return __ldcg(gmask + bidx) != 0;
+        return (__ldcg(gbits + (bidx >> 5)) >> (bidx & 31)) & 1u;
     };
     auto mask_clear = [&](int bidx) {
         if (LM) atomicAnd(&mbits[bidx >> 5], ~(1u << (bidx & 31)));
-        else if (rank == 0) __stcg(gmask + bidx, (uint8_t)0);
+        else atomicAnd(gbits + (bidx >> 5), ~(1u << (bidx & 31)));  // result unused: RED to L2
     };
     __shared__ uint32_t ordbuf[PCL_ORD];
     __shared__ uint32_t wkeys[PCL_THREADS / 32][PCL_B];   // [row warp][compact slot of the live point]
@@ -125,12 +129,12 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     for (int i = tid; i < p.slice_cells; i += PCL_THREADS) acc[i] = (unsigned short)PCL_BIAS;
     for (int i = tid; i < p.numangle * 3; i += PCL_THREADS) s_step[i] = p.step[i];
     // bitmask of the edge map (raster bit order), built from global memory once
-    const int nwords = LM ? (px + 31) >> 5 : 0;
+    const int nwords = (px + 31) >> 5;
     for (int wd = warp; wd < nwords; wd += PCL_THREADS / 32) {
         const int q = wd * 32 + lane;
         const bool e = q < px && __ldg(edges + q) != 0;
         const unsigned b = __ballot_sync(0xffffffffu, e);
-        if (lane == 0) mbits[wd] = b;
+        if (lane == 0) { if (LM) mbits[wd] = b; else __stcg(gbits + wd, b); }
     }
 
     int pos = 0, buf_lo = 0, buf_hi = 0;
@@ -258,7 +262,6 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 }
             }
             __syncthreads();
-            if (!LM) cl.sync();  // every CTA has finished reading the shared mask before rank 0 clears it
             const bool good = abs(ev_ex[1] - ev_ex[0]) >= p.line_length || abs(ev_ey[1] - ev_ey[0]) >= p.line_length;
             if (!good) {
                 if (warp < 2) {  // clear the segment (start pixel included by direction 0)
@@ -337,7 +340,6 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 }
                 nl++;
             }
-            if (!LM) { __threadfence(); cl.sync(); }  // rank 0's clears are visible to the whole cluster
             __syncthreads();  // mask clears visible; ev_* / setbits may be reused
             // did the cleared segment take one of the later batch points?
             const bool stilllive = lane < nb && mask_set(mybit);

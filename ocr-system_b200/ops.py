@@ -235,6 +235,21 @@ def rotation_matrix(cx: float, cy: float, angle: float, scale: float = 1.0) -> n
     return m.reshape(2, 3)
 
 
+def deskew_decide(lines_host: np.ndarray, nlines_host: np.ndarray, h: int, w: int):
+    """Reference gating (image_preprocessing.py:409-444) for a batch in one host call:
+    (angles[N] f64, forward matrices[N,6] f64, apply[N] u8)."""
+    ln = np.ascontiguousarray(lines_host, dtype=np.int32)
+    nl = np.ascontiguousarray(nlines_host, dtype=np.int32)
+    n, stride = ln.shape[0], ln.shape[1]
+    angles = np.zeros(n, np.float64)
+    mats = np.zeros((n, 6), np.float64)
+    apply = np.zeros(n, np.uint8)
+    _L().lumina_deskew_decide_host(ln.ctypes.data_as(C.c_void_p), nl.ctypes.data_as(C.c_void_p), n, stride, int(h), int(w),
+                                   angles.ctypes.data_as(C.c_void_p), mats.ctypes.data_as(C.c_void_p),
+                                   apply.ctypes.data_as(C.c_void_p))
+    return angles, mats, apply
+
+
 def warp_affine_cubic(pages: torch.Tensor, mats: np.ndarray, apply: Optional[np.ndarray] = None) -> torch.Tensor:
     """cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE) with per-page forward 2x3 matrices (host)."""
     sq = pages.dim() == 3
@@ -260,21 +275,7 @@ def deskew(pages: torch.Tensor, max_lines: int = 4096):
         return deskew(pages, max_lines=int(nl.max()))
     keep = int(nl.max(initial=0))
     lh = lines[:, :max(keep, 1)].cpu().numpy()
-    angles = np.zeros(n, np.float64)
-    mats = np.zeros((n, 6), np.float64)
-    apply = np.zeros(n, np.uint8)
-    for i in range(n):
-        if nl[i] == 0:
-            continue  # "No lines detected" -> image, 0.0
-        a = median_angle(lh[i, : nl[i]])
-        if abs(a) < 0.5:
-            angles[i] = a
-            continue
-        if abs(a) > 45:
-            continue  # angle too large -> image, 0.0
-        angles[i] = a
-        mats[i] = rotation_matrix(w // 2, h // 2, a).reshape(6)
-        apply[i] = 1
+    angles, mats, apply = deskew_decide(lh, nl, h, w)
     if not apply.any():
         return pages, angles
     out = warp_affine_cubic(x, mats, apply)

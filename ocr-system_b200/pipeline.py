@@ -118,19 +118,7 @@ class PagePipeline:
             lines, nlines = ops.hough_lines_p(edges, max_lines=keep)
             nl = nlines.cpu().numpy()
         lh = lines[:, : max(keep, 1)].cpu().numpy()
-        angles = np.zeros(n, np.float64)
-        mats = np.zeros((n, 6), np.float64)
-        apply = np.zeros(n, np.uint8)
-        for i in range(n):
-            if nl[i] == 0:
-                continue
-            a = ops.median_angle(lh[i, : nl[i]])
-            if abs(a) < 0.5:
-                angles[i] = a
-            elif abs(a) <= 45:
-                angles[i] = a
-                mats[i] = ops.rotation_matrix(w // 2, h // 2, a).reshape(6)
-                apply[i] = 1
+        angles, mats, apply = ops.deskew_decide(lh, nl, h, w)
         if apply.any():
             x = ops.warp_affine_cubic(x, mats, apply)
         return x, angles
@@ -168,7 +156,8 @@ class PagePipeline:
         comp = torch.cuda.current_stream(dev)
         st = getattr(self, "_stream_state", None)
         if st is None or st["dev"] != dev:  # copy stream + double buffer live as long as the pipeline object
-            st = self._stream_state = {"dev": dev, "copy": torch.cuda.Stream(dev), "buf": [None, None], "free": [None, None]}
+            st = self._stream_state = {"dev": dev, "copy": torch.cuda.Stream(dev), "buf": [None, None], "free": [None, None],
+                                       "out": None}
         copy_stream = st["copy"]
         it = iter(host_batches)
         dev_buf = st["buf"]         # persistent double buffer for the rasters (no allocator traffic per batch)
@@ -196,7 +185,7 @@ class PagePipeline:
             return
         issue(0, cur_hb)
         i = 0
-        out_host = None
+        out_host = st["out"]  # pinned result buffers are kept too: cudaHostAlloc costs ~100 ms per call otherwise
         while cur_hb is not None:
             k = i & 1
             nxt = next(it, None)
@@ -208,7 +197,7 @@ class PagePipeline:
             fe.record(comp)
             free[k] = fe
             if out_host is None or out_host["pages"].shape != res.pages.shape:
-                out_host = {
+                out_host = st["out"] = {
                     "pages": torch.empty(res.pages.shape, dtype=torch.uint8, pin_memory=True),
                     "binary": torch.empty(res.binary.shape, dtype=torch.uint8, pin_memory=True),
                 }

@@ -24,3 +24,13 @@ print("overlapped H2D + run_device ms", (time.perf_counter()-t)*1e3, "issue ms",
 t = time.perf_counter(); n = 0
 for out, res, h2d, d2h in pipe.run_host_stream([host_in] * 6):
     n += 1; print("  batch", n, "t=", round((time.perf_counter()-t)*1e3, 1))
+print("---- second call (persistent buffers), K=5 ----")
+torch.cuda.synchronize()
+t = time.perf_counter(); n = 0
+for out, res, h2d, d2h in pipe.run_host_stream([host_in] * 5):
+    n += 1; print("  batch", n, "t=", round((time.perf_counter()-t)*1e3, 1))
+print("---- third call, K=5, with event timing like bench ----")
+f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+f0.record()
+for out, res, h2d, d2h in pipe.run_host_stream([host_in] * 5): pass
+f1.record(); torch.cuda.synchronize(); print("event ms/step", f0.elapsed_time(f1)/5)
