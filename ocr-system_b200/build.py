@@ -49,6 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc, *ARCH, *COMMON]
         if src in NO_FMA:
             cmd.append("-fmad=false")
+        if os.environ.get("LUMINA_PPHT_PROFILE") and src == "k_ppht.cu":
+            cmd.append("-DLUMINA_PPHT_PROFILE=1")  # per-phase clock64 ticks in the stats buffer (tools/ppht_stats.py)
         cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

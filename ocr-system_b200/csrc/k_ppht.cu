@@ -29,7 +29,8 @@
 namespace lumina {
 
 struct PphtLayout {
-    size_t acc_off, mask_off, nz_off, order_off, count_off, trig_off, step_off, stats_off, rholo_off, celloff_off, evbuf_off, total;
+    size_t acc_off, mask_off, nz_off, order_off, count_off, trig_off, step_off, stats_off, rholo_off, celloff_off, evbuf_off, pageorder_off, bits_off, total;
+    size_t bits_stride;         // words per page of the shared edge bitmask (multiple of 4)
     size_t evbuf_words;
     size_t acc_words_per_page;  // uint32 words (2 counters per word)
     int numangle, numrho;
@@ -56,7 +57,10 @@ static PphtLayout ppht_layout(int n, int h, int w, double rho_d, double theta_d)
     L.rholo_off = off; off = align256(off + (size_t)L.numangle * 4);
     L.celloff_off = off; off = align256(off + (size_t)L.numangle * 4);
     L.evbuf_words = ((size_t)h * w + 31) / 32;  // words of one private bitmask copy
-    L.evbuf_off = off; off = align256(off + (size_t)n * 8 * L.evbuf_words * 4);
+    L.evbuf_off = off; off = align256(off + (size_t)n * 8 * (((L.evbuf_words + 3) & ~(size_t)3)) * 4);
+    L.pageorder_off = off; off = align256(off + (size_t)n * 4);
+    L.bits_stride = (L.evbuf_words + 3) & ~(size_t)3;
+    L.bits_off = off; off = align256(off + (size_t)n * L.bits_stride * 4);
     L.total = off;
     return L;
 }
@@ -171,6 +175,43 @@ __global__ void __launch_bounds__(32) ppht_order_kernel(uint32_t *__restrict__ n
         i += b;
         idx = idx_next;
     }
+}
+
+// ---- A2: edge bitmask (raster bit order): one 32-pixel word per thread ---------------------------
+__global__ void __launch_bounds__(256) ppht_bitmask_kernel(const uint8_t *__restrict__ edges, uint32_t *__restrict__ bits,
+                                                           int px, int stride_words) {
+    const int page = blockIdx.y;
+    const int wd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wd >= stride_words) return;
+    const uint8_t *e = edges + (size_t)page * px + (size_t)wd * 32;
+    uint32_t b = 0;
+    const int left = px - wd * 32;
+    if (left >= 32 && ((uintptr_t)e & 15) == 0) {
+        const uint4 lo = ldg_stream_u4(e), hi = ldg_stream_u4(e + 16);
+        const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) b |= (((wv[k] >> (8 * q)) & 0xffu) != 0u ? 1u : 0u) << (k * 4 + q);
+        }
+    } else {
+        for (int k = 0; k < 32 && k < left; k++) b |= (e[k] != 0 ? 1u : 0u) << k;
+    }
+    bits[(size_t)page * stride_words + wd] = b;
+}
+
+// ---- B2: launch order of the pages: most edge points first (longest-processing-time-first keeps the
+// last wave of clusters short); ties by page index.  O(n^2) compares, n is a batch of pages.
+__global__ void __launch_bounds__(256) ppht_page_order_kernel(const int *__restrict__ count, int *__restrict__ page_order, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ci = count[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        const int cj = __ldg(count + j);
+        rank += (cj > ci) || (cj == ci && j < i);
+    }
+    page_order[rank] = i;
 }
 
 // ---- C: main loop -----------------------------------------------------------------
@@ -535,8 +576,16 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
 
     ppht_collect_kernel<<<n, 1024, 0, st>>>(d_edges, ws + L.mask_off, (uint32_t *)(ws + L.nz_off), (int *)(ws + L.count_off), h, w);
     LUMINA_KERNEL_CHECK("ppht_collect_kernel");
+    ppht_bitmask_kernel<<<dim3((unsigned)((L.bits_stride + 255) / 256), (unsigned)n), 256, 0, st>>>(
+        d_edges, (uint32_t *)(ws + L.bits_off), h * w, (int)L.bits_stride);
+    LUMINA_KERNEL_CHECK("ppht_bitmask_kernel");
     ppht_order_kernel<<<n, 32, 0, st>>>((uint32_t *)(ws + L.nz_off), (uint32_t *)(ws + L.order_off), (const int *)(ws + L.count_off), h * w);
     LUMINA_KERNEL_CHECK("ppht_order_kernel");
+    const bool lpt_order = n > 1 && n <= 8192;
+    if (lpt_order) {
+        ppht_page_order_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int *)(ws + L.count_off), (int *)(ws + L.pageorder_off), n);
+        LUMINA_KERNEL_CHECK("ppht_page_order_kernel");
+    }
     // ---- shared-memory (cluster) paths: per-theta rho range the page can reach ----
     std::vector<int> rho_lo(L.numangle), row_cells(L.numangle);
     {
@@ -567,7 +616,7 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
         const cudaError_t fe = lm ? cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<true>)
                                   : cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<false>);
         if (fe != cudaSuccess) { cudaGetLastError(); continue; }
-        const long long mask_bytes = lm ? (((long long)h * w + 31) / 32) * 4 : 0;
+        const long long mask_bytes = lm ? (long long)L.bits_stride * 4 : 0;
         const long long budget = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024 - mask_bytes;
         for (int c = 1; c <= 8 && budget > 0; c++) {
             const int T = (L.numangle + c - 1) / c;
@@ -583,10 +632,12 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
             LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.rholo_off, rho_lo.data(), rho_lo.size() * 4, cudaMemcpyHostToDevice, st));
             LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.celloff_off, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, st));
             PphtLmParams q;
-            q.edges = d_edges; q.gbits = (uint32_t *)(ws + L.evbuf_off);
+            q.bits = (const uint32_t *)(ws + L.bits_off); q.bits_stride = (int)L.bits_stride;
+            q.gbits = (uint32_t *)(ws + L.evbuf_off);
             q.order = (const uint32_t *)(ws + L.order_off); q.count = (const int *)(ws + L.count_off);
             q.trig = (const float *)(ws + L.trig_off); q.step = (const int *)(ws + L.step_off);
             q.rho_lo = (const int *)(ws + L.rholo_off); q.cell_off = (const int *)(ws + L.celloff_off);
+            q.page_order = lpt_order ? (const int *)(ws + L.pageorder_off) : nullptr;
             q.lines = d_lines; q.nlines = d_nlines; q.stats = (int32_t *)(ws + L.stats_off);
             q.stats_ll = (long long *)(ws + L.stats_off + (((size_t)n * 8 * 4 + 7) & ~(size_t)7));
             q.h = h; q.w = w; q.numangle = L.numangle; q.numrho = L.numrho; q.theta_per_cta = T;

@@ -28,7 +28,11 @@ constexpr int PCL_ORD = 1024;      // visiting-order window in shared memory
 constexpr int PCL_MKWIN = 256;     // mask values refreshed per L2 trip
 constexpr int PCL_BIAS = 0x4000;
 constexpr int PCL_EVMAX = 512;     // un-vote pixel list entries per chunk
+#ifdef LUMINA_PPHT_PROFILE
 #define PCL_TICK(i) do { const long long t__ = clock64(); tph[i] += t__ - tc0; tc0 = t__; } while (0)
+#else
+#define PCL_TICK(i) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // When a CTA can also hold the page's edge mask as a bitmask (h*w/8 bytes) next
@@ -36,12 +40,48 @@ constexpr int PCL_EVMAX = 512;     // un-vote pixel list entries per chunk
 // locally (the walk is deterministic given the mask), so events need no cluster barrier, no L2 round
 // trips and no published pixel list.  The only cross-CTA traffic is 32 keys per batch over DSMEM.
 // ---------------------------------------------------------------------------------------------
+// cvRound(x*cos + y*sin) + half_rho.  The float -> int conversion (round half to even) is done by adding
+// 1.5 * 2^23: exact for |v| < 2^22 (rho never exceeds 2 * 65535), and it stays off the quarter-rate
+// conversion pipe.
+__device__ __forceinline__ int pcl_round(float v) {
+    return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
+}
 __device__ __forceinline__ int pcl_rho(float fx, float fy, float c, float s, int half_rho) {
-    return __float2int_rn(__fadd_rn(__fmul_rn(fx, c), __fmul_rn(fy, s))) + half_rho;
+    return pcl_round(__fadd_rn(__fmul_rn(fx, c), __fmul_rn(fy, s))) + half_rho;
+}
+
+// ---- cluster key exchange: remote shared-memory stores that complete a transaction barrier -------
+__device__ __forceinline__ uint32_t pcl_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t pcl_mapa(uint32_t cta_addr, int cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void pcl_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pcl_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pcl_st_async(uint32_t cluster_addr, uint32_t value, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(cluster_addr), "r"(value), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void pcl_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PCL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PCL_DONE;\n"
+        "bra PCL_WAIT;\n"
+        "PCL_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 struct PphtLmParams {
-    const uint8_t *edges;    // [n][h][w] the Canny output (nonzero = edge)
+    const uint32_t *bits;    // [n][bits_stride] edge bitmask (raster bit order), built by ppht_bitmask_kernel
+    int bits_stride;         // words per page (multiple of 4)
     uint32_t *gbits;         // [n][8][(h*w+31)/32] per-CTA private edge bitmasks in L2 (LM=false variant only)
     const uint32_t *order;
     const int *count;
@@ -49,26 +89,28 @@ struct PphtLmParams {
     const int *step;
     const int *rho_lo;
     const int *cell_off;
+    const int *page_order;   // [n] pages in launch order (heaviest first), or null
     int32_t *lines, *nlines, *stats;
     long long *stats_ll;
     int h, w, numangle, numrho, theta_per_cta, slice_cells;
     int threshold, line_length, line_gap, max_lines;
 };
 
-// apply `sign` (+1 vote / -1 take back) for up to 4 points at once on this thread's theta row.
-// Loads are issued together; duplicates inside the group are resolved in registers so the values
-// equal the sequential ones.  Returns the post-update values in v[].
-__device__ __forceinline__ void pcl_group_update(unsigned short *row, const int r[4], int cnt, int sign, int v[4]) {
+// apply `sign` (+1 vote / -1 take back) for up to 4 points at once on this thread's theta row.  Entries
+// with r < 0 are inactive (and pairwise distinct, so they never look like duplicates).  Loads are issued
+// together; duplicates inside the group are resolved in registers so the values equal the sequential
+// ones.  Returns the post-update values in v[].
+__device__ __forceinline__ void pcl_group_update(unsigned short *row, const int r[4], int sign, int v[4]) {
     int a[4];
 #pragma unroll
-    for (int g = 0; g < 4; g++) a[g] = g < cnt ? (int)row[r[g]] : 0;
+    for (int g = 0; g < 4; g++) a[g] = r[g] >= 0 ? (int)row[r[g]] : 0;
     v[0] = a[0] + sign;
     v[1] = a[1] + sign * (1 + (r[1] == r[0]));
     v[2] = a[2] + sign * (1 + (r[2] == r[0]) + (r[2] == r[1]));
     v[3] = a[3] + sign * (1 + (r[3] == r[0]) + (r[3] == r[1]) + (r[3] == r[2]));
 #pragma unroll
     for (int g = 0; g < 4; g++)
-        if (g < cnt) row[r[g]] = (unsigned short)v[g];  // in order: a later duplicate carries the larger count
+        if (r[g] >= 0) row[r[g]] = (unsigned short)v[g];  // in order: a later duplicate carries the final count
 }
 
 // Every CTA of the cluster owns a private copy of the page's edge bitmask and replays each line event on
@@ -78,21 +120,30 @@ __device__ __forceinline__ void pcl_group_update(unsigned short *row, const int 
 // LM = false: the copy lives in L2 (81 KB per CTA at 678x960, 10 MB per 64-page batch); mask reads cost an
 //             L2 round trip, but large pages (bitmask > shared memory) are covered and the slices of a
 //             678x960 page fit 2 CTAs.
+// Per batch of 32 points of the visiting order:
+//   votes   : the row warps compute the 32 rho values of their theta row up front (independent), then
+//             apply them in order, 4 at a time; a row that reaches the threshold posts its key
+//             (value << 16 | first theta) with a shared-memory atomicMax -- rows below the threshold
+//             (almost all) post nothing, so there is no per-point reduction;
+//   exchange: warp 0 sends the CTA's 32 keys to every CTA of the cluster (DSMEM), one cluster barrier;
+//   events  : warp 0 alone walks, tests and clears the lines that are not "good" (both directions
+//             interleaved in one warp, no CTA barrier); the CTA joins only for a good line (un-vote by
+//             all threads) or when later points of the batch have to take their votes back.
 template <bool LM>
 __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const PphtLmParams p) {
     cg::cluster_group cl = cg::this_cluster();
     const int CS = (int)cl.num_blocks();
     const int rank = (int)cl.block_rank();
-    const int page = blockIdx.x / CS;
+    const int page = p.page_order ? p.page_order[blockIdx.x / CS] : (int)(blockIdx.x / CS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = p.h * p.w;
-    const uint8_t *edges = p.edges + (size_t)page * px;
-    const int nwords_all = (px + 31) >> 5;
-    uint32_t *gbits = LM ? nullptr : p.gbits + ((size_t)page * 8 + rank) * nwords_all;
+    const uint32_t *bits = p.bits + (size_t)page * p.bits_stride;
+    uint32_t *gbits = LM ? nullptr : p.gbits + ((size_t)page * 8 + rank) * p.bits_stride;
     const uint32_t *order = p.order + (size_t)page * px;
     int32_t *lines = p.lines + (size_t)page * p.max_lines * 4;
     const int N = p.count[page];
     const int half_rho = (p.numrho - 1) / 2;
+    const int thr_b = p.threshold + PCL_BIAS;
 
     extern __shared__ __align__(16) unsigned char dynsm[];
     unsigned short *acc = reinterpret_cast<unsigned short *>(dynsm);                              // [slice_cells]
@@ -106,14 +157,14 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
         else atomicAnd(gbits + (bidx >> 5), ~(1u << (bidx & 31)));  // result unused: RED to L2
     };
     __shared__ uint32_t ordbuf[PCL_ORD];
-    __shared__ uint32_t wkeys[PCL_THREADS / 32][PCL_B];   // [row warp][compact slot of the live point]
+    __shared__ uint32_t hkey[2][PCL_B];                  // [parity][compact slot]: best key of the rows that reached the threshold
     __shared__ float2 lpt[PCL_THREADS / 32][PCL_B];      // per-warp compact table of the batch's live points (x, y)
     __shared__ uint32_t keys[2][8][PCL_B];
     __shared__ uint32_t setbits[2][PPHT_MAXWIN];
     __shared__ uint32_t evpx[PCL_EVMAX];
     __shared__ int ev_n, ev_end[2], ev_ex[2], ev_ey[2], ev_done[2];
-    __shared__ float s_cos[PCL_THREADS], s_sin[PCL_THREADS];  // row tables for the all-thread un-vote
-    __shared__ int s_rlo[PCL_THREADS], s_coff[PCL_THREADS];
+    __shared__ int s_status, s_ks, s_maxn;
+    __shared__ __align__(8) unsigned long long xbar[2];  // key-exchange transaction barriers, one per batch parity
     __shared__ int s_step[192 * 3];  // per-theta walk direction table (xflag, dx0, dy0)
 
     const int th0 = rank * p.theta_per_cta;
@@ -125,22 +176,42 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     int rlo = 0;
     unsigned short *row = acc;
     if (has_row) { cth = p.trig[theta * 2]; sth = p.trig[theta * 2 + 1]; rlo = p.rho_lo[theta]; row = acc + p.cell_off[theta]; }
-    s_cos[tid] = cth; s_sin[tid] = sth; s_rlo[tid] = rlo; s_coff[tid] = has_row ? p.cell_off[theta] : 0;
+    if (tid < 2 * PCL_B) hkey[tid / PCL_B][tid % PCL_B] = 0u;
+    if (tid == 0) {
+        pcl_mbar_init(pcl_smem_u32(&xbar[0]), 1);
+        pcl_mbar_init(pcl_smem_u32(&xbar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int i = tid; i < p.slice_cells; i += PCL_THREADS) acc[i] = (unsigned short)PCL_BIAS;
     for (int i = tid; i < p.numangle * 3; i += PCL_THREADS) s_step[i] = p.step[i];
-    // bitmask of the edge map (raster bit order), built from global memory once
-    const int nwords = (px + 31) >> 5;
-    for (int wd = warp; wd < nwords; wd += PCL_THREADS / 32) {
-        const int q = wd * 32 + lane;
-        const bool e = q < px && __ldg(edges + q) != 0;
-        const unsigned b = __ballot_sync(0xffffffffu, e);
-        if (lane == 0) { if (LM) mbits[wd] = b; else __stcg(gbits + wd, b); }
+    // private copy of the page's edge bitmask (128-bit loads; bits_stride is a multiple of 4 words)
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bits);
+        uint4 *dst = LM ? reinterpret_cast<uint4 *>(mbits) : reinterpret_cast<uint4 *>(gbits);
+        const int nq = (((px + 31) >> 5) + 3) >> 2;
+        for (int i = tid; i < nq; i += PCL_THREADS) {
+            const uint4 v = __ldg(src + i);
+            if (LM) dst[i] = v; else __stcg(dst + i, v);
+        }
+    }
+    // un-vote mapping: thread = (row ut, pixel phase us); the row constants stay in registers
+    const int nthpad = row_warps * 32;
+    const int ugroups = nthpad > 0 ? PCL_THREADS / nthpad : 0;
+    const int ut = nthpad > 0 ? tid % nthpad : 0, us = nthpad > 0 ? tid / nthpad : 0;
+    const bool uact = us < ugroups && ut < nth;
+    float ucos = 0.f, usin = 0.f;
+    int ubase = 0;
+    if (uact) {
+        ucos = p.trig[(th0 + ut) * 2]; usin = p.trig[(th0 + ut) * 2 + 1];
+        ubase = p.cell_off[th0 + ut] - p.rho_lo[th0 + ut] + half_rho;
     }
 
     int pos = 0, buf_lo = 0, buf_hi = 0;
     int nl = 0, n_votes = 0, n_events = 0, n_batches = 0;
+#ifdef LUMINA_PPHT_PROFILE
     long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tc0 = clock64();
+#endif
     __syncthreads();
     cl.sync();
     PCL_TICK(9);
@@ -161,130 +232,168 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
         const uint32_t mypt = lane < nb ? ordbuf[pos + lane - buf_lo] : 0u;
         const int myx = (int)(mypt & 0xffffu), myy = (int)(mypt >> 16);
         const int mybit = myy * p.w + myx;
-        const bool mylive = lane < nb && mask_set(mybit);
+        bool mylive = false;
+        if (warp < row_warps || warp == 0) mylive = lane < nb && mask_set(mybit);
         const unsigned livebits = __ballot_sync(0xffffffffu, mylive);
-        const float myfx = (float)myx, myfy = (float)myy;
-        // ---- votes: groups of 4 live points, all rows of this warp in lock step ----
         const int nlive = __popc(livebits);
         const int myslot = __popc(livebits & ((1u << lane) - 1u));
+        // ---- votes: all rho values first (independent), then groups of 4 in order ----
+        int rr[PCL_B];
         if (warp < row_warps) {
-            if (mylive) lpt[warp][myslot] = make_float2(myfx, myfy);
+            if (mylive) lpt[warp][myslot] = make_float2((float)myx, (float)myy);
             __syncwarp();
-            for (int j0 = 0; j0 < nlive; j0 += 4) {
-                const int cnt = min(4, nlive - j0);
-                int r[4], v[4];
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    r[g] = -1 - g;
-                    if (g < cnt) {
-                        const float2 q = lpt[warp][j0 + g];
-                        r[g] = pcl_rho(q.x, q.y, cth, sth, half_rho) - rlo;
-                    }
-                }
-                if (has_row) pcl_group_update(row, r, cnt, +1, v);
+            for (int j = 0; j < PCL_B; j++) {  // branch-free: entries past nlive hold stale coordinates, masked below
+                const float2 q = lpt[warp][j];
+                const int r = pcl_rho(q.x, q.y, cth, sth, half_rho) - rlo;
+                rr[j] = (j < nlive && has_row) ? r : -1 - (j & 3);
+            }
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    if (g < cnt) {
-                        uint32_t key = has_row ? (((uint32_t)v[g] << 16) | (uint32_t)(65535 - theta)) : 0u;
-                        key = __reduce_max_sync(0xffffffffu, key);
-                        if (lane == 0) wkeys[warp][j0 + g] = key;
+            for (int j0 = 0; j0 < PCL_B; j0 += 4) {
+                if (j0 < nlive) {
+                    int v[4];
+                    pcl_group_update(row, &rr[j0], +1, v);  // inactive entries come back far below the threshold
+                    const bool h0 = v[0] >= thr_b, h1 = v[1] >= thr_b, h2 = v[2] >= thr_b, h3 = v[3] >= thr_b;
+                    if (h0 | h1 | h2 | h3) {
+                        const uint32_t kth = (uint32_t)(65535 - theta);
+                        if (h0) atomicMax(&hkey[par][j0 + 0], ((uint32_t)v[0] << 16) | kth);
+                        if (h1) atomicMax(&hkey[par][j0 + 1], ((uint32_t)v[1] << 16) | kth);
+                        if (h2) atomicMax(&hkey[par][j0 + 2], ((uint32_t)v[2] << 16) | kth);
+                        if (h3) atomicMax(&hkey[par][j0 + 3], ((uint32_t)v[3] << 16) | kth);
                     }
                 }
             }
         }
         __syncthreads();
         PCL_TICK(1);
-        // ---- combine the row warps, publish this CTA's 32 keys to every CTA of the cluster ----
+        // ---- exchange: this CTA's 32 keys go to every CTA of the cluster as asynchronous remote stores that
+        // complete the receiver's transaction barrier; only warp 0 waits (no cluster-wide barrier, no fence) ----
         if (warp == 0) {
-            uint32_t key = 0;
-            if ((livebits >> lane) & 1u)
-                for (int wv = 0; wv < row_warps; wv++) key = max(key, wkeys[wv][myslot]);
-            for (int c = 0; c < CS; c++) *cl.map_shared_rank(&keys[par][rank][lane], c) = key;
+            const uint32_t key = ((livebits >> lane) & 1u) ? hkey[par][myslot] : 0u;
+            __syncwarp();
+            hkey[par][lane] = 0u;  // next used two batches from now
+            const uint32_t bar = pcl_smem_u32(&xbar[par]);
+            if (lane == 0) pcl_mbar_expect_tx(bar, (uint32_t)(CS * PCL_B * 4));
+            const uint32_t slot = pcl_smem_u32(&keys[par][rank][lane]);
+            for (int c = 0; c < CS; c++) pcl_st_async(pcl_mapa(slot, c), key, pcl_mapa(bar, c));
+            PCL_TICK(2);
+            pcl_mbar_wait(bar, (uint32_t)(((n_batches - 1) >> 1) & 1));
         }
-        PCL_TICK(2);
-        cl.sync();
         PCL_TICK(3);
-        // every lane k holds the cluster-wide key (exact sequential value, first theta) of point k
-        uint32_t g = 0;
-        if (lane < nb)
-            for (int c = 0; c < CS; c++) g = max(g, keys[par][c][lane]);
-        const bool reaches = g != 0u && (int)(g >> 16) - PCL_BIAS >= p.threshold;
-        int scan_lo = 0;
-        bool restart = false;
+        // ---- events: warp 0 handles every line that is not good on its own ----
         // A line that turns out "not good" only clears mask pixels: the votes of the later batch points and
         // therefore their exact values stay valid, so the scan continues inside the same batch.  Only a good
         // line (un-votes) or a cleared batch point forces the later points to be taken back and replayed.
-        for (;;) {
-            const unsigned hits = __ballot_sync(0xffffffffu, reaches && lane >= scan_lo) & livebits;
-            if (!hits) break;
-            const int ks = __ffs(hits) - 1;
-            const uint32_t gkey = __shfl_sync(0xffffffffu, g, ks);
-            n_events++;
-            const int ej = __shfl_sync(0xffffffffu, myx, ks), ei = __shfl_sync(0xffffffffu, myy, ks);
-            const int max_n = 65535 - (int)(gkey & 0xffffu);
-            const int shift = 16;
-            const int xflag = s_step[max_n * 3], dx0 = s_step[max_n * 3 + 1], dy0 = s_step[max_n * 3 + 2];
-            int x0 = ej, y0 = ei;
-            if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
-            else x0 = (x0 << shift) + (1 << (shift - 1));
-            // ---- walk 1: warp d follows direction d on this CTA's mask copy ----
-            if (warp < 2) {
-                const int d = warp;
-                const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
-                int gap = 0, ek = 0, base = 0, win = 0;
-                for (;; base += 32, win++) {
+        if (warp == 0) {
+            uint32_t g = 0;
+            if (lane < nb)
+                for (int c = 0; c < CS; c++) g = max(g, keys[par][c][lane]);
+            const bool reaches = g != 0u && (int)(g >> 16) >= thr_b;
+            int scan_lo = 0, status = 0, ks = 0, max_n = 0;
+            for (;;) {
+                const unsigned hits = __ballot_sync(0xffffffffu, reaches && lane >= scan_lo) & livebits;
+                if (!hits) break;
+                ks = __ffs(hits) - 1;
+                const uint32_t gkey = __shfl_sync(0xffffffffu, g, ks);
+                n_events++;
+                const int ej = __shfl_sync(0xffffffffu, myx, ks), ei = __shfl_sync(0xffffffffu, myy, ks);
+                max_n = 65535 - (int)(gkey & 0xffffu);
+                const int shift = 16;
+                const int xflag = s_step[max_n * 3], dx0 = s_step[max_n * 3 + 1], dy0 = s_step[max_n * 3 + 2];
+                int x0 = ej, y0 = ei;
+                if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
+                else x0 = (x0 << shift) + (1 << (shift - 1));
+                // walk both directions, 32 positions per step each
+                int gap[2] = {0, 0}, ek[2] = {0, 0};
+                bool fin[2] = {false, false};
+                for (int base = 0, win = 0; !(fin[0] && fin[1]); base += 32, win++) {
                     const int kp = base + lane;
-                    const int X = x0 + kp * dx, Y = y0 + kp * dy;
-                    const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                    const bool inb = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
-                    const int bidx = i1 * p.w + j1;
-                    const bool st = inb && mask_set(bidx);
-                    const unsigned bset = __ballot_sync(0xffffffffu, st);
-                    if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset;
-                    const unsigned below = bset & ((2u << lane) - 1u);
-                    const int gk = below ? lane - (31 - __clz(below)) : gap + lane + 1;
-                    const bool brk = !inb || (!st && gk > p.line_gap);
-                    const unsigned bbrk = __ballot_sync(0xffffffffu, brk);
-                    if (bbrk) {
-                        const int fb = __ffs(bbrk) - 1;
-                        const unsigned sb = fb ? (bset & ((1u << fb) - 1u)) : 0u;
-                        if (sb) ek = base + 31 - __clz(sb);
-                        break;
+                    bool inb[2], st[2];
+                    unsigned bset[2];
+#pragma unroll
+                    for (int d = 0; d < 2; d++) {
+                        const int X = d ? x0 - kp * dx0 : x0 + kp * dx0, Y = d ? y0 - kp * dy0 : y0 + kp * dy0;
+                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
+                        inb[d] = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
+                        st[d] = !fin[d] && inb[d] && mask_set(i1 * p.w + j1);
                     }
-                    if (bset) { ek = base + 31 - __clz(bset); gap = __clz(bset); }
-                    else gap += 32;
+#pragma unroll
+                    for (int d = 0; d < 2; d++) bset[d] = __ballot_sync(0xffffffffu, st[d]);
+#pragma unroll
+                    for (int d = 0; d < 2; d++) {
+                        if (fin[d]) continue;
+                        if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset[d];
+                        const unsigned below = bset[d] & ((2u << lane) - 1u);
+                        const int gk = below ? lane - (31 - __clz(below)) : gap[d] + lane + 1;
+                        const bool brk = !inb[d] || (!st[d] && gk > p.line_gap);
+                        const unsigned bbrk = __ballot_sync(0xffffffffu, brk);
+                        if (bbrk) {
+                            const int fb = __ffs(bbrk) - 1;
+                            const unsigned sb = fb ? (bset[d] & ((1u << fb) - 1u)) : 0u;
+                            if (sb) ek[d] = base + 31 - __clz(sb);
+                            fin[d] = true;
+                        } else if (bset[d]) { ek[d] = base + 31 - __clz(bset[d]); gap[d] = __clz(bset[d]); }
+                        else gap[d] += 32;
+                    }
                 }
-                if (lane == 0) {
-                    const int X = x0 + ek * dx, Y = y0 + ek * dy;
-                    ev_end[d] = ek;
-                    ev_ex[d] = xflag ? X : (X >> shift);
-                    ev_ey[d] = xflag ? (Y >> shift) : Y;
+                int ex[2], ey[2];
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    const int X = d ? x0 - ek[d] * dx0 : x0 + ek[d] * dx0, Y = d ? y0 - ek[d] * dy0 : y0 + ek[d] * dy0;
+                    ex[d] = xflag ? X : (X >> shift);
+                    ey[d] = xflag ? (Y >> shift) : Y;
                 }
-            }
-            __syncthreads();
-            const bool good = abs(ev_ex[1] - ev_ex[0]) >= p.line_length || abs(ev_ey[1] - ev_ey[0]) >= p.line_length;
-            if (!good) {
-                if (warp < 2) {  // clear the segment (start pixel included by direction 0)
-                    const int d = warp;
-                    const int dx = d ? -dx0 : dx0, dy = d ? -dy0 : dy0;
-                    const int end_d = ev_end[d];
-                    for (int base = 0, win = 0; base <= end_d; base += 32, win++) {
-                        unsigned bset = setbits[d][win < PPHT_MAXWIN ? win : PPHT_MAXWIN - 1];
-                        const int rem = end_d - base;
-                        if (rem < 31) bset &= (2u << rem) - 1u;
-                        if (bset & (1u << lane)) {
+                const bool good = abs(ex[1] - ex[0]) >= p.line_length || abs(ey[1] - ey[0]) >= p.line_length;
+                if (good) {
+                    if (lane == 0) {
+                        ev_end[0] = ek[0]; ev_ex[0] = ex[0]; ev_ey[0] = ey[0];
+                        ev_end[1] = ek[1]; ev_ex[1] = ex[1]; ev_ey[1] = ey[1];
+                    }
+                    status = 2;
+                    break;
+                }
+                __syncwarp();
+                // clear the segment (start pixel included by direction 0)
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    for (int base = 0, win = 0; base <= ek[d]; base += 32, win++) {
+                        unsigned bs = setbits[d][win < PPHT_MAXWIN ? win : PPHT_MAXWIN - 1];
+                        const int rem = ek[d] - base;
+                        if (rem < 31) bs &= (2u << rem) - 1u;
+                        if (bs & (1u << lane)) {
                             const int kp = base + lane;
-                            const int X = x0 + kp * dx, Y = y0 + kp * dy;
+                            const int X = d ? x0 - kp * dx0 : x0 + kp * dx0, Y = d ? y0 - kp * dy0 : y0 + kp * dy0;
                             const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                            const int bidx = i1 * p.w + j1;
-                            mask_clear(bidx);
+                            mask_clear(i1 * p.w + j1);
                         }
                     }
                 }
-            } else {
+                __syncwarp();
+                // did the cleared segment take one of the later batch points?
+                const bool stilllive = lane < nb && mask_set(mybit);
+                const unsigned later = ks < 31 ? ~((2u << ks) - 1u) : 0u;
+                const unsigned nowlive = __ballot_sync(0xffffffffu, stilllive);
+                if ((livebits ^ nowlive) & later) { status = 1; break; }
+                scan_lo = ks + 1;
+            }
+            if (lane == 0) { s_status = status; s_ks = ks; s_maxn = max_n; }
+        }
+        __syncthreads();
+        PCL_TICK(4);
+        const int status = s_status;
+        if (status != 0) {
+            const int ks = s_ks;
+            if (status == 2) {
                 // good line: warps 0/1 clear their direction and list the set pixels; then ALL threads
                 // un-vote (pixel, row) pairs with shared-memory atomics on the packed 16-bit counters
                 // (subtraction commutes; rows keep their owner for everything order-sensitive).
+                const int max_n = s_maxn;
+                const int shift = 16;
+                const int xflag = s_step[max_n * 3], dx0 = s_step[max_n * 3 + 1], dy0 = s_step[max_n * 3 + 2];
+                const uint32_t ept = ordbuf[pos + ks - buf_lo];
+                int x0 = (int)(ept & 0xffffu), y0 = (int)(ept >> 16);
+                if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
+                else x0 = (x0 << shift) + (1 << (shift - 1));
                 int done[2] = {0, 0};  // windows already consumed per direction (chunked when the list is full)
                 for (;;) {
                     if (tid == 0) ev_n = 0;
@@ -320,13 +429,12 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                     __syncthreads();
                     const int npx = ev_n;
                     done[0] = ev_done[0]; done[1] = ev_done[1];
-                    // (pixel, row) pairs spread over every thread of the CTA
-                    if (nth > 0) {
+                    // (pixel, row) pairs: thread (ut, us) takes pixels us, us + ugroups, ... on row ut
+                    if (uact) {
                         uint32_t *acc32 = reinterpret_cast<uint32_t *>(acc);
-                        for (int pr = tid; pr < npx * nth; pr += PCL_THREADS) {
-                            const int q = pr / nth, t = pr - q * nth;
+                        for (int q = us; q < npx; q += ugroups) {
                             const uint32_t pt = evpx[q];
-                            const int cell = s_coff[t] + pcl_rho((float)(pt & 0xffffu), (float)(pt >> 16), s_cos[t], s_sin[t], half_rho) - s_rlo[t];
+                            const int cell = ubase + pcl_round(__fadd_rn(__fmul_rn((float)(pt & 0xffffu), ucos), __fmul_rn((float)(pt >> 16), usin)));
                             atomicSub(&acc32[cell >> 1], (cell & 1) ? 0x10000u : 1u);
                         }
                     }
@@ -340,48 +448,36 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 }
                 nl++;
             }
-            __syncthreads();  // mask clears visible; ev_* / setbits may be reused
-            // did the cleared segment take one of the later batch points?
-            const bool stilllive = lane < nb && mask_set(mybit);
-            const unsigned later = ks < 31 ? ~((2u << ks) - 1u) : 0u;
-            const unsigned nowlive = __ballot_sync(0xffffffffu, stilllive);
-            if (good || ((livebits ^ nowlive) & later)) {
-                // ---- later live points of the batch take their votes back and are replayed ----
-                if (warp < row_warps) {
-                    const int first = __popc(livebits & ((2u << ks) - 1u));  // compact slot of the first later point
-                    for (int j0 = first; j0 < nlive; j0 += 4) {
-                        const int cnt = min(4, nlive - j0);
-                        int r[4], v[4];
+            // ---- later live points of the batch take their votes back and are replayed ----
+            if (warp < row_warps && has_row) {
+                const int first = __popc(livebits & ((2u << ks) - 1u));  // compact slot of the first later point
 #pragma unroll
-                        for (int gq = 0; gq < 4; gq++) {
-                            r[gq] = -1 - gq;
-                            if (gq < cnt) {
-                                const float2 q = lpt[warp][j0 + gq];
-                                r[gq] = pcl_rho(q.x, q.y, cth, sth, half_rho) - rlo;
-                            }
-                        }
-                        if (has_row) pcl_group_update(row, r, cnt, -1, v);
+                for (int j0 = 0; j0 < PCL_B; j0 += 4) {
+                    if (j0 + 4 > first && j0 < nlive) {
+                        int r4[4], v[4];
+#pragma unroll
+                        for (int g = 0; g < 4; g++) r4[g] = (j0 + g >= first) ? rr[j0 + g] : -1 - g;
+                        pcl_group_update(row, r4, -1, v);
                     }
                 }
-                n_votes += __popc(livebits & ((2u << ks) - 1u));
-                pos += ks + 1;
-                restart = true;
-                __syncthreads();
-                break;
             }
-            scan_lo = ks + 1;
-        }
-        PCL_TICK(5);
-        if (!restart) {
+            n_votes += __popc(livebits & ((2u << ks) - 1u));
+            pos += ks + 1;
+            __syncthreads();
+        } else {
             n_votes += __popc(livebits);
             pos += nb;
         }
+        PCL_TICK(5);
     }
+    cl.sync();  // no CTA leaves while a peer could still address its shared memory
     if (rank == 0 && tid == 0) {
         p.nlines[page] = nl;
         int32_t *st = p.stats + page * 8;
         st[0] = N; st[1] = n_votes; st[2] = n_events; st[3] = nl; st[4] = 1; st[5] = n_batches; st[6] = CS;
+#ifdef LUMINA_PPHT_PROFILE
         for (int i = 0; i < 10; i++) p.stats_ll[page * 10 + i] = tph[i];
+#endif
     }
 }
 

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, ctypes as C
 from ocr_system_b200 import ops, _abi
 L = _abi.lib()
-n = 16
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 pages = ops.synth_pages(n, 3508, 2480, 0)
 small = ops.resize_if_needed(pages, 960)
 edges = ops.canny(small)
