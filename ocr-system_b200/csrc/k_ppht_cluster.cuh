@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     }
 
     int pos = 0, buf_lo = 0, buf_hi = 0;
-    int nl = 0, n_votes = 0, n_events = 0, n_batches = 0;
+    int nl = 0, n_votes = 0, n_events = 0, n_batches = 0, n_fast = 0;
 #ifdef LUMINA_PPHT_PROFILE
     long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tc0 = clock64();
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 const int r = pcl_rho(q.x, q.y, cth, sth, half_rho) - rlo;
                 rr[j] = (j < nlive && has_row) ? r : -1 - (j & 3);
             }
+            PCL_TICK(6);
 #pragma unroll
             for (int j0 = 0; j0 < PCL_B; j0 += 4) {
                 if (j0 < nlive) {
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                     }
                 }
             }
+            PCL_TICK(7);
         }
         __syncthreads();
         PCL_TICK(1);
@@ -289,13 +291,71 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
             if (lane < nb)
                 for (int c = 0; c < CS; c++) g = max(g, keys[par][c][lane]);
             const bool reaches = g != 0u && (int)(g >> 16) >= thr_b;
-            int scan_lo = 0, status = 0, ks = 0, max_n = 0;
-            for (;;) {
-                const unsigned hits = __ballot_sync(0xffffffffu, reaches && lane >= scan_lo) & livebits;
-                if (!hits) break;
+            // every lane prepares the walk of its own point (as if it were the event) in unified 16.16
+            // coordinates: X = xs + k * dxs, Y = ys + k * dys, pixel = (X >> 16, Y >> 16); unsigned
+            // arithmetic, so a coordinate that leaves the page on the low side wraps above w / h.
+            uint32_t my_xs = 0, my_ys = 0, my_dxs = 0, my_dys = 0;
+            if (reaches) {
+                const int mn = 65535 - (int)(g & 0xffffu);
+                const int xf = s_step[mn * 3], d0 = s_step[mn * 3 + 1], d1 = s_step[mn * 3 + 2];
+                my_xs = ((uint32_t)myx << 16) + (xf ? 0u : 0x8000u);
+                my_ys = ((uint32_t)myy << 16) + (xf ? 0x8000u : 0u);
+                my_dxs = xf ? ((uint32_t)d0 << 16) : (uint32_t)d0;
+                my_dys = xf ? (uint32_t)d1 : ((uint32_t)d1 << 16);
+            }
+            const int gap_m = p.line_gap + 1;  // unset run length that stops a walk
+            int status = 0, ks = 0, max_n = 0;
+            unsigned hits = __ballot_sync(0xffffffffu, reaches) & livebits;
+            for (; hits; hits &= ~((2u << ks) - 1u)) {
                 ks = __ffs(hits) - 1;
-                const uint32_t gkey = __shfl_sync(0xffffffffu, g, ks);
                 n_events++;
+                // ---- fast path: both directions end inside their first 32 positions ----
+                {
+                    const uint32_t xs = __shfl_sync(0xffffffffu, my_xs, ks), ys = __shfl_sync(0xffffffffu, my_ys, ks);
+                    const uint32_t dxs = __shfl_sync(0xffffffffu, my_dxs, ks), dys = __shfl_sync(0xffffffffu, my_dys, ks);
+                    const uint32_t ja = (xs + lane * dxs) >> 16, ia = (ys + lane * dys) >> 16;
+                    const uint32_t jb = (xs - lane * dxs) >> 16, ib = (ys - lane * dys) >> 16;
+                    const bool ina = ja < (uint32_t)p.w && ia < (uint32_t)p.h, inb = jb < (uint32_t)p.w && ib < (uint32_t)p.h;
+                    const int bia = (int)(ia * p.w + ja), bib = (int)(ib * p.w + jb);
+                    const bool sa = ina && mask_set(bia), sb = inb && mask_set(bib);
+                    const unsigned Ba = __ballot_sync(0xffffffffu, sa), Bb = __ballot_sync(0xffffffffu, sb);
+                    const unsigned Oa = __ballot_sync(0xffffffffu, !ina), Ob = __ballot_sync(0xffffffffu, !inb);
+                    // bit k of R: positions k - line_gap .. k are all unset (position 0, the start pixel, is set)
+                    unsigned Ra = 0, Rb = 0;
+                    if (gap_m <= 32) {
+                        Ra = ~Ba; Rb = ~Bb;
+                        int len = 1;
+                        for (; 2 * len <= gap_m; len *= 2) { Ra &= Ra << len; Rb &= Rb << len; }
+                        if (len < gap_m) { Ra &= Ra << (gap_m - len); Rb &= Rb << (gap_m - len); }
+                    }
+                    const unsigned brka = Ra | Oa, brkb = Rb | Ob;
+                    if (brka != 0u && brkb != 0u) {
+                        n_fast++;
+                        const unsigned keepa = Ba & ((1u << (__ffs(brka) - 1)) - 1u), keepb = Bb & ((1u << (__ffs(brkb) - 1)) - 1u);
+                        const int eka = 31 - __clz(keepa), ekb = 31 - __clz(keepb);  // bit 0 is always set
+                        const int exa = (int)((xs + eka * dxs) >> 16), eya = (int)((ys + eka * dys) >> 16);
+                        const int exb = (int)((xs - ekb * dxs) >> 16), eyb = (int)((ys - ekb * dys) >> 16);
+                        if (abs(exb - exa) >= p.line_length || abs(eyb - eya) >= p.line_length) {
+                            if (lane == 0) {
+                                ev_end[0] = eka; ev_ex[0] = exa; ev_ey[0] = eya; setbits[0][0] = Ba;
+                                ev_end[1] = ekb; ev_ex[1] = exb; ev_ey[1] = eyb; setbits[1][0] = Bb;
+                            }
+                            max_n = 65535 - (int)(__shfl_sync(0xffffffffu, g, ks) & 0xffffu);
+                            status = 2;
+                            break;
+                        }
+                        if ((keepa >> lane) & 1u) mask_clear(bia);
+                        if ((keepb >> lane) & 1u & (lane != 0)) mask_clear(bib);
+                        __syncwarp();
+                        const bool stilllive = lane < nb && mask_set(mybit);
+                        const unsigned later = ks < 31 ? ~((2u << ks) - 1u) : 0u;
+                        const unsigned nowlive = __ballot_sync(0xffffffffu, stilllive);
+                        if ((livebits ^ nowlive) & later) { status = 1; break; }
+                        continue;
+                    }
+                }
+                // ---- general path: walks longer than one window ----
+                const uint32_t gkey = __shfl_sync(0xffffffffu, g, ks);
                 const int ej = __shfl_sync(0xffffffffu, myx, ks), ei = __shfl_sync(0xffffffffu, myy, ks);
                 max_n = 65535 - (int)(gkey & 0xffffu);
                 const int shift = 16;
@@ -374,7 +434,6 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 const unsigned later = ks < 31 ? ~((2u << ks) - 1u) : 0u;
                 const unsigned nowlive = __ballot_sync(0xffffffffu, stilllive);
                 if ((livebits ^ nowlive) & later) { status = 1; break; }
-                scan_lo = ks + 1;
             }
             if (lane == 0) { s_status = status; s_ks = ks; s_maxn = max_n; }
         }
@@ -474,7 +533,7 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     if (rank == 0 && tid == 0) {
         p.nlines[page] = nl;
         int32_t *st = p.stats + page * 8;
-        st[0] = N; st[1] = n_votes; st[2] = n_events; st[3] = nl; st[4] = 1; st[5] = n_batches; st[6] = CS;
+        st[0] = N; st[1] = n_votes; st[2] = n_events; st[3] = nl; st[4] = 1; st[5] = n_batches; st[6] = CS; st[7] = n_fast;
 #ifdef LUMINA_PPHT_PROFILE
         for (int i = 0; i < 10; i++) p.stats_ll[page * 10 + i] = tph[i];
 #endif

@@ -23,6 +23,6 @@ wsn = ws.cpu().numpy()
 st = wsn[stats_off:stats_off + n*32].view(np.int32).reshape(n, 8)
 ll_off = stats_off + ((n*32 + 7) & ~7)
 ph = wsn[ll_off: ll_off + n*80].view(np.int64).reshape(n, 10)
-print("page  N     votes  events good batches | Mcycles: fill vote reduce sync1 rollback event")
+print("page  N     votes  events good batches | Mcycles: fill vote(sync) send wait events good+rollback rho groups")
 for i in range(n):
-    print(i, st[i, :4].tolist(), st[i, 5], "|", (ph[i, :6] / 1e6).round(1).tolist(), "total", round(ph[i].sum()/1e6, 1))
+    print(i, st[i, :4].tolist(), st[i, 5], "fast", st[i, 7], "|", (ph[i, :8] / 1e6).round(1).tolist(), "total", round(ph[i].sum()/1e6, 1))
