@@ -144,6 +144,16 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
     const int N = p.count[page];
     const int half_rho = (p.numrho - 1) / 2;
     const int thr_b = p.threshold + PCL_BIAS;
+    // unset run length that stops a walk, and the shift schedule that detects such runs in a 32-bit window
+    // (doubling steps 1, 2, 4, ... then the remainder; six 5-bit fields, unused ones 0)
+    const int gap_m = p.line_gap + 1;
+    const bool gap_small = gap_m <= 32;
+    uint32_t gap_sh = 0;
+    if (gap_small) {
+        int len = 1, i = 0;
+        for (; 2 * len <= gap_m; len *= 2) gap_sh |= (uint32_t)len << (5 * i++);
+        if (len < gap_m) gap_sh |= (uint32_t)(gap_m - len) << (5 * i);
+    }
 
     extern __shared__ __align__(16) unsigned char dynsm[];
     unsigned short *acc = reinterpret_cast<unsigned short *>(dynsm);                              // [slice_cells]
@@ -303,128 +313,115 @@ __global__ void __launch_bounds__(PCL_THREADS) ppht_cluster_lm_kernel(const Ppht
                 my_dxs = xf ? ((uint32_t)d0 << 16) : (uint32_t)d0;
                 my_dys = xf ? (uint32_t)d1 : ((uint32_t)d1 << 16);
             }
-            const int gap_m = p.line_gap + 1;  // unset run length that stops a walk
             int status = 0, ks = 0, max_n = 0;
             unsigned hits = __ballot_sync(0xffffffffu, reaches) & livebits;
             for (; hits; hits &= ~((2u << ks) - 1u)) {
                 ks = __ffs(hits) - 1;
                 n_events++;
-                // ---- fast path: both directions end inside their first 32 positions ----
+                // ---- walk: both directions together, 32 positions per step; everything that decides is
+                // warp-uniform bit arithmetic on the ballots ----
+                const uint32_t xs = __shfl_sync(0xffffffffu, my_xs, ks), ys = __shfl_sync(0xffffffffu, my_ys, ks);
+                const uint32_t dxs = __shfl_sync(0xffffffffu, my_dxs, ks), dys = __shfl_sync(0xffffffffu, my_dys, ks);
+                // window 0 (positions 0..31 of both directions) is straight-line code: most events end here
+                int bia0, bib0, eka, ekb, carrya, carryb;
+                unsigned Wa0, Wb0;
+                bool fina, finb;
                 {
-                    const uint32_t xs = __shfl_sync(0xffffffffu, my_xs, ks), ys = __shfl_sync(0xffffffffu, my_ys, ks);
-                    const uint32_t dxs = __shfl_sync(0xffffffffu, my_dxs, ks), dys = __shfl_sync(0xffffffffu, my_dys, ks);
                     const uint32_t ja = (xs + lane * dxs) >> 16, ia = (ys + lane * dys) >> 16;
                     const uint32_t jb = (xs - lane * dxs) >> 16, ib = (ys - lane * dys) >> 16;
                     const bool ina = ja < (uint32_t)p.w && ia < (uint32_t)p.h, inb = jb < (uint32_t)p.w && ib < (uint32_t)p.h;
-                    const int bia = (int)(ia * p.w + ja), bib = (int)(ib * p.w + jb);
-                    const bool sa = ina && mask_set(bia), sb = inb && mask_set(bib);
+                    bia0 = (int)(ia * p.w + ja); bib0 = (int)(ib * p.w + jb);
+                    const bool sa = ina && mask_set(bia0), sb = inb && mask_set(bib0);
                     const unsigned Ba = __ballot_sync(0xffffffffu, sa), Bb = __ballot_sync(0xffffffffu, sb);
                     const unsigned Oa = __ballot_sync(0xffffffffu, !ina), Ob = __ballot_sync(0xffffffffu, !inb);
-                    // bit k of R: positions k - line_gap .. k are all unset (position 0, the start pixel, is set)
-                    unsigned Ra = 0, Rb = 0;
-                    if (gap_m <= 32) {
-                        Ra = ~Ba; Rb = ~Bb;
-                        int len = 1;
-                        for (; 2 * len <= gap_m; len *= 2) { Ra &= Ra << len; Rb &= Rb << len; }
-                        if (len < gap_m) { Ra &= Ra << (gap_m - len); Rb &= Rb << (gap_m - len); }
+                    // warp-uniform: bit k of R = the gap_m positions ending at k are all unset (position 0 is set)
+                    unsigned Ra = gap_small ? ~Ba : 0u, Rb = gap_small ? ~Bb : 0u;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        const int sh = (gap_sh >> (5 * i)) & 31;
+                        Ra &= Ra << sh; Rb &= Rb << sh;
                     }
                     const unsigned brka = Ra | Oa, brkb = Rb | Ob;
-                    if (brka != 0u && brkb != 0u) {
-                        n_fast++;
-                        const unsigned keepa = Ba & ((1u << (__ffs(brka) - 1)) - 1u), keepb = Bb & ((1u << (__ffs(brkb) - 1)) - 1u);
-                        const int eka = 31 - __clz(keepa), ekb = 31 - __clz(keepb);  // bit 0 is always set
-                        const int exa = (int)((xs + eka * dxs) >> 16), eya = (int)((ys + eka * dys) >> 16);
-                        const int exb = (int)((xs - ekb * dxs) >> 16), eyb = (int)((ys - ekb * dys) >> 16);
-                        if (abs(exb - exa) >= p.line_length || abs(eyb - eya) >= p.line_length) {
-                            if (lane == 0) {
-                                ev_end[0] = eka; ev_ex[0] = exa; ev_ey[0] = eya; setbits[0][0] = Ba;
-                                ev_end[1] = ekb; ev_ex[1] = exb; ev_ey[1] = eyb; setbits[1][0] = Bb;
-                            }
-                            max_n = 65535 - (int)(__shfl_sync(0xffffffffu, g, ks) & 0xffffu);
-                            status = 2;
-                            break;
+                    fina = brka != 0u; finb = brkb != 0u;
+                    Wa0 = fina ? Ba & ((1u << (__ffs(brka) - 1)) - 1u) : Ba;   // bit 0 (the start pixel) is always set
+                    Wb0 = finb ? Bb & ((1u << (__ffs(brkb) - 1)) - 1u) : Bb;
+                    eka = 31 - __clz(Wa0); ekb = 31 - __clz(Wb0);
+                    carrya = __clz(Wa0); carryb = __clz(Wb0);
+                }
+                const bool one_window = fina && finb;
+                if (!one_window) {
+                    // ---- longer walks: further windows, same warp-uniform logic plus the run carried over ----
+                    if (lane == 0) { setbits[0][0] = Wa0; setbits[1][0] = Wb0; }
+                    for (int base = 32, win = 1;; base += 32, win++) {
+                        const uint32_t k = (uint32_t)(base + lane);
+                        const uint32_t ja = (xs + k * dxs) >> 16, ia = (ys + k * dys) >> 16;
+                        const uint32_t jb = (xs - k * dxs) >> 16, ib = (ys - k * dys) >> 16;
+                        const bool ina = fina || (ja < (uint32_t)p.w && ia < (uint32_t)p.h);
+                        const bool inb = finb || (jb < (uint32_t)p.w && ib < (uint32_t)p.h);
+                        const bool sa = !fina && ina && mask_set((int)(ia * p.w + ja));
+                        const bool sb = !finb && inb && mask_set((int)(ib * p.w + jb));
+                        const unsigned Ba = __ballot_sync(0xffffffffu, sa), Bb = __ballot_sync(0xffffffffu, sb);
+                        const unsigned Oa = __ballot_sync(0xffffffffu, !ina), Ob = __ballot_sync(0xffffffffu, !inb);
+                        unsigned Ra = gap_small ? ~Ba : 0u, Rb = gap_small ? ~Bb : 0u;
+#pragma unroll
+                        for (int i = 0; i < 6; i++) {
+                            const int sh = (gap_sh >> (5 * i)) & 31;
+                            Ra &= Ra << sh; Rb &= Rb << sh;
                         }
-                        if ((keepa >> lane) & 1u) mask_clear(bia);
-                        if ((keepb >> lane) & 1u & (lane != 0)) mask_clear(bib);
-                        __syncwarp();
-                        const bool stilllive = lane < nb && mask_set(mybit);
-                        const unsigned later = ks < 31 ? ~((2u << ks) - 1u) : 0u;
-                        const unsigned nowlive = __ballot_sync(0xffffffffu, stilllive);
-                        if ((livebits ^ nowlive) & later) { status = 1; break; }
-                        continue;
+                        if (!fina) {
+                            // a run that started in the previous window completes at position gap_m - carry - 1
+                            const int need = gap_m - carrya, z = Ba ? __ffs(Ba) - 1 : 32;
+                            unsigned brk = Ra | Oa;
+                            if (need <= 32 && z >= need) brk |= 1u << (need - 1);
+                            unsigned Wa = Ba;
+                            if (brk) { Wa = Ba & ((1u << (__ffs(brk) - 1)) - 1u); fina = true; }
+                            if (Wa) { eka = base + 31 - __clz(Wa); carrya = __clz(Wa); }
+                            else carrya += 32;
+                            if (lane == 0 && win < PPHT_MAXWIN) setbits[0][win] = Wa;
+                        }
+                        if (!finb) {
+                            const int need = gap_m - carryb, z = Bb ? __ffs(Bb) - 1 : 32;
+                            unsigned brk = Rb | Ob;
+                            if (need <= 32 && z >= need) brk |= 1u << (need - 1);
+                            unsigned Wb = Bb;
+                            if (brk) { Wb = Bb & ((1u << (__ffs(brk) - 1)) - 1u); finb = true; }
+                            if (Wb) { ekb = base + 31 - __clz(Wb); carryb = __clz(Wb); }
+                            else carryb += 32;
+                            if (lane == 0 && win < PPHT_MAXWIN) setbits[1][win] = Wb;
+                        }
+                        if (fina && finb) break;
                     }
                 }
-                // ---- general path: walks longer than one window ----
-                const uint32_t gkey = __shfl_sync(0xffffffffu, g, ks);
-                const int ej = __shfl_sync(0xffffffffu, myx, ks), ei = __shfl_sync(0xffffffffu, myy, ks);
-                max_n = 65535 - (int)(gkey & 0xffffu);
-                const int shift = 16;
-                const int xflag = s_step[max_n * 3], dx0 = s_step[max_n * 3 + 1], dy0 = s_step[max_n * 3 + 2];
-                int x0 = ej, y0 = ei;
-                if (xflag) y0 = (y0 << shift) + (1 << (shift - 1));
-                else x0 = (x0 << shift) + (1 << (shift - 1));
-                // walk both directions, 32 positions per step each
-                int gap[2] = {0, 0}, ek[2] = {0, 0};
-                bool fin[2] = {false, false};
-                for (int base = 0, win = 0; !(fin[0] && fin[1]); base += 32, win++) {
-                    const int kp = base + lane;
-                    bool inb[2], st[2];
-                    unsigned bset[2];
-#pragma unroll
-                    for (int d = 0; d < 2; d++) {
-                        const int X = d ? x0 - kp * dx0 : x0 + kp * dx0, Y = d ? y0 - kp * dy0 : y0 + kp * dy0;
-                        const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                        inb[d] = j1 >= 0 && j1 < p.w && i1 >= 0 && i1 < p.h;
-                        st[d] = !fin[d] && inb[d] && mask_set(i1 * p.w + j1);
-                    }
-#pragma unroll
-                    for (int d = 0; d < 2; d++) bset[d] = __ballot_sync(0xffffffffu, st[d]);
-#pragma unroll
-                    for (int d = 0; d < 2; d++) {
-                        if (fin[d]) continue;
-                        if (lane == 0 && win < PPHT_MAXWIN) setbits[d][win] = bset[d];
-                        const unsigned below = bset[d] & ((2u << lane) - 1u);
-                        const int gk = below ? lane - (31 - __clz(below)) : gap[d] + lane + 1;
-                        const bool brk = !inb[d] || (!st[d] && gk > p.line_gap);
-                        const unsigned bbrk = __ballot_sync(0xffffffffu, brk);
-                        if (bbrk) {
-                            const int fb = __ffs(bbrk) - 1;
-                            const unsigned sb = fb ? (bset[d] & ((1u << fb) - 1u)) : 0u;
-                            if (sb) ek[d] = base + 31 - __clz(sb);
-                            fin[d] = true;
-                        } else if (bset[d]) { ek[d] = base + 31 - __clz(bset[d]); gap[d] = __clz(bset[d]); }
-                        else gap[d] += 32;
-                    }
-                }
-                int ex[2], ey[2];
-#pragma unroll
-                for (int d = 0; d < 2; d++) {
-                    const int X = d ? x0 - ek[d] * dx0 : x0 + ek[d] * dx0, Y = d ? y0 - ek[d] * dy0 : y0 + ek[d] * dy0;
-                    ex[d] = xflag ? X : (X >> shift);
-                    ey[d] = xflag ? (Y >> shift) : Y;
-                }
-                const bool good = abs(ex[1] - ex[0]) >= p.line_length || abs(ey[1] - ey[0]) >= p.line_length;
-                if (good) {
+                if (one_window) n_fast++;
+                const int exa = (int)((xs + (uint32_t)eka * dxs) >> 16), eya = (int)((ys + (uint32_t)eka * dys) >> 16);
+                const int exb = (int)((xs - (uint32_t)ekb * dxs) >> 16), eyb = (int)((ys - (uint32_t)ekb * dys) >> 16);
+                if (abs(exb - exa) >= p.line_length || abs(eyb - eya) >= p.line_length) {
                     if (lane == 0) {
-                        ev_end[0] = ek[0]; ev_ex[0] = ex[0]; ev_ey[0] = ey[0];
-                        ev_end[1] = ek[1]; ev_ex[1] = ex[1]; ev_ey[1] = ey[1];
+                        ev_end[0] = eka; ev_ex[0] = exa; ev_ey[0] = eya;
+                        ev_end[1] = ekb; ev_ex[1] = exb; ev_ey[1] = eyb;
+                        if (one_window) { setbits[0][0] = Wa0; setbits[1][0] = Wb0; }
                     }
+                    max_n = 65535 - (int)(__shfl_sync(0xffffffffu, g, ks) & 0xffffu);
                     status = 2;
                     break;
                 }
-                __syncwarp();
-                // clear the segment (start pixel included by direction 0)
-#pragma unroll
-                for (int d = 0; d < 2; d++) {
-                    for (int base = 0, win = 0; base <= ek[d]; base += 32, win++) {
-                        unsigned bs = setbits[d][win < PPHT_MAXWIN ? win : PPHT_MAXWIN - 1];
-                        const int rem = ek[d] - base;
-                        if (rem < 31) bs &= (2u << rem) - 1u;
-                        if (bs & (1u << lane)) {
-                            const int kp = base + lane;
-                            const int X = d ? x0 - kp * dx0 : x0 + kp * dx0, Y = d ? y0 - kp * dy0 : y0 + kp * dy0;
-                            const int j1 = xflag ? X : (X >> shift), i1 = xflag ? (Y >> shift) : Y;
-                            mask_clear(i1 * p.w + j1);
+                // ---- not good: clear the segment (start pixel by direction a); window 0 from registers ----
+                if ((Wa0 >> lane) & 1u) mask_clear(bia0);
+                if (((Wb0 >> lane) & 1u) && lane != 0) mask_clear(bib0);
+                if (eka >= 32 || ekb >= 32) {
+                    __syncwarp();
+                    for (int base = 32, win = 1; base <= eka; base += 32, win++) {
+                        const unsigned bs = setbits[0][win < PPHT_MAXWIN ? win : PPHT_MAXWIN - 1];
+                        if ((bs >> lane) & 1u) {
+                            const uint32_t k = (uint32_t)(base + lane);
+                            mask_clear((int)(((ys + k * dys) >> 16) * p.w + ((xs + k * dxs) >> 16)));
+                        }
+                    }
+                    for (int base = 32, win = 1; base <= ekb; base += 32, win++) {
+                        const unsigned bs = setbits[1][win < PPHT_MAXWIN ? win : PPHT_MAXWIN - 1];
+                        if ((bs >> lane) & 1u) {
+                            const uint32_t k = (uint32_t)(base + lane);
+                            mask_clear((int)(((ys - k * dys) >> 16) * p.w + ((xs - k * dxs) >> 16)));
                         }
                     }
                 }
