@@ -122,55 +122,118 @@ __global__ void __launch_bounds__(1024) ppht_collect_kernel(const uint8_t *__res
 }
 
 // ---- B: visiting order (cv::RNG MWC + swap-remove), data independent ------------
-__global__ void __launch_bounds__(32) ppht_order_kernel(uint32_t *__restrict__ nz_all, uint32_t *__restrict__ order_all,
-                                                        const int *__restrict__ count, int px) {
-    const int page = blockIdx.x, lane = threadIdx.x;
+// One CTA per page; warp 0 runs the sequential process, 32 draws per step:
+//   * the MWC chain of the next step is computed while the memory operations of this step are in flight;
+//   * a step whose 32 draws do not interact (distinct indices, none inside the 32 tail slots) is one
+//     parallel gather + scatter;
+//   * a step with interacting draws is replayed in order on a 64-slot shared-memory image of the cells it
+//     touches (one memory round trip, not one per draw);
+//   * once the live list fits in shared memory (cap entries) it is moved there by the whole CTA and the
+//     remaining steps never leave the SM.
+constexpr int PORD_THREADS = 256;
+__global__ void __launch_bounds__(PORD_THREADS) ppht_order_kernel(uint32_t *__restrict__ nz_all, uint32_t *__restrict__ order_all,
+                                                                  const int *__restrict__ count, int px, int cap) {
+    extern __shared__ uint32_t sA[];          // [cap] the live list once it fits
+    __shared__ uint32_t V[64], O[32];
+    __shared__ int slot_of[32];
+    const int page = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *nz = nz_all + (size_t)page * px;
     uint32_t *order = order_all + (size_t)page * px;
+    const int N = count[page];
     unsigned long long state = ~0ull;
-    int cnt = count[page];
-    int i = 0;
-    // the 32 draws of a step; computed one step ahead so the MWC chain overlaps the L2 round trips
+    int cnt = N, i = 0;
+    // the 32 draws of a step (lane k gets draw k); chained multiply-with-carry, fully unrolled for full steps
     auto draw = [&](int c) -> int {
-        const int b = c < 32 ? c : 32;
         unsigned long long s = state;
         uint32_t my_r = 0;
-        for (int k = 0; k < b; k++) {
-            s = (unsigned long long)(uint32_t)s * 4164903690ull + (s >> 32);
-            if (k == lane) my_r = (uint32_t)s;
+        if (c >= 32) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                s = (unsigned long long)(uint32_t)s * 4164903690ull + (s >> 32);
+                if (k == lane) my_r = (uint32_t)s;
+            }
+        } else {
+            for (int k = 0; k < c; k++) {
+                s = (unsigned long long)(uint32_t)s * 4164903690ull + (s >> 32);
+                if (k == lane) my_r = (uint32_t)s;
+            }
         }
         state = s;
-        return lane < b ? (int)(my_r % (uint32_t)(c - lane)) : -1 - lane;
+        return lane < c ? (int)(my_r % (uint32_t)(c - lane)) : -1 - lane;
     };
-    int idx = cnt > 0 ? draw(cnt) : 0;
+    int idx = 0;
+    if (warp == 0) {
+        idx = cnt > 0 ? draw(cnt) : 0;
+        // ---- phase A: the list is still larger than shared memory, cells live in L2 ----
+        while (cnt > cap) {
+            const int b = 32;  // cap >= 32, so every step here is full
+            const unsigned same = __match_any_sync(0xffffffffu, idx);
+            const int first = __ffs(same) - 1;
+            const bool in_tail = idx >= cnt - b;
+            const bool slow = __any_sync(0xffffffffu, first != lane || in_tail);
+            const uint32_t pt = __ldcg(nz + idx), tl = __ldcg(nz + (cnt - 1 - lane));      // in flight ...
+            const int idx_next = draw(cnt - b);                                            // ... while the next draws are computed
+            if (!slow) {
+                __stcg(nz + idx, tl);
+                __stcg(order + i + lane, pt);
+            } else {
+                // replay in order on the touched cells: slots 0..31 = the tail cells, 32+k = first use of an index
+                const int slot = in_tail ? cnt - 1 - idx : 32 + first;
+                V[lane] = tl;
+                if (!in_tail && first == lane) V[32 + lane] = pt;
+                slot_of[lane] = slot;
+                __syncwarp();
+                if (lane == 0) {
+                    for (int k = 0; k < b; k++) {
+                        const int sk = slot_of[k];
+                        const uint32_t o = V[sk];
+                        V[sk] = V[k];
+                        O[k] = o;
+                    }
+                }
+                __syncwarp();
+                __stcg(order + i + lane, O[lane]);
+                if (!in_tail && first == lane) __stcg(nz + idx, V[32 + lane]);   // tail cells die with this step
+            }
+            __syncwarp();
+            cnt -= b;
+            i += b;
+            idx = idx_next;
+        }
+    }
+    __syncthreads();
+    // ---- phase B: the remaining list lives in shared memory ----
+    const int nB = N > cap ? N - ((N - cap + 31) / 32) * 32 : N;   // entries left when phase A ends (same on all threads)
+    for (int t = tid; t < nB; t += PORD_THREADS) sA[t] = __ldcg(nz + t);
+    __syncthreads();
+    if (warp != 0) return;
     while (cnt > 0) {
         const int b = cnt < 32 ? cnt : 32;
         const bool act = lane < b;
-        const int my_cnt = cnt - lane;
         const unsigned same = __match_any_sync(0xffffffffu, idx);
-        const bool c1 = act && (same & ((1u << lane) - 1u)) != 0u;
-        const bool c2 = act && idx >= cnt - b;
-        const bool slow = __any_sync(0xffffffffu, c1 || c2);
+        const int first = __ffs(same) - 1;
+        const bool slow = __any_sync(0xffffffffu, act && (first != lane || idx >= cnt - b));
         uint32_t pt = 0, tl = 0;
-        if (!slow && act) { pt = __ldcg(nz + idx); tl = __ldcg(nz + (my_cnt - 1)); }  // in flight ...
-        const int idx_next = cnt - b > 0 ? draw(cnt - b) : 0;                        // ... while the next draws are computed
-        if (slow) {
-            // exact sequential replay of this step
-            for (int k = 0; k < b; k++) {
-                const int ik = __shfl_sync(0xffffffffu, idx, k);
-                if (lane == 0) {
-                    const uint32_t p1 = __ldcg(nz + ik);
-                    const uint32_t t1 = __ldcg(nz + (cnt - k - 1));
-                    __stcg(nz + ik, t1);
-                    __stcg(order + i + k, p1);
+        if (act) { pt = sA[idx]; tl = sA[cnt - 1 - lane]; }
+        const int idx_next = cnt - b > 0 ? draw(cnt - b) : 0;
+        if (!slow) {
+            __syncwarp();
+            if (act) { sA[idx] = tl; __stcg(order + i + lane, pt); }
+        } else {
+            slot_of[lane] = idx;
+            __syncwarp();
+            if (lane == 0) {
+                for (int k = 0; k < b; k++) {
+                    const int ik = slot_of[k];
+                    const uint32_t o = sA[ik];
+                    sA[ik] = sA[cnt - 1 - k];
+                    O[k] = o;
                 }
             }
             __syncwarp();
-        } else {
-            __syncwarp();
-            if (act) { __stcg(nz + idx, tl); __stcg(order + i + lane, pt); }
-            __syncwarp();
+            if (act) __stcg(order + i + lane, O[lane]);
         }
+        __syncwarp();
         cnt -= b;
         i += b;
         idx = idx_next;
@@ -579,7 +642,19 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
     ppht_bitmask_kernel<<<dim3((unsigned)((L.bits_stride + 255) / 256), (unsigned)n), 256, 0, st>>>(
         d_edges, (uint32_t *)(ws + L.bits_off), h * w, (int)L.bits_stride);
     LUMINA_KERNEL_CHECK("ppht_bitmask_kernel");
-    ppht_order_kernel<<<n, 32, 0, st>>>((uint32_t *)(ws + L.nz_off), (uint32_t *)(ws + L.order_off), (const int *)(ws + L.count_off), h * w);
+    {
+        int max_optin = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        LUMINA_CUDA_TRY(cudaFuncGetAttributes(&fa, ppht_order_kernel));
+        long long cap = ((long long)max_optin - (long long)fa.sharedSizeBytes - 256) / 4;
+        if (cap > (long long)h * w) cap = (long long)h * w;
+        if (cap < 32) cap = 32;
+        LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 4)));
+        ppht_order_kernel<<<n, PORD_THREADS, (size_t)cap * 4, st>>>((uint32_t *)(ws + L.nz_off), (uint32_t *)(ws + L.order_off),
+                                                                    (const int *)(ws + L.count_off), h * w, (int)cap);
+    }
     LUMINA_KERNEL_CHECK("ppht_order_kernel");
     const bool lpt_order = n > 1 && n <= 8192;
     if (lpt_order) {
