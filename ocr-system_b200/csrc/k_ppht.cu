@@ -22,6 +22,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -776,17 +777,34 @@ LUMINA_API double lumina_median_angle_host(const int32_t *h_lines, int nlines) {
 // getRotationMatrix2D((w//2, h//2), median, 1.0).
 LUMINA_API void lumina_deskew_decide_host(const int32_t *h_lines, const int32_t *h_nlines, int n, int lines_stride,
                                           int h, int w, double *h_angles, double *h_m6, uint8_t *h_apply) {
-    for (int i = 0; i < n; i++) {
+    auto one = [=](int i) {
         h_angles[i] = 0.0;
         h_apply[i] = 0;
         for (int k = 0; k < 6; k++) h_m6[(size_t)i * 6 + k] = 0.0;
         const int nl = h_nlines[i] < lines_stride ? h_nlines[i] : lines_stride;
-        if (nl <= 0) continue;
+        if (nl <= 0) return;
         const double a = lumina_median_angle_host(h_lines + (size_t)i * lines_stride * 4, nl);
-        if (fabs(a) < 0.5) { h_angles[i] = a; continue; }
-        if (fabs(a) > 45) continue;
+        if (fabs(a) < 0.5) { h_angles[i] = a; return; }
+        if (fabs(a) > 45) return;
         h_angles[i] = a;
         h_apply[i] = 1;
         lumina_rotation_matrix_host((double)(w / 2), (double)(h / 2), a, 1.0, h_m6 + (size_t)i * 6);
+    };
+    // ~25 us per page (libm atan2 per line + sort); the GPU waits for this, so a batch is spread over a few
+    // host threads (pages are independent; same libm, same result)
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = n / 8;
+    if (nt > 8) nt = 8;
+    if (hw > 0 && nt > (int)hw) nt = (int)hw;
+    if (nt <= 1) {
+        for (int i = 0; i < n; i++) one(i);
+        return;
     }
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (int t = 0; t < nt; t++)
+        pool.emplace_back([=]() {
+            for (int i = t; i < n; i += nt) one(i);
+        });
+    for (auto &th : pool) th.join();
 }

@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(256) resize_strip_dp4a_kernel(const ResizeDp4a
     }
     const uint8_t *src_end = p.src + p.src_total;
     int next_oy = oy0;
+    __shared__ int s_oy_end;
 
     for (int r0 = ys; r0 < ye; r0 += RB) {
         const int nrows = min(RB, ye - r0);
@@ -361,28 +362,55 @@ __global__ void __launch_bounds__(256) resize_strip_dp4a_kernel(const ResizeDp4a
                 }
             }
         }
+        if (tid == 255) {  // which output rows have their whole tap window in the ring after this chunk
+            const int rows_done = r0 + nrows;
+            int oe = next_oy;
+            while (oe < oy1 && p.by[oe * 2] + p.by[oe * 2 + 1] <= rows_done) oe++;
+            s_oy_end = oe;
+        }
         __syncthreads();
-        // ---- vertical pass ----
-        const int rows_done = r0 + nrows;
-        int oy_end = next_oy;
-        while (oy_end < oy1 && p.by[oy_end * 2] + p.by[oy_end * 2 + 1] <= rows_done) oy_end++;
-        const int ntask = (oy_end - next_oy) * ROWB;
+        // ---- vertical pass: a thread owns 4 adjacent byte columns of one output row (one 128-bit ring
+        // load per 4 taps x 4 columns, the row's coefficient words shared by the 4 columns) ----
+        const int oy_end = s_oy_end;
+        constexpr int COL4 = ROWB / 4;
+        const int ntask = (oy_end - next_oy) * COL4;
         const int row_bytes = p.out_w * 3;
         for (int task = tid; task < ntask; task += 256) {
-            const int oy = next_oy + task / ROWB, col = task % ROWB;
-            const int bcol = ox0 * 3 + col;
+            const int orow = task / COL4, c4 = task - orow * COL4;
+            const int oy = next_oy + orow;
+            const int bcol = ox0 * 3 + c4 * 4;
             if (bcol >= row_bytes) continue;
             const int ymin = p.by[oy * 2];
             const uint32_t *k = p.cyp + (size_t)oy * 3 * p.kyw;
-            int s0 = 0, s1 = 0, s2 = 0;
+            int s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+            int rgrp = (ymin >> 2) & (RINGG - 1);
             for (int j = 0; j < p.kyw; j++) {
-                const uint32_t v = ring[(size_t)(((ymin >> 2) + j) & (RINGG - 1)) * ROWB + col];
-                s0 = (int)__dp4a(v, __ldg(k + j), (uint32_t)s0);
-                s1 = (int)__dp4a(v, __ldg(k + p.kyw + j), (uint32_t)s1);
-                s2 = dp4a_u8s8(v, __ldg(k + 2 * p.kyw + j), s2);
+                const uint4 v = *reinterpret_cast<const uint4 *>(ring + (size_t)rgrp * ROWB + c4 * 4);
+                const uint32_t k0 = __ldg(k + j), k1 = __ldg(k + p.kyw + j), k2 = __ldg(k + 2 * p.kyw + j);
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    s0[q] = (int)__dp4a(vv[q], k0, (uint32_t)s0[q]);
+                    s1[q] = (int)__dp4a(vv[q], k1, (uint32_t)s1[q]);
+                    s2[q] = dp4a_u8s8(vv[q], k2, s2[q]);
+                }
+                rgrp = (rgrp + 1) & (RINGG - 1);
             }
-            dst[(size_t)oy * row_bytes + bcol] =
-                clip8((int)((1u << (PREC_BITS - 1)) + (uint32_t)s0 + ((uint32_t)s1 << 8) + ((uint32_t)s2 << 16)));
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                o[q] = clip8((int)((1u << (PREC_BITS - 1)) + (uint32_t)s0[q] + ((uint32_t)s1[q] << 8) + ((uint32_t)s2[q] << 16)));
+            uint8_t *dp = dst + (size_t)oy * row_bytes + bcol;
+            if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 3) == 0) {
+                *reinterpret_cast<uint32_t *>(dp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+            } else if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 1) == 0) {
+                *reinterpret_cast<uint16_t *>(dp) = (uint16_t)(o[0] | (o[1] << 8));
+                *reinterpret_cast<uint16_t *>(dp + 2) = (uint16_t)(o[2] | (o[3] << 8));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (bcol + q < row_bytes) dp[q] = (uint8_t)o[q];
+            }
         }
         next_oy = oy_end;
         __syncthreads();

@@ -22,6 +22,8 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
+import threading
+
 import torch
 
 from . import ops
@@ -106,18 +108,32 @@ class PagePipeline:
         det, shape_list = t.run("det_resize_normalize", lambda: ops.det_resize_normalize(x, self.det_limit))
         return PageBatchResult(x, angles, gray, binary, det, shape_list, t)
 
+    _rotate_stage = None   # pinned staging for the line lists (shape-keyed)
+
     @staticmethod
     def _rotate(x: torch.Tensor, lines: torch.Tensor, nlines: torch.Tensor):
         """Host median / gating (image_preprocessing.py:414-439) + one warp launch.  The only
         host synchronisation of the chain: the line lists (a few KB per page) come back."""
         n, h, w = x.shape[0], x.shape[1], x.shape[2]
-        nl = nlines.cpu().numpy()
+        # one pinned staging buffer, one synchronisation: counts and line lists come back together
+        key = (n, lines.shape[1], x.device, threading.get_ident())
+        st = PagePipeline._rotate_stage
+        if st is None or st[0] != key:
+            st = PagePipeline._rotate_stage = (key, torch.empty(n, dtype=torch.int32, pin_memory=True),
+                                               torch.empty((n, lines.shape[1], 4), dtype=torch.int32, pin_memory=True))
+        _, nl_pin, ln_pin = st
+        nl_pin.copy_(nlines, non_blocking=True)
+        ln_pin.copy_(lines, non_blocking=True)
+        torch.cuda.current_stream(x.device).synchronize()
+        nl = nl_pin.numpy()
         keep = int(nl.max(initial=0))
         if keep > lines.shape[1]:  # truncated list: redo the Hough stage with room for every line
             edges = ops.canny(x, 50, 150)
             lines, nlines = ops.hough_lines_p(edges, max_lines=keep)
             nl = nlines.cpu().numpy()
-        lh = lines[:, : max(keep, 1)].cpu().numpy()
+            lh = lines.cpu().numpy()
+        else:
+            lh = ln_pin.numpy()
         angles, mats, apply = ops.deskew_decide(lh, nl, h, w)
         if apply.any():
             x = ops.warp_affine_cubic(x, mats, apply)
