@@ -153,6 +153,21 @@ int lumina_db_postprocess(const float *d_pred, int n, int h, int w, float thresh
 int lumina_db_mask_ccl(const float *d_pred, int n, int h, int w, float thresh, uint8_t *d_mask,
                        int32_t *d_labels, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- "next" row: reading order / line merge ---------------- */
+/* backend/utils/ocr_postprocessor.py:101-182 (group_into_lines + sort_and_merge_lines) for a batch of
+ * pages.  Page p owns boxes [d_offsets[p], d_offsets[p+1]) of d_boxes [total][4][2] f64 (x, y quads in
+ * detector order; Python floats) and d_conf [total] f64.  Outputs, all indexed from d_offsets[p]:
+ *   d_order[k]   = index inside the page of the k-th block in reading order,
+ *   d_line_of[k] = 0-based line of that block (lines top to bottom, blocks left to right),
+ *   d_nlines[p], d_line_conf[l] = mean confidence, d_line_y[l] = mean y_center of line l (f64).
+ * Stable sorts and float64 sums exactly as the reference's Python (sum() as in CPython >= 3.12).
+ * y_tolerance_ratio < 0: every page is ONE line whose input order breaks x ties (sort_and_merge_lines on
+ * lines that were grouped elsewhere).  max_boxes_per_page >= the largest page, <= 4096. */
+int lumina_reading_order(const double *d_boxes, const double *d_conf, const int32_t *d_offsets, int n_pages,
+                         int max_boxes_per_page, double y_tolerance_ratio, int32_t *d_order,
+                         int32_t *d_line_of, int32_t *d_nlines, double *d_line_conf, double *d_line_y,
+                         void *stream);
+
 /* ---- synthetic workloads (bench/test inputs generated in HBM) ------------ */
 /* A4-like text page, seeded by page index; identical bytes to the host
  * generator in include/lumina_synth.h compiled for the CPU. */

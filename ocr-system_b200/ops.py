@@ -368,3 +368,44 @@ def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: 
                                     int(max_candidates), int(min_size), hw.ctypes.data_as(C.c_void_p), _ptr(boxes),
                                     _ptr(scores), _ptr(counts), _ptr(ws), wsb, _stream()))
     return boxes, scores, counts
+
+
+# --------------------------------------------------------------------------- next row 8f.2
+def reading_order(boxes: torch.Tensor, conf: torch.Tensor, offsets: torch.Tensor, y_tolerance_ratio: float = 0.5,
+                  max_boxes_per_page: Optional[int] = None):
+    """ocr_postprocessor.py:101-182 for a batch of pages.
+
+    boxes  CUDA float64 [total,4,2], conf CUDA float64 [total], offsets int32 [pages+1] (CUDA or host).
+    y_tolerance_ratio < 0: every page is one pre-grouped line (input order breaks x ties).
+    Returns device tensors (order[total] int32, line_of[total] int32, nlines[pages] int32,
+    line_conf[total] f64, line_y[total] f64), all indexed from offsets[p]."""
+    if not boxes.is_cuda or boxes.dtype != torch.float64 or boxes.dim() != 3 or tuple(boxes.shape[1:]) != (4, 2):
+        raise TypeError("reading_order expects CUDA float64 boxes [total,4,2]")
+    if conf.dtype != torch.float64 or not conf.is_cuda or conf.numel() != boxes.shape[0]:
+        raise TypeError("reading_order expects CUDA float64 confidences [total]")
+    off_host = offsets.detach().to("cpu", torch.int32)
+    pages = off_host.numel() - 1
+    if pages < 1 or int(off_host[0]) != 0 or int(off_host[-1]) != boxes.shape[0]:
+        raise ValueError("offsets must run from 0 to the number of boxes")
+    counts = (off_host[1:] - off_host[:-1])
+    if int(counts.min()) < 0:
+        raise ValueError("offsets must be non-decreasing")
+    mb = int(counts.max()) if max_boxes_per_page is None else int(max_boxes_per_page)
+    dev = boxes.device
+    off_dev = off_host.to(dev)
+    b = boxes.contiguous()
+    c = conf.contiguous()
+    total = max(int(b.shape[0]), 1)
+    order = torch.empty(total, dtype=torch.int32, device=dev)
+    line_of = torch.empty(total, dtype=torch.int32, device=dev)
+    nlines = torch.empty(pages, dtype=torch.int32, device=dev)
+    line_conf = torch.empty(total, dtype=torch.float64, device=dev)
+    line_y = torch.empty(total, dtype=torch.float64, device=dev)
+    if b.shape[0] == 0:
+        nlines.zero_()
+        return order[:0], line_of[:0], nlines, line_conf[:0], line_y[:0]
+    with torch.cuda.device(dev):
+        _chk(_L().lumina_reading_order(_ptr(b), _ptr(c), _ptr(off_dev), pages, mb, float(y_tolerance_ratio), _ptr(order),
+                                       _ptr(line_of), _ptr(nlines), _ptr(line_conf), _ptr(line_y), _stream()))
+    n = int(b.shape[0])
+    return order[:n], line_of[:n], nlines, line_conf[:n], line_y[:n]
