@@ -168,6 +168,21 @@ int lumina_reading_order(const double *d_boxes, const double *d_conf, const int3
                          int32_t *d_line_of, int32_t *d_nlines, double *d_line_conf, double *d_line_y,
                          void *stream);
 
+/* ---- "next" row: JPEG encode for compress_for_azure ----------- */
+/* image_preprocessing.py:496-557 (compress_for_azure: image.save(format='JPEG', quality=q, optimize=True) in
+ * a quality loop) and :331-347 (image_to_bytes).  Baseline JPEG of n equally sized RGB pages [n][h][w][3]:
+ * YCbCr 4:2:0, libjpeg's integer (islow) DCT, Annex K quantisers scaled by `quality` (1..100), standard or
+ * per-image optimal Huffman tables -- the same byte stream Pillow / libjpeg-turbo writes for
+ * image.save(format='JPEG', quality=quality, optimize=bool(flags & 1)).
+ * flags bit 1: reuse the DCT coefficients the previous call left in this workspace (same pages, next quality
+ * of the loop).  h_sizes[i] (host) receives the file size of page i; the file itself is written to
+ * h_out + i * out_stride when it fits in out_stride bytes (the reference's "size <= target" test; a page that
+ * does not fit is simply not copied).  Synchronous with respect to `stream`. */
+size_t lumina_jpeg_workspace_bytes(int n, int h, int w);
+int lumina_jpeg_encode_rgb(const uint8_t *d_rgb, int n, int h, int w, int quality, int flags, uint8_t *h_out,
+                           size_t out_stride, int64_t *h_sizes, void *d_workspace, size_t workspace_bytes,
+                           void *stream);
+
 /* ---- synthetic workloads (bench/test inputs generated in HBM) ------------ */
 /* A4-like text page, seeded by page index; identical bytes to the host
  * generator in include/lumina_synth.h compiled for the CPU. */

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "lumina_db_postprocess": (_I, [_P, _I, _I, _I, _F, _D, _D, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "lumina_db_mask_ccl": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "lumina_reading_order": (_I, [_P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P, _P]),
+    "lumina_jpeg_workspace_bytes": (_Z, [_I, _I, _I]),
+    "lumina_jpeg_encode_rgb": (_I, [_P, _I, _I, _I, _I, _I, _P, _Z, _P, _P, _Z, _P]),
     "lumina_synth_pages_u8": (_I, [_P, _I, _I, _I, C.c_uint64, _P]),
 }
 

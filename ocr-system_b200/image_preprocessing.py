@@ -247,28 +247,65 @@ class ImagePreprocessor:
     def adaptive_binarize(self, image: Image.Image) -> Image.Image:
         return self._to_pil(ops.adaptive_binarize(self._to_device(image), 2))
 
+    def compress_pages_for_azure(self, pages: torch.Tensor, target_size_mb: float = 2.0, initial_quality: int = 95,
+                                 min_quality: int = 30) -> List[bytes]:
+        """``compress_for_azure`` (reference :496-557) for a resident batch [N,H,W,3] (or [N,H,W,1], replicated to
+        RGB like ``image.convert('RGB')``): the quality ladder initial..min step 10 runs on the GPU encoder, which
+        writes the byte stream Pillow would (``optimize=True``); the DCT is computed once per batch and
+        re-quantised per quality.  Pages that still exceed the target at ``min_quality`` are Lanczos-shrunk by
+        sqrt(target/current) and encoded once more, as in the reference."""
+        target = int(target_size_mb * 1024 * 1024)
+        if pages.dim() == 3:
+            pages = pages.unsqueeze(-1)
+        if pages.shape[-1] == 1:
+            pages = pages.expand(-1, -1, -1, 3)
+        cur = pages.contiguous()
+        n = cur.shape[0]
+        out: List[Optional[bytes]] = [None] * n
+        todo = list(range(n))
+        enc = self._jpeg_encoder()
+        quality, fresh = initial_quality, True
+        while quality >= min_quality and todo:
+            files, _ = enc.encode(cur, quality, optimize=True, max_bytes=target, reuse_dct=not fresh)
+            fresh = False
+            keep = []
+            for j, i in enumerate(todo):
+                if files[j] is not None:
+                    logger.info(f"Compressed to {len(files[j]) / 1024 / 1024:.2f}MB at quality={quality}")
+                    out[i] = files[j]
+                else:
+                    keep.append(j)
+            if keep and len(keep) < len(todo):
+                cur = cur[keep].contiguous()   # a different batch: its DCT is recomputed at the next quality
+                fresh = True
+            todo = [todo[j] for j in keep]
+            quality -= 10
+        if todo:
+            logger.warning("Quality reduction not enough, also resizing image")
+            _, sizes = enc.encode(cur, min_quality, optimize=False, max_bytes=0)   # reference :543: no optimize here
+            for j, i in enumerate(todo):
+                scale = (target / int(sizes[j])) ** 0.5
+                new_w, new_h = int(cur.shape[2] * scale), int(cur.shape[1] * scale)
+                small = ops.resize_lanczos(cur[j:j + 1], new_w, new_h)
+                out[i] = ops.jpeg_encode(small, min_quality, optimize=True)[0]
+                logger.info(f"Compressed to {len(out[i]) / 1024 / 1024:.2f}MB after resize to {(new_w, new_h)}")
+        return out  # type: ignore[return-value]
+
+    def _jpeg_encoder(self) -> "ops.JpegEncoder":
+        enc = getattr(self, "_jpeg", None)
+        if enc is None:
+            enc = self._jpeg = ops.JpegEncoder()
+        return enc
+
     def compress_for_azure(self, image: Image.Image, target_size_mb: float = 2.0, initial_quality: int = 95,
                            min_quality: int = 30) -> bytes:
-        """JPEG encode-to-size on the host codec (the step after the path).
-        Quality ladder initial..min step 10, then a Lanczos shrink by sqrt(target/current) on the GPU."""
-        target = int(target_size_mb * 1024 * 1024)
+        """Reference :496-557 for one PIL image; the JPEG encoding itself runs on the GPU
+        and returns the bytes Pillow's encoder would."""
         if image.mode in ("RGBA", "P", "L"):
             image = image.convert("RGB")
-        quality = initial_quality
-        while quality >= min_quality:
-            buf = io.BytesIO()
-            image.save(buf, format="JPEG", quality=quality, optimize=True)
-            if buf.tell() <= target:
-                return buf.getvalue()
-            quality -= 10
-        buf = io.BytesIO()
-        image.save(buf, format="JPEG", quality=min_quality)
-        scale = (target / buf.tell()) ** 0.5
-        new_w, new_h = int(image.width * scale), int(image.height * scale)
-        small = self._to_pil(ops.resize_lanczos(self._to_device(image), new_w, new_h))
-        buf = io.BytesIO()
-        small.save(buf, format="JPEG", quality=min_quality, optimize=True)
-        return buf.getvalue()
+        if image.mode != "RGB":
+            raise OSError(f"cannot write mode {image.mode} as JPEG")   # Pillow's own error for unsupported modes
+        return self.compress_pages_for_azure(self._to_device(image), target_size_mb, initial_quality, min_quality)[0]
 
     def preprocess_device(self, x: torch.Tensor, apply_deskew: bool = True, apply_binarize: bool = False,
                           apply_contrast: bool = True, apply_sharpness: bool = True):
@@ -295,7 +332,7 @@ class ImagePreprocessor:
         logger.info(f"Preprocessing image: {img.size}, mode={img.mode}")
         x, _ = self.preprocess_device(self._to_device(img), apply_deskew, apply_binarize, apply_contrast,
                                       apply_sharpness)
-        return self.compress_for_azure(self._to_pil(x), target_size_mb=target_size_mb)
+        return self.compress_pages_for_azure(x, target_size_mb=target_size_mb)[0]
 
 
 class _LazySingleton:

@@ -409,3 +409,48 @@ def reading_order(boxes: torch.Tensor, conf: torch.Tensor, offsets: torch.Tensor
                                        _ptr(line_of), _ptr(nlines), _ptr(line_conf), _ptr(line_y), _stream()))
     n = int(b.shape[0])
     return order[:n], line_of[:n], nlines, line_conf[:n], line_y[:n]
+
+
+# --------------------------------------------------------------------------- next row 8f.1
+class JpegEncoder:
+    """Batched baseline JPEG encoder (image_preprocessing.py:496-557, :331-347): the byte stream Pillow writes
+    for ``image.save(format='JPEG', quality=q, optimize=...)``.  Keeps its workspace (DCT coefficients of the
+    last batch included) so that the quality loop of ``compress_for_azure`` re-quantises instead of
+    re-transforming."""
+
+    def __init__(self):
+        self._ws = None
+        self._key = None
+        self._pages_id = None
+
+    def encode(self, pages: torch.Tensor, quality: int = 95, optimize: bool = False, max_bytes: Optional[int] = None,
+               reuse_dct: bool = False):
+        """pages CUDA uint8 [N,H,W,3] -> (list of bytes-or-None, sizes int64[N]).  A page whose file is larger than
+        ``max_bytes`` comes back as None (its size is still reported)."""
+        x, n, h, w, c = _pages(pages)
+        if c != 3:
+            raise ValueError("the JPEG path encodes RGB pages (the reference converts L / RGBA / P to RGB first)")
+        x = x.contiguous()
+        key = (n, h, w, x.device)
+        wsb = int(_L().lumina_jpeg_workspace_bytes(n, h, w))
+        if self._key != key or self._ws is None:
+            self._ws = _ws(wsb, x.device)
+            self._key = key
+            reuse_dct = False
+        stride = int(max_bytes) if max_bytes is not None else 1024 + 3 * h * w  # a baseline file of real content never gets there
+        out = np.empty((n, stride), np.uint8)
+        sizes = np.zeros(n, np.int64)
+        flags = (1 if optimize else 0) | (2 if reuse_dct else 0)
+        with torch.cuda.device(x.device):
+            _chk(_L().lumina_jpeg_encode_rgb(_ptr(x), n, h, w, int(quality), flags, out.ctypes.data_as(C.c_void_p), stride,
+                                             sizes.ctypes.data_as(C.c_void_p), _ptr(self._ws), wsb, _stream()))
+        files = [out[i, : int(sizes[i])].tobytes() if sizes[i] <= stride else None for i in range(n)]
+        return files, sizes
+
+
+def jpeg_encode(pages: torch.Tensor, quality: int = 95, optimize: bool = False):
+    """One-shot form of :class:`JpegEncoder`: list of JPEG files (bytes), one per page."""
+    files, sizes = JpegEncoder().encode(pages, quality, optimize)
+    if any(f is None for f in files):
+        raise _abi.LuminaError("a JPEG file exceeded the output buffer")
+    return files
