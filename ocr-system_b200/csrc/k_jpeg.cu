@@ -310,35 +310,70 @@ __device__ void jpg_derive(JpegHuff &T) {
     T.nvals = lastp;
 }
 
-// ---- K3: optimal Huffman tables (jchuff.c jpeg_gen_optimal_table), one thread per (page, table) -----
+// ---- K3: optimal Huffman tables (jchuff.c jpeg_gen_optimal_table), one warp per (page, table) ---------
+// The two "smallest frequency, larger symbol on ties" searches of every merge step are warp-parallel (each
+// lane scans 9 of the 257 entries, then a shuffle reduction on (frequency, -symbol) keys); the code-length
+// chains, the length limiting and the canonical code assignment are sequential and run on lane 0.
+__device__ __forceinline__ unsigned long long jpg_warp_min(unsigned long long k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
+        k = t < k ? t : k;
+    }
+    return k;
+}
 __global__ void __launch_bounds__(32) jpeg_opt_table_kernel(const uint32_t *__restrict__ hist, JpegHuff *__restrict__ tables) {
-    if (threadIdx.x != 0) return;
-    const int t = blockIdx.x;  // page * 4 + slot
+    __shared__ uint32_t freq[257 + 31];
+    __shared__ int codesize[257], others[257];
+    const int t = blockIdx.x, lane = threadIdx.x;  // t = page * 4 + slot
     const uint32_t *hp = hist + (size_t)t * 257;
     JpegHuff &T = tables[t];
-    long long freq[257];
-    int codesize[257], others[257];
-    uint8_t bits[33];
-    for (int i = 0; i < 256; i++) { freq[i] = hp[i]; codesize[i] = 0; others[i] = -1; }
-    freq[256] = 1; codesize[256] = 0; others[256] = -1;   // reserves the all-ones code
-    for (int i = 0; i <= 32; i++) bits[i] = 0;
+    for (int i = lane; i < 257 + 31; i += 32) freq[i] = i < 256 ? hp[i] : (i == 256 ? 1u : 0u);   // [256]: reserves the all-ones code
+    for (int i = lane; i < 257; i += 32) { codesize[i] = 0; others[i] = -1; }
+    __syncwarp();
+    constexpr unsigned long long NONE = ~0ull;
     for (;;) {
-        int c1 = -1, c2 = -1;
-        long long v = 1000000000LL;
-        for (int i = 0; i <= 256; i++)
-            if (freq[i] && freq[i] <= v) { v = freq[i]; c1 = i; }      // smallest, larger symbol on ties
-        v = 1000000000LL;
-        for (int i = 0; i <= 256; i++)
-            if (freq[i] && freq[i] <= v && i != c1) { v = freq[i]; c2 = i; }
-        if (c2 < 0) break;
-        freq[c1] += freq[c2];
-        freq[c2] = 0;
-        codesize[c1]++;
-        while (others[c1] >= 0) { c1 = others[c1]; codesize[c1]++; }
-        others[c1] = c2;
-        codesize[c2]++;
-        while (others[c2] >= 0) { c2 = others[c2]; codesize[c2]++; }
+        // key = frequency << 16 | (65535 - symbol): minimum = smallest frequency, larger symbol on ties
+        // (libjpeg's scan keeps the LAST index among equal minima; frequencies above 1e9 are never picked)
+        unsigned long long k1 = NONE;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int i = lane + 32 * j;
+            const uint32_t f = freq[i];
+            if (f && f <= 1000000000u) {
+                const unsigned long long k = ((unsigned long long)f << 16) | (unsigned long long)(65535 - i);
+                k1 = k < k1 ? k : k1;
+            }
+        }
+        k1 = jpg_warp_min(k1);
+        const int c1 = k1 == NONE ? -1 : 65535 - (int)(k1 & 0xffffu);
+        unsigned long long k2 = NONE;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int i = lane + 32 * j;
+            const uint32_t f = freq[i];
+            if (f && f <= 1000000000u && i != c1) {
+                const unsigned long long k = ((unsigned long long)f << 16) | (unsigned long long)(65535 - i);
+                k2 = k < k2 ? k : k2;
+            }
+        }
+        k2 = jpg_warp_min(k2);
+        if (k2 == NONE) break;
+        if (lane == 0) {
+            int a = c1, b = 65535 - (int)(k2 & 0xffffu);
+            freq[a] += freq[b];
+            freq[b] = 0;
+            codesize[a]++;
+            while (others[a] >= 0) { a = others[a]; codesize[a]++; }
+            others[a] = b;
+            codesize[b]++;
+            while (others[b] >= 0) { b = others[b]; codesize[b]++; }
+        }
+        __syncwarp();
     }
+    if (lane != 0) return;
+    uint8_t bits[33];
+    for (int i = 0; i <= 32; i++) bits[i] = 0;
     for (int i = 0; i <= 256; i++)
         if (codesize[i]) bits[codesize[i] > 32 ? 32 : codesize[i]]++;
     for (int i = 32; i > 16; i--) {

@@ -421,7 +421,7 @@ class JpegEncoder:
     def __init__(self):
         self._ws = None
         self._key = None
-        self._pages_id = None
+        self._out = None      # pinned host staging [n, stride]: the D2H copies run at PCIe speed
 
     def encode(self, pages: torch.Tensor, quality: int = 95, optimize: bool = False, max_bytes: Optional[int] = None,
                reuse_dct: bool = False):
@@ -437,14 +437,24 @@ class JpegEncoder:
             self._ws = _ws(wsb, x.device)
             self._key = key
             reuse_dct = False
-        stride = int(max_bytes) if max_bytes is not None else 1024 + 3 * h * w  # a baseline file of real content never gets there
-        out = np.empty((n, stride), np.uint8)
+        # without a cap: room for 1.5 bytes per pixel (quality-95 text pages need ~0.5); a page that does not fit
+        # triggers one re-run with the exact size (the DCT is reused)
+        stride = max(int(max_bytes), 1) if max_bytes is not None else 4096 + (3 * h * w) // 2
         sizes = np.zeros(n, np.int64)
-        flags = (1 if optimize else 0) | (2 if reuse_dct else 0)
-        with torch.cuda.device(x.device):
-            _chk(_L().lumina_jpeg_encode_rgb(_ptr(x), n, h, w, int(quality), flags, out.ctypes.data_as(C.c_void_p), stride,
-                                             sizes.ctypes.data_as(C.c_void_p), _ptr(self._ws), wsb, _stream()))
-        files = [out[i, : int(sizes[i])].tobytes() if sizes[i] <= stride else None for i in range(n)]
+        while True:
+            if self._out is None or self._out.shape[0] < n or self._out.shape[1] < stride:
+                self._out = torch.empty((n, stride), dtype=torch.uint8, pin_memory=True)
+            out = self._out
+            flags = (1 if optimize else 0) | (2 if reuse_dct else 0)
+            with torch.cuda.device(x.device):
+                _chk(_L().lumina_jpeg_encode_rgb(_ptr(x), n, h, w, int(quality), flags, C.c_void_p(out.data_ptr()),
+                                                 int(out.shape[1]), sizes.ctypes.data_as(C.c_void_p), _ptr(self._ws), wsb, _stream()))
+            if max_bytes is not None or int(sizes.max()) <= out.shape[1]:
+                break
+            stride, reuse_dct = int(sizes.max()), True
+        cap = stride if max_bytes is not None else out.shape[1]
+        view = out.numpy()
+        files = [view[i, : int(sizes[i])].tobytes() if sizes[i] <= cap else None for i in range(n)]
         return files, sizes
 
 
