@@ -15,10 +15,11 @@ batched API in ``pipeline.PagePipeline``.
 from __future__ import annotations
 
 import io
+from concurrent.futures import ThreadPoolExecutor
 import logging
 import os
 from pathlib import Path
-from typing import List, Optional, Tuple, Union
+from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -333,6 +334,48 @@ class ImagePreprocessor:
         x, _ = self.preprocess_device(self._to_device(img), apply_deskew, apply_binarize, apply_contrast,
                                       apply_sharpness)
         return self.compress_pages_for_azure(x, target_size_mb=target_size_mb)[0]
+
+
+    def preprocess_pages_for_azure(self, images: Sequence[ImageSource], apply_deskew: bool = True, apply_binarize: bool = False,
+                                   apply_contrast: bool = True, apply_sharpness: bool = True,
+                                   target_size_mb: float = 2.0) -> List[bytes]:
+        """``preprocess_for_azure`` for many pages at once (the page loop of
+        ``OCRService.process_pdf_as_images_sync``, ocr_service.py:613-624, as one batched submission).
+        Pages are grouped by (size, mode) -- the pages of one PDF share both -- and every group goes through the
+        device chain and the JPEG ladder as one batch; results come back in input order and are the same bytes the
+        per-page call returns."""
+        imgs = [self._open(im) for im in images]
+        # EXIF orientation (reference :171-173): pages without the tag -- every rasterised PDF page -- are used as
+        # they are (exif_transpose would only copy them); the rare tagged image takes the per-image GPU transpose
+        imgs = [im if im.getexif().get(0x0112) not in (2, 3, 4, 5, 6, 7, 8) else self.auto_orient(im) for im in imgs]
+        out: List[Optional[bytes]] = [None] * len(imgs)
+        groups = {}
+        for i, im in enumerate(imgs):
+            groups.setdefault((im.size, im.mode), []).append(i)
+        for ((w, h), mode), idx in groups.items():
+            if mode not in ("RGB", "L"):
+                raise ValueError(f"unsupported image mode {mode!r}: load_image() converts to RGB/L first")
+            c = 3 if mode == "RGB" else 1
+            stage = self._host_stage(len(idx), h, w, c)
+            view = stage.numpy()
+
+            def unpack(j, i=None):   # Pillow's raw encoder -> the pinned staging slot, one thread per page
+                view[j] = np.asarray(imgs[idx[j]]).reshape(h, w, c)
+
+            with ThreadPoolExecutor(max_workers=min(8, len(idx))) as ex:
+                list(ex.map(unpack, range(len(idx))))
+            x = stage[: len(idx)].to(self.device, non_blocking=True)
+            x, _ = self.preprocess_device(x, apply_deskew, apply_binarize, apply_contrast, apply_sharpness)
+            for i, b in zip(idx, self.compress_pages_for_azure(x, target_size_mb=target_size_mb)):
+                out[i] = b
+        return out  # type: ignore[return-value]
+
+    def _host_stage(self, n: int, h: int, w: int, c: int) -> torch.Tensor:
+        """Persistent pinned staging buffer for page uploads (grown on demand, reused across calls)."""
+        st = getattr(self, "_stage", None)
+        if st is None or st.shape[1:] != (h, w, c) or st.shape[0] < n:
+            st = self._stage = torch.empty((n, h, w, c), dtype=torch.uint8, pin_memory=True)
+        return st
 
 
 class _LazySingleton:

@@ -134,6 +134,46 @@ def page_chain(page: np.ndarray, max_dim: int = 960, enhance: bool = False):
     return rgb, angle, np.asarray(gray), np.asarray(binary), norm
 
 
+def compress_for_azure(image: Image.Image, target_size_mb: float = 2.0, initial_quality: int = 95, min_quality: int = 30) -> bytes:
+    """:496-557 -- JPEG quality ladder (optimize=True), then Lanczos shrink by sqrt(target/current)."""
+    import io
+
+    target_bytes = int(target_size_mb * 1024 * 1024)
+    if image.mode in ("RGBA", "P"):
+        image = image.convert("RGB")
+    elif image.mode == "L":
+        image = image.convert("RGB")
+    quality = initial_quality
+    while quality >= min_quality:
+        buffer = io.BytesIO()
+        image.save(buffer, format="JPEG", quality=quality, optimize=True)
+        if buffer.tell() <= target_bytes:
+            return buffer.getvalue()
+        quality -= 10
+    buffer = io.BytesIO()
+    image.save(buffer, format="JPEG", quality=min_quality)
+    scale = (target_bytes / buffer.tell()) ** 0.5
+    resized = image.resize((int(image.width * scale), int(image.height * scale)), Image.Resampling.LANCZOS)
+    buffer = io.BytesIO()
+    resized.save(buffer, format="JPEG", quality=min_quality, optimize=True)
+    return buffer.getvalue()
+
+
+def preprocess_for_azure(page: np.ndarray, max_dim: int = 2000, apply_deskew: bool = True, apply_binarize: bool = False,
+                         target_size_mb: float = 2.0) -> bytes:
+    """:559-626 -- what OCRService._process_single_image_sync runs per page before the Azure call:
+    auto_orient -> resize_if_needed -> deskew -> (adaptive_binarize | contrast 1.2 -> sharpness 1.1) -> compress."""
+    img = auto_orient(Image.fromarray(page))
+    img = resize_if_needed(img, max_dim)
+    if apply_deskew:
+        img, _ = deskew(img)
+    if apply_binarize:
+        img = adaptive_binarize(img)
+    else:
+        img = enhance_sharpness(enhance_contrast(img, 1.2), 1.1)
+    return compress_for_azure(img, target_size_mb)
+
+
 _PAGES = None  # inherited by the forked workers: no per-task pickling of 26 MB rasters
 
 
@@ -146,6 +186,31 @@ def _worker_chain(args):
     idx, max_dim, enhance = args
     out = page_chain(_PAGES[idx], max_dim, enhance)
     return float(out[1])
+
+
+def _worker_azure(args):
+    idx, max_dim = args
+    return preprocess_for_azure(_PAGES[idx], max_dim)
+
+
+def run_pool_azure(pages, max_dim: int = 2000, procs: int | None = None):
+    """preprocess_for_azure over `pages`, one page per task on `procs` workers -> (seconds, list of JPEG bytes)."""
+    import multiprocessing as mp
+    import os
+    import time
+
+    global _PAGES
+    procs = procs or os.cpu_count() or 1
+    _PAGES = pages
+    try:
+        with mp.get_context("fork").Pool(procs, initializer=_worker_init) as pool:
+            pool.map(_worker_azure, [(i, max_dim) for i in range(min(len(pages), procs))])   # warm the workers
+            t0 = time.perf_counter()
+            out = pool.map(_worker_azure, [(i, max_dim) for i in range(len(pages))])
+            dt = time.perf_counter() - t0
+    finally:
+        _PAGES = None
+    return dt, out
 
 
 def run_pool(pages, max_dim: int = 960, enhance: bool = False, procs: int | None = None):
