@@ -94,3 +94,22 @@ def test_gpu_compress_for_azure_equals_reference(cuda):
     d = ip.compress_for_azure(g)
     assert d == _pil(np.asarray(g.convert("RGB")), 95, True)
     assert Image.open(io.BytesIO(d)).size == (127, 93)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binarize", [False, True])
+def test_gpu_preprocess_for_azure_files_equal_reference_sequence(cuda, oracle, binarize):
+    """The app's whole per-page job (ocr_service.py:412-417): host raster -> JPEG bytes, batched and per page,
+    against the reference's call sequence on Pillow/OpenCV (oracle/reference_port.preprocess_for_azure)."""
+    from PIL import Image
+    from oracle import reference_port as RP
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+
+    pages = [oracle.synth_page(877, 620, s) for s in (0, 1, 2)] + [oracle.synth_page(620, 877, 3)]
+    imgs = [Image.fromarray(p) for p in pages]
+    ip = ImagePreprocessor(max_dimension=400)
+    got = ip.preprocess_pages_for_azure(imgs, apply_binarize=binarize)
+    for p, im, g in zip(pages, imgs, got):
+        want = RP.preprocess_for_azure(p, 400, apply_binarize=binarize)
+        assert g == want
+        assert ip.preprocess_for_azure(im, apply_binarize=binarize) == want
