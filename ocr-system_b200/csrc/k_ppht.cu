@@ -7,18 +7,19 @@
 // The algorithm is a sequential randomised loop (cv::RNG seeded with (uint64)-1,
 // swap-remove of a raster-ordered point list, vote / arg-max / line walk per
 // point).  What is parallel is exploited without changing the result:
-//   ppht_collect_kernel : raster-order compaction of edge pixels (CTA-wide scan)
-//   ppht_order_kernel   : the visiting order depends only on N and the seed, not
-//                         on the votes, so the RNG + swap-remove permutation is
-//                         produced ahead of time, 32 draws per warp step with an
-//                         exact sequential fallback when two draws interact
-//   ppht_main_kernel    : one warp per page; the 180 theta votes of a point are
-//                         spread over the lanes (L2 atomics on packed 16-bit
-//                         counters), arg-max by one redux.sync, line walks test 32
-//                         positions per step with ballots, un-voting is fire-and-
-//                         forget RED traffic.  Pages are independent, so a batch
-//                         keeps up to one warp per page in flight.
-// This stage is latency-bound (dependent L2 round trips), not bandwidth-bound.
+//   ppht_collect_kernel    : raster-order compaction of edge pixels (CTA-wide scan)
+//   ppht_bitmask_kernel    : the edge map as a bitmask (one 32-pixel word per thread)
+//   ppht_order_kernel      : the visiting order depends only on N and the seed, not on the votes, so the
+//                            RNG + swap-remove permutation is produced ahead of time, 32 draws per step,
+//                            in shared memory once the live list fits, with an exact in-order replay of
+//                            the steps whose draws interact
+//   ppht_page_order_kernel : pages are launched heaviest first (longest-processing-time-first)
+//   ppht_cluster_lm_kernel : (k_ppht_cluster.cuh) accumulator rows distributed over the shared memory of
+//                            a thread-block cluster, a private edge bitmask per CTA -- the product path
+//   ppht_main_kernel       : last resort for pages whose theta rows do not fit 8 CTAs: one CTA per page,
+//                            the 180 theta votes of a point spread over the lanes (L2 atomics on packed
+//                            16-bit counters), batched with exact rank resolution
+// This stage is latency-bound (a serial dependency chain per page), not bandwidth-bound.
 #include <math.h>
 #include <stdlib.h>
 

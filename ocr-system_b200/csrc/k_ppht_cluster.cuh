@@ -7,13 +7,14 @@
 // vote is a shared-memory read-modify-write by the thread that owns the theta row: no atomics, no L2.
 //   * 32 points of the (precomputed) visiting order per batch; the theta-thread applies them in
 //     order (groups of 4, duplicates resolved in registers), so every per-(point,theta) value is the
-//     exact sequential value;
-//   * per point the row warps reduce max/first-theta (redux.sync), CTAs exchange their 32 keys through
-//     DSMEM (st.shared::cluster) and one cluster barrier, then all CTAs take the same decision;
-//   * the first point that reaches the threshold runs its line event, replayed by every CTA (the walk
-//     is deterministic given the mask); a line that is not "good" only clears mask pixels, so the scan
-//     continues inside the batch; a good line (un-votes) or a cleared batch point makes the later
-//     points take their votes back and replay.
+//     exact sequential value; a row that reaches the threshold posts value<<16 | first theta with a
+//     shared-memory atomicMax (rows below the threshold post nothing);
+//   * warp 0 sends the CTA's 32 keys to every CTA of the cluster with st.async stores that complete
+//     the receiver's transaction mbarrier and waits on its own: no cluster barrier, no fence;
+//   * warp 0 alone runs the line events that are not "good" (such a line only clears mask pixels, so
+//     the scan continues inside the batch); every CTA replays them on its private mask copy; the CTA
+//     joins for a good line (un-vote by all threads) or when a later batch point was cleared (those
+//     points take their votes back and the batch restarts behind the event).
 // Identical result to cv2.HoughLinesP (same lines, same order).
 #pragma once
 #include <cooperative_groups.h>
