@@ -261,7 +261,7 @@ struct ResizeDp4aParams {
 };
 
 template <int KXW>
-__global__ void __launch_bounds__(256) resize_strip_dp4a_kernel(const ResizeDp4aParams p) {
+__global__ void __launch_bounds__(256, 4) resize_strip_dp4a_kernel(const ResizeDp4aParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int ROWB = TOW * 3;
     uint8_t *inbuf = smem;                                             // [RB][3][segpx]
