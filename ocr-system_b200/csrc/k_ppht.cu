@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(NW * 32) ppht_main_kernel(const PphtParams p) 
 
 }  // namespace lumina
 
-#include "k_ppht_cluster.cuh"
+#include "k_ppht_pipe.cuh"
 
 using namespace lumina;
 
@@ -681,17 +681,21 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
             row_cells[a] = hi - lo + 1;
         }
     }
-    const char *force = getenv("LUMINA_PPHT");  // diagnostics: "l2" | "cluster" force a slower variant
+    const char *force = getenv("LUMINA_PPHT");  // diagnostics: "l2" | "cluster" | "nopipe" force a slower variant
+    const bool want_l2 = force && force[0] == 'l', want_cluster = force && force[0] == 'c', no_pipe = force && force[0] == 'n';
     // variant 0: accumulator slice + a private copy of the edge bitmask in each CTA's shared memory
+    //            (software-pipelined kernel, or the one-phase-at-a-time kernel with LUMINA_PPHT=nopipe)
     // variant 1: accumulator slices in shared memory, the private bitmask copies in L2
-    for (int variant = (force ? 1 : 0); variant < 2 && !(force && force[0] == 'l'); variant++) {
+    for (int variant = (want_cluster ? 1 : 0); variant < 2 && !want_l2; variant++) {
         const bool lm = variant == 0;
+        const bool pipe = lm && !no_pipe;
         int max_optin = 0, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa;
-        const cudaError_t fe = lm ? cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<true>)
-                                  : cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<false>);
+        const cudaError_t fe = pipe ? cudaFuncGetAttributes(&fa, ppht_cluster_pipe_kernel)
+                               : lm ? cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<true>)
+                                    : cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<false>);
         if (fe != cudaSuccess) { cudaGetLastError(); continue; }
         const long long mask_bytes = lm ? (long long)L.bits_stride * 4 : 0;
         const long long budget = (long long)max_optin - (long long)fa.sharedSizeBytes - 1024 - mask_bytes;
@@ -721,11 +725,12 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
             q.slice_cells = worst; q.threshold = threshold; q.line_length = min_line_length;
             q.line_gap = max_line_gap; q.max_lines = max_lines;
             const size_t dyn = (((size_t)worst * 2 + 15) & ~(size_t)15) + (size_t)mask_bytes;
-            if (lm) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            if (pipe) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            else if (lm) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             else LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(n * c));
-            cfg.blockDim = dim3(PCL_THREADS);
+            cfg.blockDim = dim3(pipe ? PPI_THREADS : PCL_THREADS);
             cfg.dynamicSmemBytes = dyn;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
@@ -733,9 +738,10 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
             attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            if (lm) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel<true>, q));
+            if (pipe) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_pipe_kernel, q));
+            else if (lm) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel<true>, q));
             else LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel<false>, q));
-            LUMINA_KERNEL_CHECK("ppht_cluster_lm_kernel");
+            LUMINA_KERNEL_CHECK(pipe ? "ppht_cluster_pipe_kernel" : "ppht_cluster_lm_kernel");
             return LUMINA_OK;
         }
     }

@@ -198,7 +198,7 @@ def test_ctc_greedy(oracle, cuda, n, t, c):
     assert np.max(np.abs(conf - rconf)) <= 1e-4
 
 
-@pytest.mark.parametrize("variant", ["l2", "cluster"])
+@pytest.mark.parametrize("variant", ["l2", "cluster", "nopipe"])
 def test_ppht_fallback_variants_are_exact_too(oracle, cuda, variant, monkeypatch):
     """The default HoughLinesP kernel keeps accumulator + edge bitmask in (distributed) shared memory;
     larger pages fall back to a cluster kernel with the mask in L2, then to L2 atomics.  All three
