@@ -277,10 +277,10 @@ def main_ours(args):
             "det_resize_normalize": B * (px * 3 + 3 * 960 * 672 * 4),
         }
         # DRAM bytes of one resize launch from the ncu --set full capture of this kernel at this batch size
-        # (profiles/r1_ncu_resize_dp4a.txt: dram__bytes_read.sum 1.790 GB + dram__bytes_write.sum 72.7 MB)
+        # (profiles/r1_ncu_resize_dp4a.txt: dram__bytes_read.sum 1.757 GB + dram__bytes_write.sum 71.1 MB)
         traffic, traffic_src = args.traffic_bytes, "--traffic-bytes"
         if traffic is None and B == 64 and args.max_dim == 960:
-            traffic, traffic_src = 1.7904e9 + 72.7e6, "ncu capture profiles/r1_ncu_resize_dp4a.txt (batch 64, per launch)"
+            traffic, traffic_src = 1.7570e9 + 71.1e6, "ncu capture profiles/r1_ncu_resize_dp4a.txt (batch 64, per launch)"
         elif traffic is None:
             traffic_src = None
         line = {
@@ -307,7 +307,7 @@ def main_ours(args):
             "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "stages_GBps": {k: round(per_stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9, 1)
                             for k in stage_ms if k in per_stage_bytes and stage_ms[k] > 0},
-            "latency_bound": {"kernel": "ppht_cluster_lm_kernel (exact cv2.HoughLinesP: serial dependency chain, "
+            "latency_bound": {"kernel": "ppht_cluster_pipe_kernel (exact cv2.HoughLinesP: serial dependency chain, "
                                         "3-CTA clusters, accumulator + edge bitmask in distributed shared memory)",
                               "ms_per_step": round(stage_ms.get("ppht", float("nan")), 3),
                               "share_of_step": round(stage_ms.get("ppht", 0.0) / ms_step, 3)},
