@@ -105,6 +105,14 @@ size_t lumina_ppht_workspace_bytes(int n, int h, int w, double rho, double theta
 int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double rho, double theta, int threshold,
                 int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
                 void *d_workspace, size_t workspace_bytes, void *stream);
+/* The same call in two halves for stream pipelines: prepare = point collection, edge bitmask, visiting order
+ * (wide, short kernels; touches only the workspace); lines = the long cluster kernel on a prepared workspace.
+ * lumina_ppht_prepare + lumina_ppht_lines with the same arguments == lumina_ppht. */
+int lumina_ppht_prepare(const uint8_t *d_edges, int n, int h, int w, double rho, double theta, void *d_workspace,
+                        size_t workspace_bytes, void *stream);
+int lumina_ppht_lines(const uint8_t *d_edges, int n, int h, int w, double rho, double theta, int threshold,
+                      int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
+                      void *d_workspace, size_t workspace_bytes, void *stream);
 /* (iv)+(v) host: per-line degrees(arctan2) folded to +-45, np.median.  Host
  * code on purpose (glibc atan2 == the reference's libm). nlines==0 -> 0.0 */
 double lumina_median_angle_host(const int32_t *h_lines, int nlines);

@@ -602,11 +602,13 @@ LUMINA_API size_t lumina_ppht_workspace_bytes(int n, int h, int w, double rho, d
     return ppht_layout(n, h, w, rho, theta).total;
 }
 
-LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double rho_d, double theta_d, int threshold,
-                           int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
-                           void *d_workspace, size_t workspace_bytes, void *stream) {
-    LUMINA_REQUIRE(d_edges && d_lines && d_nlines && d_workspace, "null pointer");
-    LUMINA_REQUIRE(n > 0 && h > 0 && w > 0 && max_lines > 0, "empty batch");
+// phases: 1 = prepare (tables, point collection, bitmask, visiting order, page order; touches only the workspace),
+//         2 = line extraction from a prepared workspace, 3 = both
+static int ppht_run(const uint8_t *d_edges, int n, int h, int w, double rho_d, double theta_d, int threshold, int min_line_length,
+                    int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines, void *d_workspace,
+                    size_t workspace_bytes, int phases, void *stream) {
+    LUMINA_REQUIRE(d_edges && d_workspace && ((phases & 2) == 0 || (d_lines && d_nlines)), "null pointer");
+    LUMINA_REQUIRE(n > 0 && h > 0 && w > 0, "empty batch");
     LUMINA_REQUIRE(h < 65536 && w < 65536, "page too large (16-bit packed coordinates)");
     LUMINA_REQUIRE(rho_d > 0 && theta_d > 0, "rho/theta must be positive");
     const PphtLayout L = ppht_layout(n, h, w, rho_d, theta_d);
@@ -635,6 +637,8 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
         }
         step[a * 3] = xflag; step[a * 3 + 1] = dx0; step[a * 3 + 2] = dy0;
     }
+    const bool lpt_order = n > 1 && n <= 8192;
+    if (phases & 1) {
     LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.trig_off, trig.data(), trig.size() * 4, cudaMemcpyHostToDevice, st));
     LUMINA_CUDA_TRY(cudaMemcpyAsync(ws + L.step_off, step.data(), step.size() * 4, cudaMemcpyHostToDevice, st));
     // pageable-source async copies are staged before returning, so the vectors may die here
@@ -658,11 +662,12 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
                                                                     (const int *)(ws + L.count_off), h * w, (int)cap);
     }
     LUMINA_KERNEL_CHECK("ppht_order_kernel");
-    const bool lpt_order = n > 1 && n <= 8192;
     if (lpt_order) {
         ppht_page_order_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int *)(ws + L.count_off), (int *)(ws + L.pageorder_off), n);
         LUMINA_KERNEL_CHECK("ppht_page_order_kernel");
     }
+    }
+    if ((phases & 2) == 0) return LUMINA_OK;
     // ---- shared-memory (cluster) paths: per-theta rho range the page can reach ----
     std::vector<int> rho_lo(L.numangle), row_cells(L.numangle);
     {
@@ -757,6 +762,28 @@ LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double r
     ppht_main_kernel<6, PPHT_WARPS><<<n, PPHT_WARPS * 32, 0, st>>>(p);
     LUMINA_KERNEL_CHECK("ppht_main_kernel");
     return LUMINA_OK;
+}
+
+LUMINA_API int lumina_ppht(const uint8_t *d_edges, int n, int h, int w, double rho_d, double theta_d, int threshold,
+                           int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
+                           void *d_workspace, size_t workspace_bytes, void *stream) {
+    LUMINA_REQUIRE(max_lines > 0, "empty batch");
+    return ppht_run(d_edges, n, h, w, rho_d, theta_d, threshold, min_line_length, max_line_gap, d_lines, d_nlines, max_lines,
+                    d_workspace, workspace_bytes, 3, stream);
+}
+
+// The same call in two halves, so that a pipeline can run the wide preparation kernels and the long cluster
+// kernel on different streams: lumina_ppht_prepare + lumina_ppht_lines(same arguments) == lumina_ppht.
+LUMINA_API int lumina_ppht_prepare(const uint8_t *d_edges, int n, int h, int w, double rho_d, double theta_d, void *d_workspace,
+                                   size_t workspace_bytes, void *stream) {
+    return ppht_run(d_edges, n, h, w, rho_d, theta_d, 0, 0, 0, nullptr, nullptr, 1, d_workspace, workspace_bytes, 1, stream);
+}
+LUMINA_API int lumina_ppht_lines(const uint8_t *d_edges, int n, int h, int w, double rho_d, double theta_d, int threshold,
+                                 int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
+                                 void *d_workspace, size_t workspace_bytes, void *stream) {
+    LUMINA_REQUIRE(max_lines > 0, "empty batch");
+    return ppht_run(d_edges, n, h, w, rho_d, theta_d, threshold, min_line_length, max_line_gap, d_lines, d_nlines, max_lines,
+                    d_workspace, workspace_bytes, 2, stream);
 }
 
 // (iv)+(v) image_preprocessing.py:414-428 -- host on purpose (libm atan2, as numpy)

@@ -223,6 +223,38 @@ def hough_lines_p(edges: torch.Tensor, rho: float = 1.0, theta: float = float(np
     return lines, nlines
 
 
+class HoughJob:
+    """cv2.HoughLinesP in two halves for stream pipelines: ``prepare()`` (point collection, bitmask, visiting
+    order: wide, short kernels) and ``lines()`` (the long cluster kernel), each on the stream that is current
+    when it is called.  ``lines()`` must be ordered after ``prepare()`` by the caller (same stream or an event)."""
+
+    def __init__(self, edges: torch.Tensor, rho: float = 1.0, theta: float = float(np.pi / 180), threshold: int = 100,
+                 min_line_length: int = 100, max_line_gap: int = 10, max_lines: int = 4096):
+        x, n, h, w, c = _pages(edges)
+        if c != 1:
+            raise ValueError("edges must be [N,H,W]")
+        self.x, self.n, self.h, self.w = x, n, h, w
+        self.args = (float(rho), float(theta))
+        self.params = (int(threshold), int(min_line_length), int(max_line_gap))
+        self.max_lines = int(max_lines)
+        self.wsb = int(_L().lumina_ppht_workspace_bytes(n, h, w, *self.args))
+        self.ws = _ws(self.wsb, x.device)
+
+    def prepare(self):
+        _chk(_L().lumina_ppht_prepare(_ptr(self.x), self.n, self.h, self.w, *self.args, _ptr(self.ws), self.wsb, _stream()))
+        return self
+
+    def lines(self):
+        lines = torch.empty((self.n, self.max_lines, 4), dtype=torch.int32, device=self.x.device)
+        nlines = torch.empty(self.n, dtype=torch.int32, device=self.x.device)
+        _chk(_L().lumina_ppht_lines(_ptr(self.x), self.n, self.h, self.w, *self.args, *self.params, _ptr(lines), _ptr(nlines),
+                                    self.max_lines, _ptr(self.ws), self.wsb, _stream()))
+        cur = torch.cuda.current_stream(self.x.device)
+        self.ws.record_stream(cur)
+        self.x.record_stream(cur)
+        return lines, nlines
+
+
 def median_angle(lines_host: np.ndarray) -> float:
     """image_preprocessing.py:414-428 on the host (libm atan2, like numpy)."""
     a = np.ascontiguousarray(lines_host, dtype=np.int32)

@@ -94,12 +94,21 @@ class PagePipeline:
         if not pages.is_cuda:
             raise TypeError("run_device needs a CUDA tensor (use run_host for host buffers)")
         t = _StageTimer(profile)
+        return self._back(*self._front(pages, t), t)
+
+    def _front(self, pages: torch.Tensor, t: "_StageTimer"):
+        """Everything up to the line lists (no host synchronisation)."""
         x = t.run("resize_lanczos", lambda: ops.resize_if_needed(pages, self.max_dimension))
-        n = x.shape[0]
-        angles = np.zeros(n, np.float64)
+        lines = nlines = None
         if self.deskew:
             edges = t.run("canny", lambda: ops.canny(x, 50, 150))
             lines, nlines = t.run("ppht", lambda: ops.hough_lines_p(edges))
+        return x, lines, nlines
+
+    def _back(self, x, lines, nlines, t: "_StageTimer") -> PageBatchResult:
+        """Host median / gating (the chain's one synchronisation) and everything after it."""
+        angles = np.zeros(x.shape[0], np.float64)
+        if self.deskew:
             x, angles = t.run("angle+warp", lambda: self._rotate(x, lines, nlines))
         if self.enhance:
             x = t.run("contrast+sharpness", lambda: ops.contrast_sharpness(x, 1.2, 1.1))
@@ -107,6 +116,62 @@ class PagePipeline:
         binary = t.run("adaptive_binarize", lambda: ops.adaptive_binarize(gray, 2))
         det, shape_list = t.run("det_resize_normalize", lambda: ops.det_resize_normalize(x, self.det_limit))
         return PageBatchResult(x, angles, gray, binary, det, shape_list, t)
+
+    def run_device_stream(self, batches, profile: bool = False):
+        """``run_device`` over a sequence of resident batches, software-pipelined on two CUDA streams: the front
+        half of batch i+1 (resize, Canny, HoughLinesP) is enqueued before the host waits for the line lists of
+        batch i, so its kernels fill the SMs that batch i's last HoughLinesP clusters leave idle (49 pages fit at
+        once; a 64-page batch alone runs 1.3 waves).  Yields one PageBatchResult per batch, in order; the
+        results are safe to use on the caller's current stream."""
+        dev = self.device or torch.device("cuda", torch.cuda.current_device())
+        main = torch.cuda.current_stream(dev)
+        st = getattr(self, "_dev_streams", None)
+        if st is None or st[0].device != dev:
+            # one high-priority stream for the wide kernels (resize, Canny, warp, gray, binarize, normalise) and two
+            # low-priority streams that alternate for HoughLinesP: when a page's cluster retires, the freed SMs go to
+            # the wide kernels of the next batch first, so its HoughLinesP is ready to follow without a gap
+            st = self._dev_streams = (torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev, priority=0),
+                                      torch.cuda.Stream(dev, priority=0))
+        hi = st[0]
+
+        def start(i, pages):
+            lo = st[1 + (i & 1)]
+            t = _StageTimer(profile)
+            hi.wait_stream(main)
+            with torch.cuda.stream(hi):
+                x = t.run("resize_lanczos", lambda: ops.resize_if_needed(pages, self.max_dimension))
+                job = None
+                if self.deskew:
+                    edges = t.run("canny", lambda: ops.canny(x, 50, 150))
+                    job = t.run("ppht_prepare", lambda: ops.HoughJob(edges).prepare())
+            lines = nlines = None
+            if self.deskew:
+                lo.wait_stream(hi)
+                with torch.cuda.stream(lo):
+                    lines, nlines = t.run("ppht", job.lines)
+            return lo, (x, lines, nlines), t
+
+        def finish(job):
+            lo, front, t = job
+            lo.synchronize()                      # the line lists of this batch are complete
+            hi.wait_stream(lo)
+            with torch.cuda.stream(hi):
+                res = self._back(*front, t)
+            main.wait_stream(hi)
+            for ten in (res.pages, res.gray, res.binary, res.det_input):
+                ten.record_stream(main)
+            return res
+
+        prev = None
+        for i, pages in enumerate(batches):
+            if not pages.is_cuda:
+                raise TypeError("run_device_stream needs CUDA tensors")
+            job = start(i, pages)
+            if prev is not None:
+                yield finish(prev)
+            prev = job
+        if prev is not None:
+            yield finish(prev)
 
     _rotate_stage = None   # pinned staging for the line lists (shape-keyed)
 

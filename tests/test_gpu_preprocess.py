@@ -230,3 +230,29 @@ def test_ppht_degenerate_inputs(oracle, cuda):
     lines, nl = ops.hough_lines_p(_t(full[None], cuda), threshold=20, min_line_length=10, max_line_gap=2)
     ref = oracle.ppht(full, threshold=20, min_len=10, max_gap=2)
     assert int(nl[0]) == len(ref) and np.array_equal(lines[0, : int(nl[0])].cpu().numpy(), ref)
+
+
+def test_pipelined_stream_equals_sequential_steps(oracle, cuda):
+    """run_device_stream (steps overlapped on CUDA streams, HoughLinesP split into prepare + lines) must give
+    exactly what run_device gives batch by batch."""
+    import torch
+    from ocr_system_b200 import ops
+    from ocr_system_b200.pipeline import PagePipeline
+
+    batches = [ops.synth_pages(6, 877, 620, seed0=s) for s in (0, 6, 12, 18)]
+    pipe = PagePipeline(max_dimension=400)
+    want = [pipe.run_device(b) for b in batches]
+    got = list(pipe.run_device_stream(batches))
+    torch.cuda.synchronize()
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.array_equal(g.angles, w.angles)
+        for name in ("pages", "gray", "binary", "det_input"):
+            assert torch.equal(getattr(g, name), getattr(w, name)), name
+    # the two halves of the Hough call on one stream are the whole call
+    edges = ops.canny(ops.resize_if_needed(batches[0], 400))
+    l1, n1 = ops.hough_lines_p(edges)
+    l2, n2 = ops.HoughJob(edges).prepare().lines()
+    assert torch.equal(n1, n2)
+    for i in range(edges.shape[0]):
+        assert torch.equal(l1[i, : int(n1[i])], l2[i, : int(n2[i])])
