@@ -113,3 +113,17 @@ def test_gpu_preprocess_for_azure_files_equal_reference_sequence(cuda, oracle, b
         want = RP.preprocess_for_azure(p, 400, apply_binarize=binarize)
         assert g == want
         assert ip.preprocess_for_azure(im, apply_binarize=binarize) == want
+
+
+@pytest.mark.gpu
+def test_gpu_jpeg_degenerate_sizes_equal_pillow(cuda):
+    """Sizes below one block / one MCU and strongly non-square pages (dummy blocks on both edges)."""
+    import torch
+    from ocr_system_b200 import ops
+
+    rng = np.random.default_rng(11)
+    for (h, w) in [(1, 1), (1, 17), (9, 7), (8, 8), (15, 31), (17, 16), (33, 2), (2, 257)]:
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for q, opt in [(95, True), (60, False), (1, True)]:
+            got = ops.jpeg_encode(torch.from_numpy(a[None]).to(cuda), q, opt)[0]
+            assert got == _pil(a, q, opt), (h, w, q, opt)
