@@ -19,8 +19,12 @@
 
 #ifdef __CUDACC__
 #define DBG_HD __host__ __device__ __forceinline__
+// the large routines stay out of line on the device: the candidate kernel runs them on one lane of many warps that
+// are all at different places, and its stalls are instruction-cache misses (ncu: no_instruction) -- one copy each
+#define DBG_HD_BIG __host__ __device__ __noinline__
 #else
 #define DBG_HD static inline
+#define DBG_HD_BIG static inline
 #endif
 
 #ifndef DBG_PI
@@ -37,7 +41,7 @@ DBG_HD long long dbg_cross(const DbgPt &o, const DbgPt &a, const DbgPt &b) {
 
 // in-place heap sort by (y, x)
 DBG_HD bool dbg_less(const DbgPt &a, const DbgPt &b) { return a.y < b.y || (a.y == b.y && a.x < b.x); }
-DBG_HD void dbg_sort(DbgPt *p, int n) {
+DBG_HD_BIG void dbg_sort(DbgPt *p, int n) {
     for (int start = n / 2 - 1; start >= 0; start--) {
         int root = start;
         for (;;) {
@@ -65,7 +69,7 @@ DBG_HD void dbg_sort(DbgPt *p, int n) {
 
 // Monotone chain on points already sorted by (y, x) (duplicates allowed).  `hull` must hold n+1
 // points.  Collinear points are dropped.  Returns the hull size (1, 2 or >= 3).
-DBG_HD int dbg_hull_sorted(const DbgPt *p, int n, DbgPt *hull) {
+DBG_HD_BIG int dbg_hull_sorted(const DbgPt *p, int n, DbgPt *hull) {
     if (n <= 0) return 0;
     int k = 0;
     for (int i = 0; i < n; i++) {
@@ -106,7 +110,7 @@ DBG_HD void dbg_hull_rotate(DbgPt *h, int n, int mode, int sx, int sy) {
 }
 
 // cv::minAreaRect on a convex hull (float32 evaluation as rotcalipers.cpp).
-DBG_HD DbgRect dbg_min_area_rect(const DbgPt *hp, int n) {
+DBG_HD_BIG DbgRect dbg_min_area_rect(const DbgPt *hp, int n) {
     DbgRect box;
     box.cx = box.cy = box.w = box.h = box.angle = 0.f;
     if (n <= 0) return box;
@@ -250,7 +254,7 @@ DBG_HD long long dbg_floordiv(long long a, long long b) {  // b > 0
 }
 DBG_HD long long dbg_ceildiv(long long a, long long b) { return -dbg_floordiv(-a, b); }
 
-DBG_HD int dbg_row_cover(const DbgPt q[4], int y, int lo[5], int hi[5]) {
+DBG_HD_BIG int dbg_row_cover(const DbgPt q[4], int y, int lo[5], int hi[5]) {
     int cnt = 0;
     // boundary edges: cv::Line -> LineIterator(8-connected, left_to_right)
     for (int e = 0; e < 4; e++) {
@@ -331,7 +335,7 @@ DBG_HD long long dbg_cround(double v) { return v < 0 ? (long long)(v - 0.5) : (l
 
 // in: 4 float points (truncated to integers like pyclipper); out: up to max_out int points.
 // Returns the number of points, 0 if the path degenerates, -1 on overflow.
-DBG_HD int dbg_clipper_offset(const DbgPtF in[4], double delta, DbgPt *out, int max_out) {
+DBG_HD_BIG int dbg_clipper_offset(const DbgPtF in[4], double delta, DbgPt *out, int max_out) {
     DbgPt c[4];
     int n = 0;
     {

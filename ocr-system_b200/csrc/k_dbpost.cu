@@ -19,8 +19,8 @@
 namespace lumina {
 
 struct DbLayout {
-    size_t mask_off, labels_off, cand_off, bbox_off, ncand_off, pool_off, poolctr_off, accept_off, tmpbox_off, tmpscore_off,
-        total;
+    size_t mask_off, labels_off, cand_off, bbox_off, ncand_off, pool_off, poolctr_off, accept_off, cmeta_off, tmpbox_off,
+        tmpscore_off, total;
     size_t pool_pts_per_map;
 };
 
@@ -39,6 +39,7 @@ static DbLayout db_layout(int n, int h, int w, int maxc) {
     L.pool_off = off; off = a256(off + (size_t)n * L.pool_pts_per_map * 8);
     L.poolctr_off = off; off = a256(off + (size_t)n * 4);
     L.accept_off = off; off = a256(off + (size_t)n * maxc);
+    L.cmeta_off = off; off = a256(off + (size_t)n * maxc * 2 * 4);
     L.tmpbox_off = off; off = a256(off + (size_t)n * maxc * 8 * 4);
     L.tmpscore_off = off; off = a256(off + (size_t)n * maxc * 4);
     L.total = off;
@@ -261,6 +262,7 @@ struct DbParams {
     DbgPt *pool;
     int *poolctr;
     uint8_t *accept;
+    int *cmeta;          // [n][maxc][2] pool offset and point count of every candidate
     int *tmpbox;
     float *tmpscore;
     const int *src_hw;  // [n][2] device copy
@@ -281,11 +283,17 @@ __device__ __noinline__ int db_row_intervals(const DbgPt *q4, int ry, int *lo, i
 }
 
 constexpr int DB_WARPS = 4;
-constexpr int DB_OFFS_MAX = 384;  // Clipper offset vertices kept in shared memory per warp
+constexpr int DB_OFFS_MAX = 384;  // Clipper offset vertices kept in shared memory per candidate
 
-__global__ void __launch_bounds__(DB_WARPS * 32) db_candidate_geometry_kernel(const DbParams p) {
-    __shared__ DbgPt offs[DB_WARPS][DB_OFFS_MAX + 2];
-    __shared__ DbgPt offs_hull[DB_WARPS][DB_OFFS_MAX + 2];
+// The per-candidate geometry runs as four small kernels.  As one kernel (one warp per candidate, the serial
+// routines on lane 0) its dominant stall was instruction fetch: thousands of warps, each at a different
+// place of a large body.  Split, the serial routines run one candidate per THREAD (32 candidates share every
+// instruction fetch) and the warp-parallel parts (pixel scans) keep one warp per candidate.
+// accept[] carries the state between them: 2 = row extremes ready, 3 = first quad ready, 4 = score passed,
+// 1 = accepted; 11 / 12 / 13 / 15 = reject reasons (too small, score, unclip, pool overflow); 0 = empty slot.
+
+// ---- 5a. row extremes of the candidate's point set (one warp per candidate) -------------------------------
+__global__ void __launch_bounds__(DB_WARPS * 32) db_cand_rows_kernel(const DbParams p) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int page = blockIdx.y;
     const int slot = blockIdx.x * DB_WARPS + wib;
@@ -293,7 +301,6 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_candidate_geometry_kernel(co
     const int px = p.h * p.w;
     const uint8_t *M = p.mask + (size_t)page * px;
     const int *L = p.labels + (size_t)page * px;
-    const float *P = p.pred + (size_t)page * px;
     const int centry = p.cand[(size_t)page * p.maxc + slot];
     const bool hole = centry < 0;
     const int root = hole ? -1 - centry : centry;
@@ -309,8 +316,6 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_candidate_geometry_kernel(co
     pbase = __shfl_sync(0xffffffffu, pbase, 0);
     if ((size_t)pbase + 4 * rows + 2 > p.pool_pts_per_map) { if (lane == 0) *acc = 15; return; }  // pathological masks only (> px/4 candidate rows): dropped
     DbgPt *pts = p.pool + (size_t)page * p.pool_pts_per_map + pbase;
-    DbgPt *hull = pts + 2 * rows;
-    // ---- row extremes of the candidate's point set ----
     int npts = 0;
     for (int y = by0; y <= by1; y++) {
         int rmin = 0x7fffffff, rmax = -1;
@@ -344,25 +349,54 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_candidate_geometry_kernel(co
             npts += 2;
         }
     }
-    __syncwarp();
-    // ---- first min-area quad (lane 0), broadcast ----
-    float bxs[4] = {0, 0, 0, 0}, bys[4] = {0, 0, 0, 0};
-    float sside = 0.f;
     if (lane == 0) {
-        int hn = dbg_hull_sorted(pts, npts, hull);
-        // note: roots carry the slot code in L; the root position itself is the (y,x)-smallest pixel
-        const int hy = root / p.w, hx = root - hy * p.w;
-        dbg_hull_rotate(hull, hn, hole ? 2 : 1, hx - 1, hy);
-        const DbgRect r = dbg_min_area_rect(hull, hn);
-        DbgPtF o[4];
-        sside = dbg_mini_box(r, o);
-        for (int i = 0; i < 4; i++) { bxs[i] = o[i].x; bys[i] = o[i].y; }
+        int *meta = p.cmeta + ((size_t)page * p.maxc + slot) * 2;
+        meta[0] = pbase; meta[1] = npts;
+        *acc = 2;
     }
-    sside = __shfl_sync(0xffffffffu, sside, 0);
-    if (sside < (float)p.min_size) { if (lane == 0) *acc = 11; return; }
+}
+
+// ---- 5b. hull + first min-area quad (one THREAD per candidate) -------------------------------------------------
+__global__ void __launch_bounds__(128) db_cand_rect_kernel(const DbParams p) {
+    const int page = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= p.ncand[page * 2 + 1]) return;
+    uint8_t *acc = p.accept + (size_t)page * p.maxc + slot;
+    if (*acc != 2) return;
+    const int centry = p.cand[(size_t)page * p.maxc + slot];
+    const bool hole = centry < 0;
+    const int root = hole ? -1 - centry : centry;
+    const int *meta = p.cmeta + ((size_t)page * p.maxc + slot) * 2;
+    const int *B = p.bbox + ((size_t)page * p.maxc + slot) * 4;
+    const int rows = B[3] - B[1] + 1;
+    DbgPt *pts = p.pool + (size_t)page * p.pool_pts_per_map + meta[0];
+    DbgPt *hull = pts + 2 * rows;
+    const int hn = dbg_hull_sorted(pts, meta[1], hull);
+    // note: roots carry the slot code in L; the root position itself is the (y,x)-smallest pixel
+    const int hy = root / p.w, hx = root - hy * p.w;
+    dbg_hull_rotate(hull, hn, hole ? 2 : 1, hx - 1, hy);
+    const DbgRect r = dbg_min_area_rect(hull, hn);
+    DbgPtF o[4];
+    const float sside = dbg_mini_box(r, o);
+    if (sside < (float)p.min_size) { *acc = 11; return; }
+    float *qf = reinterpret_cast<float *>(p.tmpbox + ((size_t)page * p.maxc + slot) * 8);   // the quad parks in tmpbox
+    for (int i = 0; i < 4; i++) { qf[i * 2] = o[i].x; qf[i * 2 + 1] = o[i].y; }
+    *acc = 3;
+}
+
+// ---- 5c. box_score_fast: mean of pred over cv2.fillPoly(int32(box - (xmin, ymin))) (one warp per candidate) ---
+__global__ void __launch_bounds__(DB_WARPS * 32) db_cand_score_kernel(const DbParams p) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int page = blockIdx.y;
+    const int slot = blockIdx.x * DB_WARPS + wib;
+    if (slot >= p.ncand[page * 2 + 1]) return;
+    uint8_t *acc = p.accept + (size_t)page * p.maxc + slot;
+    if (*acc != 3) return;
+    const float *P = p.pred + (size_t)page * p.h * p.w;
+    const float *qf = reinterpret_cast<const float *>(p.tmpbox + ((size_t)page * p.maxc + slot) * 8);
+    float bxs[4], bys[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { bxs[i] = __shfl_sync(0xffffffffu, bxs[i], 0); bys[i] = __shfl_sync(0xffffffffu, bys[i], 0); }
-    // ---- box_score_fast: mean of pred over cv2.fillPoly(int32(box - (xmin, ymin))) ----
+    for (int i = 0; i < 4; i++) { bxs[i] = qf[i * 2]; bys[i] = qf[i * 2 + 1]; }
     const float fminx = fminf(fminf(bxs[0], bxs[1]), fminf(bxs[2], bxs[3]));
     const float fmaxx = fmaxf(fmaxf(bxs[0], bxs[1]), fmaxf(bxs[2], bxs[3]));
     const float fminy = fminf(fminf(bys[0], bys[1]), fminf(bys[2], bys[3]));
@@ -390,46 +424,53 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_candidate_geometry_kernel(co
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     const double score = cnt > 0 ? sum / (double)cnt : 0.0;
-    if (p.box_thresh > score) {
-        if (lane == 0) {  // reject code + the score that failed (diagnostics)
-            *acc = 12;
-            p.tmpscore[(size_t)page * p.maxc + slot] = (float)score;
-        }
-        return;
+    if (lane == 0) {
+        p.tmpscore[(size_t)page * p.maxc + slot] = (float)score;   // for a reject: the score that failed (diagnostics)
+        *acc = p.box_thresh > score ? 12 : 4;
     }
-    // ---- unclip + second min-area quad (lane 0) ----
+}
+
+// ---- 5d. unclip + second min-area quad (one THREAD per candidate, offset polygon in shared memory) ------------
+constexpr int DB_UNCLIP_THREADS = 32;
+__global__ void __launch_bounds__(DB_UNCLIP_THREADS) db_cand_unclip_kernel(const DbParams p) {
+    extern __shared__ __align__(16) unsigned char db_smem[];
+    DbgPt *offs = reinterpret_cast<DbgPt *>(db_smem) + (size_t)threadIdx.x * 2 * (DB_OFFS_MAX + 2);
+    DbgPt *offs_hull = offs + (DB_OFFS_MAX + 2);
+    const int page = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= p.ncand[page * 2 + 1]) return;
+    uint8_t *acc = p.accept + (size_t)page * p.maxc + slot;
+    if (*acc != 4) return;
+    int *tb = p.tmpbox + ((size_t)page * p.maxc + slot) * 8;
+    const float *qf = reinterpret_cast<const float *>(tb);
+    DbgPtF b4[4];
+    for (int i = 0; i < 4; i++) { b4[i].x = qf[i * 2]; b4[i].y = qf[i * 2 + 1]; }
     int ok = 0;
     int outq[8];
-    if (lane == 0) {
-        DbgPtF b4[4];
-        for (int i = 0; i < 4; i++) { b4[i].x = bxs[i]; b4[i].y = bys[i]; }
-        const double dist = dbg_unclip_distance(b4, p.unclip_ratio);
-        if (dist >= 0) {
-            const int m = dbg_clipper_offset(b4, dist, offs[wib], DB_OFFS_MAX);
-            if (m >= 3) {
-                dbg_sort(offs[wib], m);
-                const int hn = dbg_hull_sorted(offs[wib], m, offs_hull[wib]);
-                const DbgRect r2 = dbg_min_area_rect(offs_hull[wib], hn);
-                DbgPtF o2[4];
-                const float ss2 = dbg_mini_box(r2, o2);
-                if (!(ss2 < (float)(p.min_size + 2))) {
-                    const double dw = (double)p.src_hw[page * 2 + 1], dh = (double)p.src_hw[page * 2];
-                    for (int i = 0; i < 4; i++) {
-                        outq[i * 2] = dbg_scale_coord(o2[i].x, p.w, dw);
-                        outq[i * 2 + 1] = dbg_scale_coord(o2[i].y, p.h, dh);
-                    }
-                    ok = 1;
+    const double dist = dbg_unclip_distance(b4, p.unclip_ratio);
+    if (dist >= 0) {
+        const int m = dbg_clipper_offset(b4, dist, offs, DB_OFFS_MAX);
+        if (m >= 3) {
+            dbg_sort(offs, m);
+            const int hn = dbg_hull_sorted(offs, m, offs_hull);
+            const DbgRect r2 = dbg_min_area_rect(offs_hull, hn);
+            DbgPtF o2[4];
+            const float ss2 = dbg_mini_box(r2, o2);
+            if (!(ss2 < (float)(p.min_size + 2))) {
+                const double dw = (double)p.src_hw[page * 2 + 1], dh = (double)p.src_hw[page * 2];
+                for (int i = 0; i < 4; i++) {
+                    outq[i * 2] = dbg_scale_coord(o2[i].x, p.w, dw);
+                    outq[i * 2 + 1] = dbg_scale_coord(o2[i].y, p.h, dh);
                 }
+                ok = 1;
             }
         }
-        if (ok) {
-            int *tb = p.tmpbox + ((size_t)page * p.maxc + slot) * 8;
-            for (int i = 0; i < 8; i++) tb[i] = outq[i];
-            p.tmpscore[(size_t)page * p.maxc + slot] = (float)score;
-            *acc = 1;
-        } else {
-            *acc = 13;
-        }
+    }
+    if (ok) {
+        for (int i = 0; i < 8; i++) tb[i] = outq[i];
+        *acc = 1;
+    } else {
+        *acc = 13;
     }
 }
 
@@ -548,12 +589,22 @@ LUMINA_API int lumina_db_postprocess(const float *d_pred, int n, int h, int w, f
     p.pred = d_pred; p.mask = mask; p.labels = labels;
     p.cand = (const int *)(ws + L.cand_off); p.bbox = (const int *)(ws + L.bbox_off); p.ncand = (const int *)(ws + L.ncand_off);
     p.pool = (DbgPt *)(ws + L.pool_off); p.poolctr = (int *)(ws + L.poolctr_off);
-    p.accept = ws + L.accept_off; p.tmpbox = (int *)(ws + L.tmpbox_off); p.tmpscore = (float *)(ws + L.tmpscore_off);
+    p.accept = ws + L.accept_off; p.cmeta = (int *)(ws + L.cmeta_off); p.tmpbox = (int *)(ws + L.tmpbox_off); p.tmpscore = (float *)(ws + L.tmpscore_off);
     p.src_hw = src_hw_dev; p.pool_pts_per_map = L.pool_pts_per_map;
     p.h = h; p.w = w; p.maxc = max_candidates; p.min_size = min_size;
     p.box_thresh = box_thresh; p.unclip_ratio = unclip_ratio;
-    db_candidate_geometry_kernel<<<dim3(div_up(max_candidates, DB_WARPS), n), DB_WARPS * 32, 0, st>>>(p);
-    LUMINA_KERNEL_CHECK("db_candidate_geometry_kernel");
+    db_cand_rows_kernel<<<dim3(div_up(max_candidates, DB_WARPS), n), DB_WARPS * 32, 0, st>>>(p);
+    LUMINA_KERNEL_CHECK("db_cand_rows_kernel");
+    db_cand_rect_kernel<<<dim3(div_up(max_candidates, 128), n), 128, 0, st>>>(p);
+    LUMINA_KERNEL_CHECK("db_cand_rect_kernel");
+    db_cand_score_kernel<<<dim3(div_up(max_candidates, DB_WARPS), n), DB_WARPS * 32, 0, st>>>(p);
+    LUMINA_KERNEL_CHECK("db_cand_score_kernel");
+    {
+        const size_t smem = (size_t)DB_UNCLIP_THREADS * 2 * (DB_OFFS_MAX + 2) * sizeof(DbgPt);
+        LUMINA_CUDA_TRY(cudaFuncSetAttribute(db_cand_unclip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        db_cand_unclip_kernel<<<dim3(div_up(max_candidates, DB_UNCLIP_THREADS), n), DB_UNCLIP_THREADS, smem, st>>>(p);
+        LUMINA_KERNEL_CHECK("db_cand_unclip_kernel");
+    }
     db_compact_kernel<<<n, 1024, 0, st>>>(p.accept, p.tmpbox, p.tmpscore, p.ncand, d_boxes, d_scores, d_counts, max_candidates);
     LUMINA_KERNEL_CHECK("db_compact_kernel");
     return LUMINA_OK;
