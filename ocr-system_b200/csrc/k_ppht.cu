@@ -693,12 +693,13 @@ static int ppht_run(const uint8_t *d_edges, int n, int h, int w, double rho_d, d
     // variant 1: accumulator slices in shared memory, the private bitmask copies in L2
     for (int variant = (want_cluster ? 1 : 0); variant < 2 && !want_l2; variant++) {
         const bool lm = variant == 0;
-        const bool pipe = lm && !no_pipe;
+        const bool pipe = !no_pipe;
         int max_optin = 0, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa;
-        const cudaError_t fe = pipe ? cudaFuncGetAttributes(&fa, ppht_cluster_pipe_kernel)
+        const cudaError_t fe = pipe ? (lm ? cudaFuncGetAttributes(&fa, ppht_cluster_pipe_kernel<true>)
+                                          : cudaFuncGetAttributes(&fa, ppht_cluster_pipe_kernel<false>))
                                : lm ? cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<true>)
                                     : cudaFuncGetAttributes(&fa, ppht_cluster_lm_kernel<false>);
         if (fe != cudaSuccess) { cudaGetLastError(); continue; }
@@ -730,7 +731,8 @@ static int ppht_run(const uint8_t *d_edges, int n, int h, int w, double rho_d, d
             q.slice_cells = worst; q.threshold = threshold; q.line_length = min_line_length;
             q.line_gap = max_line_gap; q.max_lines = max_lines;
             const size_t dyn = (((size_t)worst * 2 + 15) & ~(size_t)15) + (size_t)mask_bytes;
-            if (pipe) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            if (pipe && lm) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            else if (pipe) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             else if (lm) LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             else LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_cluster_lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             cudaLaunchConfig_t cfg = {};
@@ -743,7 +745,8 @@ static int ppht_run(const uint8_t *d_edges, int n, int h, int w, double rho_d, d
             attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            if (pipe) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_pipe_kernel, q));
+            if (pipe && lm) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_pipe_kernel<true>, q));
+            else if (pipe) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_pipe_kernel<false>, q));
             else if (lm) LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel<true>, q));
             else LUMINA_CUDA_TRY(cudaLaunchKernelEx(&cfg, ppht_cluster_lm_kernel<false>, q));
             LUMINA_KERNEL_CHECK(pipe ? "ppht_cluster_pipe_kernel" : "ppht_cluster_lm_kernel");

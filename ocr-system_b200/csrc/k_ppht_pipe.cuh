@@ -19,6 +19,7 @@ namespace lumina {
 
 constexpr int PPI_THREADS = 224;  // warp 0 control + up to 6 row warps (192 theta rows)
 
+template <bool LM>
 __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const PphtLmParams p) {
     cg::cluster_group cl = cg::this_cluster();
     const int CS = (int)cl.num_blocks();
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = p.h * p.w;
     const uint32_t *bits = p.bits + (size_t)page * p.bits_stride;
+    uint32_t *gbits = LM ? nullptr : p.gbits + ((size_t)page * 8 + rank) * p.bits_stride;   // private mask copy in L2
     const uint32_t *order = p.order + (size_t)page * px;
     int32_t *lines = p.lines + (size_t)page * p.max_lines * 4;
     const int N = p.count[page];
@@ -44,8 +46,14 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
     extern __shared__ __align__(16) unsigned char dynsm[];
     unsigned short *acc = reinterpret_cast<unsigned short *>(dynsm);                              // [slice_cells]
     uint32_t *mbits = reinterpret_cast<uint32_t *>(dynsm + (((size_t)p.slice_cells * 2 + 15) & ~(size_t)15));  // [(px+31)/32]
-    auto mask_set = [&](int bidx) -> bool { return (mbits[bidx >> 5] >> (bidx & 31)) & 1u; };
-    auto mask_clear = [&](int bidx) { atomicAnd(&mbits[bidx >> 5], ~(1u << (bidx & 31))); };
+    auto mask_set = [&](int bidx) -> bool {
+        if (LM) return (mbits[bidx >> 5] >> (bidx & 31)) & 1u;
+        return (__ldcg(gbits + (bidx >> 5)) >> (bidx & 31)) & 1u;
+    };
+    auto mask_clear = [&](int bidx) {
+        if (LM) atomicAnd(&mbits[bidx >> 5], ~(1u << (bidx & 31)));
+        else atomicAnd(gbits + (bidx >> 5), ~(1u << (bidx & 31)));  // result unused: RED to L2
+    };
     __shared__ uint32_t ordbuf[PCL_ORD];
     __shared__ uint32_t hkey[2][PCL_B];       // [batch parity][compact slot]
     __shared__ float2 lpt[2][PCL_B];          // [batch parity] compact table of the live points (x, y)
@@ -79,9 +87,12 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
     for (int i = tid; i < p.numangle * 3; i += PPI_THREADS) s_step[i] = p.step[i];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(bits);
-        uint4 *dst = reinterpret_cast<uint4 *>(mbits);
+        uint4 *dst = LM ? reinterpret_cast<uint4 *>(mbits) : reinterpret_cast<uint4 *>(gbits);
         const int nq = (((px + 31) >> 5) + 3) >> 2;
-        for (int i = tid; i < nq; i += PPI_THREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < nq; i += PPI_THREADS) {
+            const uint4 v = __ldg(src + i);
+            if (LM) dst[i] = v; else __stcg(dst + i, v);
+        }
     }
     // un-vote mapping: thread = (row ut, pixel phase us)
     const int nthpad = row_warps * 32;
