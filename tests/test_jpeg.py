@@ -127,3 +127,23 @@ def test_gpu_jpeg_degenerate_sizes_equal_pillow(cuda):
         for q, opt in [(95, True), (60, False), (1, True)]:
             got = ops.jpeg_encode(torch.from_numpy(a[None]).to(cuda), q, opt)[0]
             assert got == _pil(a, q, opt), (h, w, q, opt)
+
+
+@pytest.mark.gpu
+def test_gpu_batched_azure_path_mixed_sizes_and_modes(cuda, oracle):
+    """preprocess_pages_for_azure groups pages by (size, mode); results come back in input order and equal the
+    per-page call."""
+    from PIL import Image
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+
+    a = Image.fromarray(oracle.synth_page(877, 620, 0))
+    b = Image.fromarray(oracle.synth_page(620, 877, 1))
+    c = Image.fromarray(oracle.synth_page(877, 620, 2)).convert("L")
+    d = Image.fromarray(oracle.synth_page(300, 200, 3))          # below max_dimension: no resize
+    imgs = [a, b, c, a, d, b]
+    ip = ImagePreprocessor(max_dimension=400)
+    got = ip.preprocess_pages_for_azure(imgs, target_size_mb=0.05)
+    assert len(got) == len(imgs) and got[0] == got[3] and got[1] == got[5]
+    for im, g in zip(imgs, got):
+        assert g == ip.preprocess_for_azure(im, target_size_mb=0.05)
+        assert Image.open(io.BytesIO(g)).mode == "RGB" and len(g) <= int(0.05 * 1024 * 1024)
