@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.1)   # NVML calls share a driver lock with kernel launches: sample sparsely
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
