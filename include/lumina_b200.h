@@ -87,6 +87,9 @@ int lumina_median3_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w,
 /* ---- a8  binarize :175-185 (convert L, point >thr -> mode "1") ---------- */
 /* c==3: fused PIL gray.  dst [n][h][w] in {0,255}. */
 int lumina_binarize_u8(const uint8_t *d_src, uint8_t *d_dst, size_t npx, int c, int threshold, void *stream);
+/* Ingest helper (load_image / pdf_to_images, image_preprocessing.py:57-75, :248-295): Pillow keeps mode "RGB"
+ * images as 4 bytes per pixel (R, G, B, pad); npx such pixels -> tightly packed R, G, B. */
+int lumina_rgbx_to_rgb_u8(const uint8_t *d_src, uint8_t *d_dst, size_t npx, void *stream);
 
 /* ---- a9  adaptive_binarize :462-494 (cv2.adaptiveThreshold GAUSSIAN 11,C) */
 /* c==3: fused PIL gray.  dst [n][h][w] in {0,255}. */

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "lumina_contrast_sharpness_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _F, _F, _P]),
     "lumina_median3_u8": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "lumina_binarize_u8": (_I, [_P, _P, _Z, _I, _I, _P]),
+    "lumina_rgbx_to_rgb_u8": (_I, [_P, _P, _Z, _P]),
     "lumina_adaptive_gauss11_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "lumina_canny_workspace_bytes": (_Z, [_I, _I, _I]),
     "lumina_canny_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),

@@ -247,6 +247,47 @@ LUMINA_API int lumina_rgb2gray_pil_u8(const uint8_t *d_rgb, uint8_t *d_gray, siz
 LUMINA_API int lumina_rgb2gray_cv_u8(const uint8_t *d_rgb, uint8_t *d_gray, size_t npx, void *stream) {
     return gray_launch(1, 0, d_rgb, d_gray, npx, 0, as_stream(stream));
 }
+// ---- ingest: Pillow keeps RGB images as 4 bytes per pixel (R, G, B, pad); drop the pad byte --------------
+// 16 pixels per thread: four 128-bit loads, three 128-bit stores
+__global__ void __launch_bounds__(256) rgbx_to_rgb16_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t npx) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p0 = t * 16;
+    if (p0 >= npx) return;
+    if (p0 + 16 <= npx) {
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 v = ldg_stream_u4(src + p0 * 4 + k * 16);
+            w[k * 4] = v.x; w[k * 4 + 1] = v.y; w[k * 4 + 2] = v.z; w[k * 4 + 3] = v.w;
+        }
+        uint32_t o[12];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {   // 4 pixels (r g b x)*4 -> 3 words
+            const uint32_t a = w[q * 4], b = w[q * 4 + 1], c = w[q * 4 + 2], d = w[q * 4 + 3];
+            o[q * 3 + 0] = __byte_perm(a, b, 0x4210);            // r0 g0 b0 r1
+            o[q * 3 + 1] = __byte_perm(b, c, 0x5421);            // g1 b1 r2 g2
+            o[q * 3 + 2] = __byte_perm(c, d, 0x6542);            // b2 r3 g3 b3
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) stg_stream_u4(dst + p0 * 3 + k * 16, make_uint4(o[k * 4], o[k * 4 + 1], o[k * 4 + 2], o[k * 4 + 3]));
+    } else {
+        for (size_t p = p0; p < npx; p++) {
+            dst[p * 3] = src[p * 4]; dst[p * 3 + 1] = src[p * 4 + 1]; dst[p * 3 + 2] = src[p * 4 + 2];
+        }
+    }
+}
+
+// npx pixels of R,G,B,pad (Pillow's in-memory layout of mode "RGB") -> tightly packed R,G,B
+LUMINA_API int lumina_rgbx_to_rgb_u8(const uint8_t *d_src, uint8_t *d_dst, size_t npx, void *stream) {
+    LUMINA_REQUIRE(d_src && d_dst, "null pointer");
+    if (npx == 0) return LUMINA_OK;
+    LUMINA_REQUIRE((((uintptr_t)d_src) & 15) == 0 && (((uintptr_t)d_dst) & 15) == 0, "buffers must be 16-byte aligned");
+    const size_t threads = (npx + 15) / 16;
+    rgbx_to_rgb16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(d_src, d_dst, npx);
+    LUMINA_KERNEL_CHECK("rgbx_to_rgb16_kernel");
+    return LUMINA_OK;
+}
+
 LUMINA_API int lumina_binarize_u8(const uint8_t *d_src, uint8_t *d_dst, size_t npx, int c, int threshold, void *stream) {
     LUMINA_REQUIRE(c == 1 || c == 3, "c must be 1 or 3");
     if (c == 3) return gray_launch(0, 1, d_src, d_dst, npx, threshold, as_stream(stream));

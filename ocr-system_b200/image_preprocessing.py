@@ -57,6 +57,7 @@ class ImagePreprocessor:
         self.max_dimension = max_dimension or _setting("OCR_MAX_IMAGE_DIMENSION", 2000)
         self.target_dpi = target_dpi
         self._device = device
+        self._raise_pil_block_size()   # images opened / rasterised from now on qualify for the zero-copy ingest
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -65,16 +66,79 @@ class ImagePreprocessor:
             raise RuntimeError("ocr_system_b200 needs a CUDA device: there is no CPU fallback for the pixel path")
         return torch.device(self._device or f"cuda:{torch.cuda.current_device()}")
 
+    # ------------------------------------------------------------------ ingest
+    # np.asarray(image) runs Pillow's raw encoder (7-10 ms per A4 page, holds the GIL).  Pillow also exports its own
+    # storage through the Arrow C data interface without a copy -- mode "RGB" as 4 bytes per pixel (R, G, B, pad),
+    # mode "L" as bytes -- when the image lives in ONE allocator block; a plain (GIL-free, threaded) copy of that
+    # view into the pinned staging buffer is ~0.5 ms per page, and the pad byte is dropped on the device.  Pillow's
+    # block size (16 MB by default) is raised once so that A4 300-dpi pages (35 MB as RGBX) qualify; images that
+    # were allocated earlier, other modes or a missing pyarrow simply take the np.asarray path.
+    _BLOCK_MB = int(os.environ.get("LUMINA_PIL_BLOCK_MB", "64"))
+
+    @classmethod
+    def _raise_pil_block_size(cls) -> None:
+        try:
+            if Image.core.get_block_size() < cls._BLOCK_MB << 20:
+                Image.core.set_block_size(cls._BLOCK_MB << 20)
+        except Exception:  # noqa: BLE001 - a tuning knob, never an error
+            pass
+
+    @staticmethod
+    def _zero_copy_view(image: Image.Image) -> Optional[np.ndarray]:
+        """[H,W,4] (mode RGB) or [H,W] (mode L) view of Pillow's own pixel storage, or None."""
+        try:
+            import pyarrow as pa
+
+            image.load()
+            arr = pa.array(image)
+            w, h = image.size
+            if image.mode == "RGB":
+                v = arr.flatten().to_numpy(zero_copy_only=True)
+                return v.reshape(h, w, 4) if v.size == h * w * 4 else None
+            if image.mode == "L":
+                v = arr.to_numpy(zero_copy_only=True)
+                return v.reshape(h, w) if v.size == h * w else None
+        except Exception:  # noqa: BLE001 - multi-block image, unsupported mode, no pyarrow: fall back
+            return None
+        return None
+
+    def _upload(self, images: Sequence[Image.Image]) -> torch.Tensor:
+        """Same-size, same-mode (RGB or L) PIL images -> one resident batch [N,H,W,C]."""
+        w, h = images[0].size
+        mode = images[0].mode
+        if mode not in ("RGB", "L"):
+            raise ValueError(f"unsupported image mode {mode!r}: load_image() converts to RGB/L first")
+        n = len(images)
+        views = [self._zero_copy_view(im) for im in images]
+        fast = all(v is not None for v in views)
+        c_mem = (4 if mode == "RGB" else 1) if fast else (3 if mode == "RGB" else 1)
+        stage = self._host_stage(n, h, w, c_mem)
+        sview = stage.numpy()
+
+        def put(j):
+            if fast:
+                np.copyto(sview[j], views[j].reshape(h, w, c_mem))          # memcpy, releases the GIL
+            else:
+                sview[j] = np.asarray(images[j]).reshape(h, w, c_mem)
+
+        if n == 1:
+            put(0)
+        else:
+            with ThreadPoolExecutor(max_workers=min(8, n)) as ex:
+                list(ex.map(put, range(n)))
+        x = stage[:n].to(self.device, non_blocking=True)
+        if fast and mode == "RGB":
+            x = ops.rgbx_to_rgb(x)
+        torch.cuda.current_stream(x.device).synchronize()   # the staging buffer is reused by the next call
+        return x
+
     def _to_device(self, image: Image.Image) -> torch.Tensor:
         if image.mode not in ("RGB", "L"):
             raise ValueError(f"unsupported image mode {image.mode!r}: load_image() converts to RGB/L first")
-        arr = np.asarray(image)
-        if not arr.flags["C_CONTIGUOUS"] or not arr.flags["WRITEABLE"]:
-            arr = np.array(arr)
-        t = torch.from_numpy(arr).unsqueeze(0)
-        if t.dim() == 3:  # L -> [1,H,W,1]: every batch on the device is NHWC
-            t = t.unsqueeze(-1)
-        return t.to(self.device, non_blocking=False)
+        x = self._upload([image])
+        if x.dim() == 3:  # L -> [1,H,W,1]: every batch on the device is NHWC
+            x = x.unsqueeze(-1)
+        return x
 
     @staticmethod
     def _to_pil(t: torch.Tensor) -> Image.Image:
@@ -355,16 +419,7 @@ class ImagePreprocessor:
         for ((w, h), mode), idx in groups.items():
             if mode not in ("RGB", "L"):
                 raise ValueError(f"unsupported image mode {mode!r}: load_image() converts to RGB/L first")
-            c = 3 if mode == "RGB" else 1
-            stage = self._host_stage(len(idx), h, w, c)
-            view = stage.numpy()
-
-            def unpack(j, i=None):   # Pillow's raw encoder -> the pinned staging slot, one thread per page
-                view[j] = np.asarray(imgs[idx[j]]).reshape(h, w, c)
-
-            with ThreadPoolExecutor(max_workers=min(8, len(idx))) as ex:
-                list(ex.map(unpack, range(len(idx))))
-            x = stage[: len(idx)].to(self.device, non_blocking=True)
+            x = self._upload([imgs[i] for i in idx])
             x, _ = self.preprocess_device(x, apply_deskew, apply_binarize, apply_contrast, apply_sharpness)
             for i, b in zip(idx, self.compress_pages_for_azure(x, target_size_mb=target_size_mb)):
                 out[i] = b

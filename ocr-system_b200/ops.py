@@ -255,6 +255,17 @@ class HoughJob:
         return lines, nlines
 
 
+def rgbx_to_rgb(pages_rgbx: torch.Tensor) -> torch.Tensor:
+    """[N,H,W,4] uint8 (Pillow's in-memory R,G,B,pad) -> [N,H,W,3]."""
+    if not pages_rgbx.is_cuda or pages_rgbx.dtype != torch.uint8 or pages_rgbx.dim() != 4 or pages_rgbx.shape[-1] != 4:
+        raise TypeError("rgbx_to_rgb expects a CUDA uint8 [N,H,W,4] tensor")
+    x = pages_rgbx.contiguous()
+    out = torch.empty(x.shape[:3] + (3,), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _chk(_L().lumina_rgbx_to_rgb_u8(_ptr(x), _ptr(out), x.shape[0] * x.shape[1] * x.shape[2], _stream()))
+    return out
+
+
 def median_angle(lines_host: np.ndarray) -> float:
     """image_preprocessing.py:414-428 on the host (libm atan2, like numpy)."""
     a = np.ascontiguousarray(lines_host, dtype=np.int32)

@@ -14,6 +14,7 @@ from ocr_system_b200.image_preprocessing import ImagePreprocessor
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     O.build()
+    ImagePreprocessor()   # first, as in the app (the singleton exists before pages are rasterised): raises Pillow's block size
     pages = np.stack([O.synth_page(3508, 2480, s) for s in range(n)])
     imgs = [Image.fromarray(pages[i]) for i in range(n)]
     res = {}
