@@ -256,3 +256,30 @@ def test_pipelined_stream_equals_sequential_steps(oracle, cuda):
     assert torch.equal(n1, n2)
     for i in range(edges.shape[0]):
         assert torch.equal(l1[i, : int(n1[i])], l2[i, : int(n2[i])])
+
+
+def test_ingest_zero_copy_and_fallback_agree(cuda):
+    """PIL pages reach the device the same whether Pillow's storage can be viewed through Arrow (one allocator
+    block) or has to go through np.asarray (multi-block image, odd L width)."""
+    import torch
+    from PIL import Image
+    from ocr_system_b200 import ops
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+
+    rng = np.random.default_rng(3)
+    x4 = torch.from_numpy(rng.integers(0, 256, (2, 37, 53, 4), dtype=np.uint8)).to(cuda)   # 1961 px: not a multiple of 16
+    assert torch.equal(ops.rgbx_to_rgb(x4), x4[..., :3].contiguous())
+    ip = ImagePreprocessor(max_dimension=4000)
+    big = rng.integers(0, 256, (1200, 900, 3), dtype=np.uint8)
+    old = Image.core.get_block_size()
+    try:
+        Image.core.set_block_size(1 << 20)                 # 1 MB blocks: the 4.3 MB image below is multi-block
+        multi = Image.fromarray(big).copy()
+    finally:
+        Image.core.set_block_size(old)
+    single = Image.fromarray(big).copy()
+    assert ip._zero_copy_view(multi) is None and ip._zero_copy_view(single) is not None
+    for imgs in ([multi, multi], [single, single, single], [single.convert("L")], [single.convert("L").crop((0, 0, 899, 1200))]):
+        got = ip._upload(imgs).cpu().numpy()
+        want = np.stack([np.asarray(im).reshape(im.size[1], im.size[0], -1) for im in imgs])
+        assert np.array_equal(got, want)
