@@ -223,6 +223,7 @@ def main_ours(args):
     torch.cuda.synchronize()
     barrier()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_unpipelined, launches0 = launches, ops.launch_count()
     p0.record()
     for r in pipe.run_device_stream([pages] * K):
         angles = r.angles
@@ -231,6 +232,8 @@ def main_ours(args):
     torch.cuda.synchronize()
     barrier()
     elapsed_ms = max_over_ranks(p0.elapsed_time(p1))
+    launches = ops.launch_count() - launches0      # kernels of the timed (pipelined) region
+    assert launches == launches_unpipelined, (launches, launches_unpipelined)   # same work either way
     clocks = sampler.stop()
     stage_ms = {}
     for t in timers:
