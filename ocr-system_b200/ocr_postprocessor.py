@@ -11,7 +11,7 @@ in one launch.  There is no CPU fallback: without the CUDA library these functio
 Coordinates and confidences travel as float64 (Python floats), sums follow CPython's ``sum()``.
 """
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -48,29 +48,32 @@ class MergedLine:
     blocks: List[TextBlock]
 
 
+def _as_block(item) -> Optional[TextBlock]:
+    """One detector item -> TextBlock, or None for a shape the reference silently skips."""
+    if all(hasattr(item, k) for k in ("box", "text", "score")):                  # dataclass items of newer RapidOCR
+        quad = item.box if isinstance(item.box, list) else item.box.tolist()
+        return TextBlock(text=item.text, confidence=item.score, box=quad)
+    if isinstance(item, (list, tuple)) and len(item) >= 3:                        # [box, text, confidence]
+        quad = item[0].tolist() if hasattr(item[0], "tolist") else item[0]
+        return TextBlock(text=str(item[1]), confidence=float(item[2]), box=quad)
+    return None
+
+
 def parse_rapidocr_output(result) -> List[TextBlock]:
-    """ocr_postprocessor.py:51-98: dataclass items (``box``/``text``/``score``) or ``[box, text, conf]``
-    lists; items that fail to parse are reported and skipped, as in the reference."""
+    """ocr_postprocessor.py:51-98.  Accepts a RapidOCR result object (``.ocr_result``) or a plain sequence;
+    an item that raises while being read is reported on stdout and skipped, exactly like the reference."""
+    items = getattr(result, "ocr_result", result) if result is not None else None
     blocks: List[TextBlock] = []
-    if result is None:
-        return blocks
-    items = result.ocr_result if hasattr(result, "ocr_result") else result
     if items is None:
         return blocks
     for item in items:
         try:
-            if hasattr(item, "box") and hasattr(item, "text") and hasattr(item, "score"):
-                blocks.append(TextBlock(text=item.text, confidence=item.score,
-                                        box=item.box if isinstance(item.box, list) else item.box.tolist()))
-            elif isinstance(item, (list, tuple)) and len(item) >= 3:
-                box, text = item[0], item[1]
-                conf = item[2] if len(item) > 2 else 1.0
-                if hasattr(box, "tolist"):
-                    box = box.tolist()
-                blocks.append(TextBlock(text=str(text), confidence=float(conf), box=box))
+            blk = _as_block(item)
         except Exception as e:  # noqa: BLE001 - reference behaviour: report and continue
             print(f"  ⚠️ Failed to parse item: {e}")
             continue
+        if blk is not None:
+            blocks.append(blk)
     return blocks
 
 
@@ -161,14 +164,12 @@ def process_ocr_result(result, y_tolerance_ratio: float = 0.5, merge_lines: bool
 
 
 def format_merged_output(merged_lines: List[MergedLine], show_confidence: bool = False) -> str:
-    """ocr_postprocessor.py:216-226."""
-    output = []
-    for i, line in enumerate(merged_lines, 1):
-        if show_confidence:
-            output.append(f"{i:02d}. [{line.confidence:.2f}] {line.text}")
-        else:
-            output.append(f"{i:02d}. {line.text}")
-    return "\n".join(output)
+    """ocr_postprocessor.py:216-226: ``NN. text`` per line, with ``[conf]`` between them on request."""
+    def row(i: int, ln: MergedLine) -> str:
+        conf = f"[{ln.confidence:.2f}] " if show_confidence else ""
+        return f"{i:02d}. {conf}{ln.text}"
+
+    return "\n".join(row(i, ln) for i, ln in enumerate(merged_lines, 1))
 
 
 def extract_text_ordered(result, y_tolerance: float = 0.5) -> str:
