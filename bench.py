@@ -172,6 +172,8 @@ def main_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from ocr_system_b200.pipeline import bind_host_to_gpu_numa_node
+    numa_node = bind_host_to_gpu_numa_node(local) if world > 1 else None   # staging memory next to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -312,7 +314,7 @@ def main_ours(args):
             "dtype": "u8", "data": "synthetic", "config": _workload(args),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / K, "pinned_h2d_GBps": round(h2d_gbps, 1),
-                    "h2d_bound_ms_per_step": round(h2d / (h2d_gbps * 1e9) * 1e3, 2),
+                    "h2d_bound_ms_per_step": round(h2d / (h2d_gbps * 1e9) * 1e3, 2), "host_numa_node_rank0": numa_node,
                     "cold_start": {"value": world * B * K / (e2e_cold_ms / 1e3), "ms_per_step": e2e_cold_ms / K,
                                    "note": "same K batches from an idle pipeline (one un-overlapped upload per K steps)"},
                     "note": "steady state of PagePipeline.run_host_stream: pinned host rasters -> HBM -> chain -> results "
