@@ -22,6 +22,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
+import os
 import threading
 
 import torch
@@ -191,16 +192,16 @@ class PagePipeline:
                 ten.record_stream(main)
             return res
 
-        prev = None
+        depth = max(1, int(os.environ.get("LUMINA_STREAM_DEPTH", "2")))   # batches enqueued ahead of the one being finished
+        pending = []
         for i, pages in enumerate(batches):
             if not pages.is_cuda:
                 raise TypeError("run_device_stream needs CUDA tensors")
-            job = start(i, pages)
-            if prev is not None:
-                yield finish(prev)
-            prev = job
-        if prev is not None:
-            yield finish(prev)
+            pending.append(start(i, pages))
+            if len(pending) > depth - 1 and len(pending) > 1:
+                yield finish(pending.pop(0))
+        while pending:
+            yield finish(pending.pop(0))
 
     _rotate_stage = None   # pinned staging for the line lists (shape-keyed)
 
