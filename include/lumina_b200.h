@@ -59,6 +59,13 @@ size_t lumina_resize_workspace_bytes(const lumina_resize_plan *plan, int n, int 
 int lumina_resize_lanczos_u8(const lumina_resize_plan *plan, const uint8_t *d_src, uint8_t *d_dst, int n,
                              int c, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Image.resize on mode "P" / "1" objects: Pillow forces NEAREST there (Geometry.c ImagingScaleAffine).  The table
+ * of source indices per output coordinate is built on the host exactly as Pillow accumulates it (double, repeated
+ * addition); planes are [n][h][w] single-byte pixels (palette indices, or 0/255 for mode "1"). */
+void lumina_nearest_table_host(int in_size, int out_size, int32_t *h_tab);
+int lumina_resize_nearest_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int in_h, int in_w, int out_h, int out_w,
+                             const int32_t *d_xtab, const int32_t *d_ytab, void *stream);
+
 /* ---- a4  convert_to_grayscale :167-169 ; deskew's cv gray :394-396 ------ */
 int lumina_rgb2gray_pil_u8(const uint8_t *d_rgb, uint8_t *d_gray, size_t npx, void *stream);
 int lumina_rgb2gray_cv_u8(const uint8_t *d_rgb, uint8_t *d_gray, size_t npx, void *stream);
@@ -172,10 +179,11 @@ int lumina_db_mask_ccl(const float *d_pred, int n, int h, int w, float thresh, u
  *   d_line_of[k] = 0-based line of that block (lines top to bottom, blocks left to right),
  *   d_nlines[p], d_line_conf[l] = mean confidence, d_line_y[l] = mean y_center of line l (f64).
  * Stable sorts and float64 sums exactly as the reference's Python (sum() as in CPython >= 3.12).
- * y_tolerance_ratio < 0: every page is ONE line whose input order breaks x ties (sort_and_merge_lines on
- * lines that were grouped elsewhere).  max_boxes_per_page >= the largest page, <= 4096. */
+ * one_line != 0: every page is ONE line whose input order breaks x ties (sort_and_merge_lines on lines that
+ * were grouped elsewhere); the ratio is then unused.  A negative or NaN ratio keeps the reference's meaning
+ * (the tolerance test never holds: one line per block).  max_boxes_per_page >= the largest page, <= 4096. */
 int lumina_reading_order(const double *d_boxes, const double *d_conf, const int32_t *d_offsets, int n_pages,
-                         int max_boxes_per_page, double y_tolerance_ratio, int32_t *d_order,
+                         int max_boxes_per_page, double y_tolerance_ratio, int one_line, int32_t *d_order,
                          int32_t *d_line_of, int32_t *d_nlines, double *d_line_conf, double *d_line_y,
                          void *stream);
 

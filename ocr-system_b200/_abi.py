@@ -34,6 +34,8 @@ PROTOTYPES = {
     "lumina_resize_plan_destroy": (None, [_P]),
     "lumina_resize_workspace_bytes": (_Z, [_P, _I, _I]),
     "lumina_resize_lanczos_u8": (_I, [_P, _P, _P, _I, _I, _P, _Z, _P]),
+    "lumina_nearest_table_host": (None, [_I, _I, _P]),
+    "lumina_resize_nearest_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "lumina_rgb2gray_pil_u8": (_I, [_P, _P, _Z, _P]),
     "lumina_rgb2gray_cv_u8": (_I, [_P, _P, _Z, _P]),
     "lumina_contrast_mean_u8": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
@@ -61,7 +63,7 @@ PROTOTYPES = {
     "lumina_db_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "lumina_db_postprocess": (_I, [_P, _I, _I, _I, _F, _D, _D, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "lumina_db_mask_ccl": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
-    "lumina_reading_order": (_I, [_P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P, _P]),
+    "lumina_reading_order": (_I, [_P, _P, _P, _I, _I, _D, _I, _P, _P, _P, _P, _P, _P]),
     "lumina_jpeg_workspace_bytes": (_Z, [_I, _I, _I]),
     "lumina_jpeg_encode_rgb": (_I, [_P, _I, _I, _I, _I, _I, _P, _Z, _P, _P, _Z, _P]),
     "lumina_synth_pages_u8": (_I, [_P, _I, _I, _I, C.c_uint64, _P]),

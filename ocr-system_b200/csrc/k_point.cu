@@ -213,11 +213,23 @@ __global__ void __launch_bounds__(256) exif_kernel(const uint8_t *__restrict__ s
     for (int k = 0; k < C; k++) d[k] = __ldg(s + k);
 }
 
+// Pillow NEAREST resize (Geometry.c ImagingScaleAffine): dst[y][x] = src[ytab[y]][xtab[x]], single-byte pixels
+__global__ void __launch_bounds__(256) resize_nearest_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int in_h,
+                                                             int in_w, int out_h, int out_w, const int32_t *__restrict__ xtab,
+                                                             const int32_t *__restrict__ ytab) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= out_w) return;
+    const int sx = xtab[x], sy = ytab[y];
+    const size_t page = blockIdx.z;
+    const uint8_t v = (sx >= 0 && sy >= 0) ? __ldg(src + (page * in_h + sy) * (size_t)in_w + sx) : (uint8_t)0;
+    dst[(page * out_h + y) * (size_t)out_w + x] = v;
+}
+
 }  // namespace lumina
 
 using namespace lumina;
 
-LUMINA_API int lumina_abi_version(void) { return 1; }
+LUMINA_API int lumina_abi_version(void) { return 2; }
 LUMINA_API const char *lumina_last_error_string(void) { return g_err; }
 LUMINA_API uint64_t lumina_launch_count(void) { return g_launches.load(); }
 
@@ -238,6 +250,28 @@ static int gray_launch(int mode, int post, const uint8_t *d_rgb, uint8_t *d_out,
     else if (mode == 1 && post == 0) gray16_kernel<1, 0><<<grid, 256, 0, st>>>(d_rgb, d_out, npx, thr);
     else gray16_kernel<0, 1><<<grid, 256, 0, st>>>(d_rgb, d_out, npx, thr);
     LUMINA_KERNEL_CHECK("gray16_kernel");
+    return LUMINA_OK;
+}
+
+// Pillow resizes mode "P" / "1" images with NEAREST whatever filter is asked for (Image.resize); the source index of
+// output x is (int)(a/2 + x*a) with the products accumulated by repeated addition in double (ImagingScaleAffine)
+LUMINA_API void lumina_nearest_table_host(int in_size, int out_size, int32_t *h_tab) {
+    const double a = (double)in_size / (double)out_size;
+    double xo = 0.0 + a * 0.5;
+    for (int x = 0; x < out_size; x++) {
+        const int xin = xo < 0.0 ? -1 : (int)xo;
+        h_tab[x] = (xin >= 0 && xin < in_size) ? xin : -1;
+        xo += a;
+    }
+}
+
+LUMINA_API int lumina_resize_nearest_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int in_h, int in_w, int out_h, int out_w,
+                                        const int32_t *d_xtab, const int32_t *d_ytab, void *stream) {
+    LUMINA_REQUIRE(d_src && d_dst && d_xtab && d_ytab, "null pointer");
+    LUMINA_REQUIRE(n > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && out_h <= 65535 && n <= 65535, "bad geometry");
+    dim3 grid(div_up(out_w, 256), out_h, n);
+    resize_nearest_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_src, d_dst, in_h, in_w, out_h, out_w, d_xtab, d_ytab);
+    LUMINA_KERNEL_CHECK("resize_nearest_kernel");
     return LUMINA_OK;
 }
 

@@ -66,7 +66,8 @@ __device__ void ro_bitonic(RoKey *keys, int npad) {
 }
 
 __global__ void __launch_bounds__(RO_THREADS) reading_order_kernel(const double *__restrict__ boxes, const double *__restrict__ conf,
-                                                                   const int32_t *__restrict__ offsets, double ratio, int32_t *__restrict__ order,
+                                                                   const int32_t *__restrict__ offsets, double ratio, int one_line_mode,
+                                                                   int32_t *__restrict__ order,
                                                                    int32_t *__restrict__ line_of, int32_t *__restrict__ nlines,
                                                                    double *__restrict__ line_conf, double *__restrict__ line_y, int npad) {
     extern __shared__ __align__(16) unsigned char ro_smem[];
@@ -82,7 +83,9 @@ __global__ void __launch_bounds__(RO_THREADS) reading_order_kernel(const double 
         return;
     }
     const double *bx = boxes + (size_t)o0 * 8;
-    const bool one_line = ratio < 0;  // pre-grouped input: the page is one line, input order breaks x ties
+    const bool one_line = one_line_mode != 0;  // pre-grouped input: the page is one line, input order breaks x ties
+    // (a negative or NaN ratio is NOT that mode: like the reference, abs(dy) <= tol is then never true and
+    //  every block opens its own line)
     // TextBlock.y_center / x_left (ocr_postprocessor.py:26-35)
     for (int i = tid; i < npad; i += RO_THREADS) {
         RoKey k;
@@ -168,7 +171,7 @@ using namespace lumina;
 
 // ocr_postprocessor.py:101-182 for a batch of pages (see include/lumina_b200.h)
 LUMINA_API int lumina_reading_order(const double *d_boxes, const double *d_conf, const int32_t *d_offsets, int n_pages,
-                                    int max_boxes_per_page, double y_tolerance_ratio, int32_t *d_order, int32_t *d_line_of,
+                                    int max_boxes_per_page, double y_tolerance_ratio, int one_line, int32_t *d_order, int32_t *d_line_of,
                                     int32_t *d_nlines, double *d_line_conf, double *d_line_y, void *stream) {
     LUMINA_REQUIRE(d_boxes && d_conf && d_offsets && d_order && d_line_of && d_nlines && d_line_conf && d_line_y, "null pointer");
     LUMINA_REQUIRE(n_pages > 0, "empty batch");
@@ -178,7 +181,7 @@ LUMINA_API int lumina_reading_order(const double *d_boxes, const double *d_conf,
     const size_t smem = (size_t)npad * (sizeof(RoKey) + 16) + (size_t)(npad + 1) * 4;
     if (smem > 48 * 1024)
         LUMINA_CUDA_TRY(cudaFuncSetAttribute(reading_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reading_order_kernel<<<n_pages, RO_THREADS, smem, as_stream(stream)>>>(d_boxes, d_conf, d_offsets, y_tolerance_ratio, d_order,
+    reading_order_kernel<<<n_pages, RO_THREADS, smem, as_stream(stream)>>>(d_boxes, d_conf, d_offsets, y_tolerance_ratio, one_line, d_order,
                                                                           d_line_of, d_nlines, d_line_conf, d_line_y, npad);
     LUMINA_KERNEL_CHECK("reading_order_kernel");
     return LUMINA_OK;

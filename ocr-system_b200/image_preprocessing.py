@@ -18,6 +18,7 @@ import io
 from concurrent.futures import ThreadPoolExecutor
 import logging
 import os
+import threading
 from pathlib import Path
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -57,6 +58,10 @@ class ImagePreprocessor:
         self.max_dimension = max_dimension or _setting("OCR_MAX_IMAGE_DIMENSION", 2000)
         self.target_dpi = target_dpi
         self._device = device
+        # The reference singleton is stateless and is called from asyncio.to_thread workers
+        # (services/ocr_service.py:674-676).  This one owns a pinned staging buffer and a JPEG workspace: both are
+        # per calling thread, so concurrent callers never see each other's pixels or DCT coefficients.
+        self._tls = threading.local()
         self._raise_pil_block_size()   # images opened / rasterised from now on qualify for the zero-copy ingest
 
     # ------------------------------------------------------------------ plumbing
@@ -140,6 +145,42 @@ class ImagePreprocessor:
             x = x.unsqueeze(-1)
         return x
 
+    # ---- PIL modes beyond RGB / L ---------------------------------------------------------------------------
+    # The reference hands whatever PIL object it gets to Pillow, so its methods also work on RGBA / LA / RGBX /
+    # CMYK / YCbCr / HSV objects (8-bit bands; Pillow processes them band by band) and, where the method starts
+    # with an explicit ``image.convert(...)`` (grayscale, binarize, adaptive_binarize, deskew, compress), on every
+    # mode.  Here the bands of such an image travel as a batch of single-channel planes [bands,H,W,1] through the
+    # same kernels; mode changes themselves (palette lookup, CMYK->RGB, alpha premultiply) stay Pillow's, on the
+    # host, exactly like ``load_image``'s ``convert('RGB')``.  Modes Pillow itself refuses for an operator (P, 1,
+    # I, F ... in ImageEnhance / ImageFilter) raise the same ValueError.
+    _BANDED = ("RGBA", "LA", "RGBX", "CMYK", "YCbCr", "HSV", "RGBa", "La")
+
+    def _planes_to_device(self, image: Image.Image) -> torch.Tensor:
+        a = np.asarray(image)
+        planes = np.ascontiguousarray(np.moveaxis(a, -1, 0))[..., None]
+        return torch.from_numpy(planes).to(self.device)
+
+    @staticmethod
+    def _planes_to_pil(t: torch.Tensor, mode: str) -> Image.Image:
+        a = np.ascontiguousarray(np.moveaxis(t.squeeze(-1).cpu().numpy(), 0, -1))
+        return Image.frombytes(mode, (a.shape[1], a.shape[0]), a.tobytes())
+
+    def _check_banded(self, image: Image.Image, what: str) -> None:
+        if image.mode not in self._BANDED:
+            # Pillow: ImageEnhance / ImageFilter on P, 1, I, F, I;16 ... -> ValueError("image has wrong mode")
+            raise ValueError(f"image has wrong mode ({image.mode!r} is not supported by {what}; "
+                             "load_image() converts to RGB/L first)")
+
+    def _gray_source(self, image: Image.Image) -> torch.Tensor:
+        """Device input whose PIL-L conversion equals ``image.convert('L')`` (reference :169,:184,:481)."""
+        if image.mode in ("RGB", "L"):
+            return self._to_device(image)
+        if image.mode == "YCbCr":                      # Pillow: YCbCr -> L is the Y band
+            return self._to_device(image.getchannel(0))
+        # every other mode: convert('L') == convert('RGB').convert('L') (same L24 weights; verified per mode in
+        # tests/test_gpu_modes.py), so the mode change is Pillow's and the grayscale is the kernel's
+        return self._to_device(image.convert("RGB"))
+
     @staticmethod
     def _to_pil(t: torch.Tensor) -> Image.Image:
         a = t[0]
@@ -177,31 +218,78 @@ class ImagePreprocessor:
             return image
         new_w, new_h = ops.target_size(width, height, max_dim)
         logger.info(f"Resizing image from {width}x{height} to {new_w}x{new_h}")
-        return self._to_pil(ops.resize_lanczos(self._to_device(image), new_w, new_h))
+        if image.mode in ("RGB", "L"):
+            return self._to_pil(ops.resize_lanczos(self._to_device(image), new_w, new_h))
+        if image.mode in ("P", "1"):      # Pillow's Image.resize forces NEAREST for these two modes
+            idx = image if image.mode == "P" else image.convert("L")        # palette indices / 0-255 bytes
+            plane = torch.from_numpy(np.frombuffer(idx.tobytes(), np.uint8).reshape(1, height, width)).to(self.device)
+            raw = ops.resize_nearest(plane, new_w, new_h)[0].cpu().numpy().tobytes()
+            if image.mode == "1":
+                return Image.frombytes("L", (new_w, new_h), raw).convert("1", dither=Image.Dither.NONE)
+            out = Image.frombytes("P", (new_w, new_h), raw)
+            out.putpalette(image.getpalette(image.palette.mode), image.palette.mode)
+            if "transparency" in image.info:
+                out.info["transparency"] = image.info["transparency"]
+            return out
+        self._check_banded(image, "resize")
+        # Pillow's Image.resize: RGBA / LA are resampled premultiplied (RGBa / La) and converted back
+        pre = {"RGBA": "RGBa", "LA": "La"}.get(image.mode)
+        src = image.convert(pre) if pre else image
+        out = self._planes_to_pil(ops.resize_lanczos(self._planes_to_device(src), new_w, new_h), src.mode)
+        return out.convert(image.mode) if pre else out
 
     # ------------------------------------------------------------------ enhancement
     def enhance_contrast(self, image: Image.Image, factor: float = 1.3) -> Image.Image:
-        return self._to_pil(ops.enhance_contrast(self._to_device(image), factor))
+        if image.mode in ("RGB", "L"):
+            return self._to_pil(ops.enhance_contrast(self._to_device(image), factor))
+        # ImageEnhance.Contrast: mean of convert('L'); degenerate = that grey in the image's mode (alpha kept)
+        self._check_banded(image, "ImageEnhance.Contrast")
+        if image.mode in ("RGBa", "La"):
+            raise ValueError(f"conversion from L to {image.mode} not supported")      # Pillow's own error
+        mean = int(ops.contrast_mean(self._gray_source(image)).cpu()[0])
+        grey = Image.new("L", (1, 1), mean).convert(image.mode).getpixel((0, 0))
+        x = self._planes_to_device(image)
+        keep = [i for i, b in enumerate(image.getbands()) if b != "A"]
+        m = torch.tensor([grey[i] for i in keep], dtype=torch.int32, device=x.device)
+        x[keep] = ops.enhance_contrast(x[keep].contiguous(), factor, mean=m)
+        return self._planes_to_pil(x, image.mode)
 
     def enhance_sharpness(self, image: Image.Image, factor: float = 1.2) -> Image.Image:
-        return self._to_pil(ops.enhance_sharpness(self._to_device(image), factor))
+        if image.mode in ("RGB", "L"):
+            return self._to_pil(ops.enhance_sharpness(self._to_device(image), factor))
+        self._check_banded(image, "ImageEnhance.Sharpness")
+        x = self._planes_to_device(image)
+        keep = [i for i, b in enumerate(image.getbands()) if b != "A"]   # degenerate.putalpha(image alpha)
+        x[keep] = ops.enhance_sharpness(x[keep].contiguous(), factor)
+        return self._planes_to_pil(x, image.mode)
 
     def denoise(self, image: Image.Image) -> Image.Image:
-        return self._to_pil(ops.median3(self._to_device(image)))
+        if image.mode in ("RGB", "L"):
+            return self._to_pil(ops.median3(self._to_device(image)))
+        if image.mode == "P":
+            raise ValueError("cannot filter palette images")                          # Pillow's own error
+        if image.mode == "1":             # RankFilter runs on the 0/255 bytes of a bilevel image
+            return self._to_pil(ops.median3(self._to_device(image.convert("L")))).convert("1", dither=Image.Dither.NONE)
+        self._check_banded(image, "ImageFilter.MedianFilter")
+        return self._planes_to_pil(ops.median3(self._planes_to_device(image)), image.mode)
 
     def convert_to_grayscale(self, image: Image.Image) -> Image.Image:
         if image.mode == "L":
             return image.copy()
-        return self._to_pil(ops.gray_pil(self._to_device(image)))
+        return self._to_pil(ops.gray_pil(self._gray_source(image)))
 
     def auto_orient(self, image: Image.Image) -> Image.Image:
         orientation = image.getexif().get(0x0112)
         if orientation not in (2, 3, 4, 5, 6, 7, 8):
             return image.copy()
-        return self._to_pil(ops.exif_transpose(self._to_device(image), int(orientation)))
+        if image.mode in ("RGB", "L"):
+            return self._to_pil(ops.exif_transpose(self._to_device(image), int(orientation)))
+        if image.mode in self._BANDED:
+            return self._planes_to_pil(ops.exif_transpose(self._planes_to_device(image), int(orientation)), image.mode)
+        raise ValueError(f"unsupported image mode {image.mode!r}: load_image() converts to RGB/L first")
 
     def binarize(self, image: Image.Image, threshold: int = 128) -> Image.Image:
-        mask = ops.binarize(self._to_device(image), threshold)
+        mask = ops.binarize(self._gray_source(image), threshold)
         return Image.fromarray(mask[0].cpu().numpy()).convert("1", dither=Image.Dither.NONE)
 
     # ------------------------------------------------------------------ composed pipelines
@@ -209,6 +297,17 @@ class ImagePreprocessor:
                          apply_denoise: bool = False, grayscale: bool = False) -> Image.Image:
         """auto_orient -> resize -> [gray] -> [median] -> contrast 1.2 -> sharpness 1.1, one H2D/D2H."""
         img = self.auto_orient(self._open(image))
+        if img.mode not in ("RGB", "L"):   # any other PIL object: the same steps, one drop-in method at a time
+            img = self.resize_if_needed(img)
+            if grayscale:
+                img = self.convert_to_grayscale(img)
+            if apply_denoise:
+                img = self.denoise(img)
+            if apply_contrast:
+                img = self.enhance_contrast(img, factor=1.2)
+            if apply_sharpness:
+                img = self.enhance_sharpness(img, factor=1.1)
+            return img
         x = self._to_device(img)
         x = ops.resize_if_needed(x, self.max_dimension)
         if grayscale and x.shape[-1] == 3:
@@ -310,7 +409,7 @@ class ImagePreprocessor:
         return self._to_pil(out), angle
 
     def adaptive_binarize(self, image: Image.Image) -> Image.Image:
-        return self._to_pil(ops.adaptive_binarize(self._to_device(image), 2))
+        return self._to_pil(ops.adaptive_binarize(self._gray_source(image), 2))
 
     def compress_pages_for_azure(self, pages: torch.Tensor, target_size_mb: float = 2.0, initial_quality: int = 95,
                                  min_quality: int = 30) -> List[bytes]:
@@ -357,9 +456,9 @@ class ImagePreprocessor:
         return out  # type: ignore[return-value]
 
     def _jpeg_encoder(self) -> "ops.JpegEncoder":
-        enc = getattr(self, "_jpeg", None)
+        enc = getattr(self._tls, "jpeg", None)     # workspace + cached DCT: one per calling thread
         if enc is None:
-            enc = self._jpeg = ops.JpegEncoder()
+            enc = self._tls.jpeg = ops.JpegEncoder()
         return enc
 
     def compress_for_azure(self, image: Image.Image, target_size_mb: float = 2.0, initial_quality: int = 95,
@@ -395,6 +494,18 @@ class ImagePreprocessor:
                              target_size_mb: float = 2.0) -> bytes:
         img = self.auto_orient(self._open(image))
         logger.info(f"Preprocessing image: {img.size}, mode={img.mode}")
+        if img.mode not in ("RGB", "L"):   # any other PIL object: the reference's steps, one drop-in method at a time
+            img = self.resize_if_needed(img)
+            if apply_deskew:
+                img, _ = self.deskew(img)
+            if apply_binarize:
+                img = self.adaptive_binarize(img)
+            else:
+                if apply_contrast:
+                    img = self.enhance_contrast(img, factor=1.2)
+                if apply_sharpness:
+                    img = self.enhance_sharpness(img, factor=1.1)
+            return self.compress_for_azure(img, target_size_mb=target_size_mb)
         x, _ = self.preprocess_device(self._to_device(img), apply_deskew, apply_binarize, apply_contrast,
                                       apply_sharpness)
         return self.compress_pages_for_azure(x, target_size_mb=target_size_mb)[0]
@@ -417,8 +528,11 @@ class ImagePreprocessor:
         for i, im in enumerate(imgs):
             groups.setdefault((im.size, im.mode), []).append(i)
         for ((w, h), mode), idx in groups.items():
-            if mode not in ("RGB", "L"):
-                raise ValueError(f"unsupported image mode {mode!r}: load_image() converts to RGB/L first")
+            if mode not in ("RGB", "L"):   # rare: such objects take the per-image path
+                for i in idx:
+                    out[i] = self.preprocess_for_azure(imgs[i], apply_deskew, apply_binarize, apply_contrast,
+                                                       apply_sharpness, target_size_mb)
+                continue
             x = self._upload([imgs[i] for i in idx])
             x, _ = self.preprocess_device(x, apply_deskew, apply_binarize, apply_contrast, apply_sharpness)
             for i, b in zip(idx, self.compress_pages_for_azure(x, target_size_mb=target_size_mb)):
@@ -427,9 +541,9 @@ class ImagePreprocessor:
 
     def _host_stage(self, n: int, h: int, w: int, c: int) -> torch.Tensor:
         """Persistent pinned staging buffer for page uploads (grown on demand, reused across calls)."""
-        st = getattr(self, "_stage", None)
+        st = getattr(self._tls, "stage", None)     # one per calling thread (see __init__)
         if st is None or st.shape[1:] != (h, w, c) or st.shape[0] < n:
-            st = self._stage = torch.empty((n, h, w, c), dtype=torch.uint8, pin_memory=True)
+            st = self._tls.stage = torch.empty((n, h, w, c), dtype=torch.uint8, pin_memory=True)
         return st
 
 

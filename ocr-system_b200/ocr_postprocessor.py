@@ -77,7 +77,7 @@ def parse_rapidocr_output(result) -> List[TextBlock]:
     return blocks
 
 
-def _device_order(pages: Sequence[Sequence[TextBlock]], y_tolerance_ratio: float):
+def _device_order(pages: Sequence[Sequence[TextBlock]], y_tolerance_ratio: float, one_line: bool = False):
     """One launch for a batch of pages -> per page (order, line_of, nlines, line_conf, line_y) on the host."""
     counts = [len(p) for p in pages]
     offsets = np.zeros(len(pages) + 1, np.int32)
@@ -94,7 +94,8 @@ def _device_order(pages: Sequence[Sequence[TextBlock]], y_tolerance_ratio: float
     conf = np.array([b.confidence for p in pages for b in p], dtype=np.float64)
     dev = torch.device("cuda", torch.cuda.current_device())
     order, line_of, nlines, line_conf, line_y = ops.reading_order(
-        torch.from_numpy(boxes).to(dev), torch.from_numpy(conf).to(dev), torch.from_numpy(offsets), y_tolerance_ratio)
+        torch.from_numpy(boxes).to(dev), torch.from_numpy(conf).to(dev), torch.from_numpy(offsets), y_tolerance_ratio,
+        one_line=one_line)
     order, line_of, nlines = order.cpu().numpy(), line_of.cpu().numpy(), nlines.cpu().numpy()
     line_conf, line_y = line_conf.cpu().numpy(), line_y.cpu().numpy()
     out = []
@@ -133,13 +134,13 @@ def _merge(blocks, order, line_of, nl, line_conf, line_y) -> List[MergedLine]:
 def sort_and_merge_lines(lines: List[List[TextBlock]], space_threshold_ratio: float = 2.0) -> List[MergedLine]:
     """ocr_postprocessor.py:146-182 for lines that are already grouped: every given line is sorted by x_left
     (stable), merged with single spaces, and the merged lines are sorted by mean y (stable).  Each line is
-    sent to the device as its own one-line page (``y_tolerance_ratio < 0`` selects that mode)."""
+    sent to the device as its own one-line page (``one_line=True``)."""
     lines = [ln for ln in lines]
     if any(len(ln) == 0 for ln in lines):
         raise ZeroDivisionError("division by zero")  # the reference divides by len(sorted_line)
     if not lines:
         return []
-    res = _device_order(lines, -1.0)
+    res = _device_order(lines, 0.0, one_line=True)
     merged = []
     for ln, (order, line_of, nl, line_conf, line_y) in zip(lines, res):
         merged.extend(_merge(ln, order, line_of, nl, line_conf, line_y))

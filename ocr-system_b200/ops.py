@@ -9,6 +9,7 @@ non-CUDA tensor is an error.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import threading
 from typing import Optional, Tuple
 
@@ -26,7 +27,27 @@ def _ptr(t) -> C.c_void_p:
 
 
 def _stream() -> C.c_void_p:
+    """The current torch stream of the CURRENT device.  Every launching function below is wrapped in
+    ``_on_tensor_device``, which makes the tensor's device current first -- so this is always the stream of the
+    device the pointers live on (the library's per-device tables key off cudaGetDevice the same way)."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_tensor_device(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current.  A cuda:1 tensor handed to a thread
+    whose current device is cuda:0 therefore launches on cuda:1's context and stream, not on cuda:0's."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+
+    return wrapper
 
 
 def _pages(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int]:
@@ -39,6 +60,8 @@ def _pages(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int, int]:
     if x.dim() != 4 or x.shape[-1] not in (1, 3):
         raise ValueError(f"expected [N,H,W,C] with C in (1,3) or [N,H,W]; got {tuple(x.shape)}")
     x = x.contiguous()
+    if x.data_ptr() & 15:      # a slice such as pages[1:] of odd-sized pages: the 128-bit kernels need 16-byte bases
+        x = x.clone()
     n, h, w, c = x.shape
     return x, n, h, w, c
 
@@ -52,6 +75,7 @@ def launch_count() -> int:
 
 
 # --------------------------------------------------------------------------- a2
+@_on_tensor_device
 def exif_transpose(pages: torch.Tensor, orientation: int) -> torch.Tensor:
     """PIL ImageOps.exif_transpose (image_preprocessing.py:173) for a fixed EXIF orientation."""
     sq = pages.dim() == 3
@@ -91,6 +115,7 @@ class _ResizePlans:
 _plans = _ResizePlans()
 
 
+@_on_tensor_device
 def resize_lanczos(pages: torch.Tensor, out_w: int, out_h: int) -> torch.Tensor:
     """PIL Image.resize((out_w,out_h), LANCZOS) (image_preprocessing.py:110), byte-exact."""
     sq = pages.dim() == 3
@@ -103,6 +128,22 @@ def resize_lanczos(pages: torch.Tensor, out_w: int, out_h: int) -> torch.Tensor:
     return _like(out, sq)
 
 
+@_on_tensor_device
+def resize_nearest(planes: torch.Tensor, out_w: int, out_h: int) -> torch.Tensor:
+    """Pillow's resize of mode "P" / "1" images (always NEAREST): planes [N,H,W] of single-byte pixels."""
+    x, n, h, w, c = _pages(planes)
+    if c != 1:
+        raise ValueError("resize_nearest works on single-byte planes [N,H,W]")
+    xt = np.empty(out_w, np.int32)
+    yt = np.empty(out_h, np.int32)
+    _L().lumina_nearest_table_host(w, out_w, xt.ctypes.data_as(C.c_void_p))
+    _L().lumina_nearest_table_host(h, out_h, yt.ctypes.data_as(C.c_void_p))
+    dxt, dyt = torch.from_numpy(xt).to(x.device), torch.from_numpy(yt).to(x.device)
+    out = torch.empty((n, out_h, out_w), dtype=torch.uint8, device=x.device)
+    _chk(_L().lumina_resize_nearest_u8(_ptr(x), _ptr(out), n, h, w, out_h, out_w, _ptr(dxt), _ptr(dyt), _stream()))
+    return out
+
+
 def resize_if_needed(pages: torch.Tensor, max_dim: int) -> torch.Tensor:
     h, w = pages.shape[1], pages.shape[2]
     if max(w, h) <= max_dim:
@@ -112,6 +153,7 @@ def resize_if_needed(pages: torch.Tensor, max_dim: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- a4
+@_on_tensor_device
 def gray_pil(pages: torch.Tensor) -> torch.Tensor:
     x, n, h, w, c = _pages(pages)
     if c == 1:
@@ -121,6 +163,7 @@ def gray_pil(pages: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def gray_cv(pages: torch.Tensor) -> torch.Tensor:
     x, n, h, w, c = _pages(pages)
     if c == 1:
@@ -131,6 +174,7 @@ def gray_cv(pages: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- a5 / a6
+@_on_tensor_device
 def contrast_mean(pages: torch.Tensor) -> torch.Tensor:
     x, n, h, w, c = _pages(pages)
     scratch = torch.empty(n, dtype=torch.int64, device=x.device)
@@ -139,6 +183,7 @@ def contrast_mean(pages: torch.Tensor) -> torch.Tensor:
     return mean
 
 
+@_on_tensor_device
 def enhance_contrast(pages: torch.Tensor, factor: float, mean: Optional[torch.Tensor] = None) -> torch.Tensor:
     sq = pages.dim() == 3
     x, n, h, w, c = _pages(pages)
@@ -149,6 +194,7 @@ def enhance_contrast(pages: torch.Tensor, factor: float, mean: Optional[torch.Te
     return _like(out, sq)
 
 
+@_on_tensor_device
 def enhance_sharpness(pages: torch.Tensor, factor: float) -> torch.Tensor:
     sq = pages.dim() == 3
     x, n, h, w, c = _pages(pages)
@@ -157,6 +203,7 @@ def enhance_sharpness(pages: torch.Tensor, factor: float) -> torch.Tensor:
     return _like(out, sq)
 
 
+@_on_tensor_device
 def contrast_sharpness(pages: torch.Tensor, contrast: float, sharpness: float) -> torch.Tensor:
     """enhance_sharpness(enhance_contrast(x, contrast), sharpness) with the contrast LUT fused
     into the stencil (image_preprocessing.py:613-618)."""
@@ -170,6 +217,7 @@ def contrast_sharpness(pages: torch.Tensor, contrast: float, sharpness: float) -
 
 
 # --------------------------------------------------------------------------- a7 / a8 / a9
+@_on_tensor_device
 def median3(pages: torch.Tensor) -> torch.Tensor:
     sq = pages.dim() == 3
     x, n, h, w, c = _pages(pages)
@@ -178,6 +226,7 @@ def median3(pages: torch.Tensor) -> torch.Tensor:
     return _like(out, sq)
 
 
+@_on_tensor_device
 def binarize(pages: torch.Tensor, threshold: int = 128) -> torch.Tensor:
     x, n, h, w, c = _pages(pages)
     out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
@@ -185,6 +234,7 @@ def binarize(pages: torch.Tensor, threshold: int = 128) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def adaptive_binarize(pages: torch.Tensor, cval: int = 2) -> torch.Tensor:
     x, n, h, w, c = _pages(pages)
     out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
@@ -198,6 +248,7 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+@_on_tensor_device
 def canny(pages: torch.Tensor, low: int = 50, high: int = 150) -> torch.Tensor:
     """cv gray (for RGB) + cv2.Canny(low, high, apertureSize=3) -> edges [N,H,W] {0,255}."""
     x, n, h, w, c = _pages(pages)
@@ -208,6 +259,7 @@ def canny(pages: torch.Tensor, low: int = 50, high: int = 150) -> torch.Tensor:
     return edges
 
 
+@_on_tensor_device
 def hough_lines_p(edges: torch.Tensor, rho: float = 1.0, theta: float = float(np.pi / 180), threshold: int = 100,
                   min_line_length: int = 100, max_line_gap: int = 10, max_lines: int = 4096):
     """cv2.HoughLinesP on a batch of edge planes -> (lines [N,max_lines,4] int32, nlines [N] int32), device."""
@@ -241,20 +293,23 @@ class HoughJob:
         self.ws = _ws(self.wsb, x.device)
 
     def prepare(self):
-        _chk(_L().lumina_ppht_prepare(_ptr(self.x), self.n, self.h, self.w, *self.args, _ptr(self.ws), self.wsb, _stream()))
+        with torch.cuda.device(self.x.device):
+            _chk(_L().lumina_ppht_prepare(_ptr(self.x), self.n, self.h, self.w, *self.args, _ptr(self.ws), self.wsb, _stream()))
         return self
 
     def lines(self):
         lines = torch.empty((self.n, self.max_lines, 4), dtype=torch.int32, device=self.x.device)
         nlines = torch.empty(self.n, dtype=torch.int32, device=self.x.device)
-        _chk(_L().lumina_ppht_lines(_ptr(self.x), self.n, self.h, self.w, *self.args, *self.params, _ptr(lines), _ptr(nlines),
-                                    self.max_lines, _ptr(self.ws), self.wsb, _stream()))
+        with torch.cuda.device(self.x.device):
+            _chk(_L().lumina_ppht_lines(_ptr(self.x), self.n, self.h, self.w, *self.args, *self.params, _ptr(lines), _ptr(nlines),
+                                        self.max_lines, _ptr(self.ws), self.wsb, _stream()))
         cur = torch.cuda.current_stream(self.x.device)
         self.ws.record_stream(cur)
         self.x.record_stream(cur)
         return lines, nlines
 
 
+@_on_tensor_device
 def rgbx_to_rgb(pages_rgbx: torch.Tensor) -> torch.Tensor:
     """[N,H,W,4] uint8 (Pillow's in-memory R,G,B,pad) -> [N,H,W,3]."""
     if not pages_rgbx.is_cuda or pages_rgbx.dtype != torch.uint8 or pages_rgbx.dim() != 4 or pages_rgbx.shape[-1] != 4:
@@ -293,6 +348,7 @@ def deskew_decide(lines_host: np.ndarray, nlines_host: np.ndarray, h: int, w: in
     return angles, mats, apply
 
 
+@_on_tensor_device
 def warp_affine_cubic(pages: torch.Tensor, mats: np.ndarray, apply: Optional[np.ndarray] = None) -> torch.Tensor:
     """cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE) with per-page forward 2x3 matrices (host)."""
     sq = pages.dim() == 3
@@ -305,6 +361,7 @@ def warp_affine_cubic(pages: torch.Tensor, mats: np.ndarray, apply: Optional[np.
     return _like(out, sq)
 
 
+@_on_tensor_device
 def deskew(pages: torch.Tensor, max_lines: int = 4096):
     """image_preprocessing.py:372-460 for a batch: returns (pages, angles[N] float64 numpy).
 
@@ -336,6 +393,7 @@ def det_target_size(h: int, w: int, limit_side_len: int = 960) -> Tuple[int, int
     return oh.value, ow.value
 
 
+@_on_tensor_device
 def det_resize_normalize(pages: torch.Tensor, limit_side_len: int = 960, mean=DET_MEAN, std=DET_STD,
                          scale: float = 1.0 / 255.0):
     """PaddleOCR DetResizeForTest('max') + NormalizeImage + ToCHWImage -> ([N,3,oh,ow] f32, shape_list)."""
@@ -352,6 +410,7 @@ def det_resize_normalize(pages: torch.Tensor, limit_side_len: int = 960, mean=DE
     return out, shape_list
 
 
+@_on_tensor_device
 def ctc_greedy(probs: torch.Tensor):
     """CTC greedy decode of [N,T,C] float32 posteriors -> (idx, pos, length, conf) device tensors."""
     if not probs.is_cuda or probs.dtype != torch.float32 or probs.dim() != 3:
@@ -377,6 +436,7 @@ def synth_pages(n: int, h: int = 3508, w: int = 2480, seed0: int = 0, device="cu
 
 
 # --------------------------------------------------------------------------- a16
+@_on_tensor_device
 def db_mask_ccl(pred: torch.Tensor, thresh: float = 0.3):
     """Stage outputs of the DB labelling: (mask {0,1} [N,H,W] u8, labels [N,H,W] int32 with
     label = min raster index of the 8-connected component + 1, 0 = background)."""
@@ -393,6 +453,7 @@ def db_mask_ccl(pred: torch.Tensor, thresh: float = 0.3):
     return mask, labels
 
 
+@_on_tensor_device
 def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: float = 0.7,
                    unclip_ratio: float = 2.0, max_candidates: int = 1000, min_size: int = 3):
     """DBPostProcess core on [N,H,W] float32 maps -> (boxes [N,max_candidates,4,2] int32,
@@ -414,12 +475,14 @@ def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: 
 
 
 # --------------------------------------------------------------------------- next row 8f.2
+@_on_tensor_device
 def reading_order(boxes: torch.Tensor, conf: torch.Tensor, offsets: torch.Tensor, y_tolerance_ratio: float = 0.5,
-                  max_boxes_per_page: Optional[int] = None):
+                  max_boxes_per_page: Optional[int] = None, one_line: bool = False):
     """ocr_postprocessor.py:101-182 for a batch of pages.
 
     boxes  CUDA float64 [total,4,2], conf CUDA float64 [total], offsets int32 [pages+1] (CUDA or host).
-    y_tolerance_ratio < 0: every page is one pre-grouped line (input order breaks x ties).
+    one_line=True: every page is one pre-grouped line (input order breaks x ties).  A negative / NaN ratio keeps
+    the reference's meaning: no two blocks ever share a line.
     Returns device tensors (order[total] int32, line_of[total] int32, nlines[pages] int32,
     line_conf[total] f64, line_y[total] f64), all indexed from offsets[p]."""
     if not boxes.is_cuda or boxes.dtype != torch.float64 or boxes.dim() != 3 or tuple(boxes.shape[1:]) != (4, 2):
@@ -448,7 +511,7 @@ def reading_order(boxes: torch.Tensor, conf: torch.Tensor, offsets: torch.Tensor
         nlines.zero_()
         return order[:0], line_of[:0], nlines, line_conf[:0], line_y[:0]
     with torch.cuda.device(dev):
-        _chk(_L().lumina_reading_order(_ptr(b), _ptr(c), _ptr(off_dev), pages, mb, float(y_tolerance_ratio), _ptr(order),
+        _chk(_L().lumina_reading_order(_ptr(b), _ptr(c), _ptr(off_dev), pages, mb, float(y_tolerance_ratio), int(bool(one_line)), _ptr(order),
                                        _ptr(line_of), _ptr(nlines), _ptr(line_conf), _ptr(line_y), _stream()))
     n = int(b.shape[0])
     return order[:n], line_of[:n], nlines, line_conf[:n], line_y[:n]

@@ -116,7 +116,14 @@ class PagePipeline:
         self.deskew = deskew
         self.enhance = enhance
         self.det_limit = int(det_limit_side_len)
-        self.device = device
+        self.device = torch.device(device) if device is not None else None
+        # streams, double buffers and pinned staging are per (pipeline object, calling thread): the reference's
+        # singleton is called from asyncio.to_thread workers (ocr_service.py:674-676), so two threads may be inside
+        # the same PagePipeline at once and must never share a staging buffer
+        self._tls = threading.local()
+
+    def _dev(self) -> torch.device:
+        return self.device or torch.device("cuda", torch.cuda.current_device())
 
     # ------------------------------------------------------------------ resident input
     def run_device(self, pages: torch.Tensor, profile: bool = False) -> PageBatchResult:
@@ -153,21 +160,22 @@ class PagePipeline:
         batch i, so its kernels fill the SMs that batch i's last HoughLinesP clusters leave idle (49 pages fit at
         once; a 64-page batch alone runs 1.3 waves).  Yields one PageBatchResult per batch, in order; the
         results are safe to use on the caller's current stream."""
-        dev = self.device or torch.device("cuda", torch.cuda.current_device())
+        dev = self._dev()
         main = torch.cuda.current_stream(dev)
-        st = getattr(self, "_dev_streams", None)
+        st = getattr(self._tls, "dev_streams", None)
         if st is None or st[0].device != dev:
             # one high-priority stream for the wide kernels (resize, Canny, warp, gray, binarize, normalise) and two
             # low-priority streams that alternate for HoughLinesP: when a page's cluster retires, the freed SMs go to
             # the wide kernels of the next batch first, so its HoughLinesP is ready to follow without a gap
-            st = self._dev_streams = (torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev, priority=0),
-                                      torch.cuda.Stream(dev, priority=0))
+            st = self._tls.dev_streams = (torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev, priority=0),
+                                          torch.cuda.Stream(dev, priority=0))
         hi = st[0]
 
         def start(i, pages):
             lo = st[1 + (i & 1)]
             t = _StageTimer(profile)
             hi.wait_stream(main)
+            pages.record_stream(hi)               # the caller may drop the batch while hi still reads it
             with torch.cuda.stream(hi):
                 x = t.run("resize_lanczos", lambda: ops.resize_if_needed(pages, self.max_dimension))
                 job = None
@@ -203,19 +211,16 @@ class PagePipeline:
         while pending:
             yield finish(pending.pop(0))
 
-    _rotate_stage = None   # pinned staging for the line lists (shape-keyed)
-
-    @staticmethod
-    def _rotate(x: torch.Tensor, lines: torch.Tensor, nlines: torch.Tensor):
+    def _rotate(self, x: torch.Tensor, lines: torch.Tensor, nlines: torch.Tensor):
         """Host median / gating (image_preprocessing.py:414-439) + one warp launch.  The only
         host synchronisation of the chain: the line lists (a few KB per page) come back."""
         n, h, w = x.shape[0], x.shape[1], x.shape[2]
         # one pinned staging buffer, one synchronisation: counts and line lists come back together
-        key = (n, lines.shape[1], x.device, threading.get_ident())
-        st = PagePipeline._rotate_stage
+        key = (n, lines.shape[1], x.device)
+        st = getattr(self._tls, "rotate_stage", None)   # pinned staging for the line lists: per thread, shape-keyed
         if st is None or st[0] != key:
-            st = PagePipeline._rotate_stage = (key, torch.empty(n, dtype=torch.int32, pin_memory=True),
-                                               torch.empty((n, lines.shape[1], 4), dtype=torch.int32, pin_memory=True))
+            st = self._tls.rotate_stage = (key, torch.empty(n, dtype=torch.int32, pin_memory=True),
+                                           torch.empty((n, lines.shape[1], 4), dtype=torch.int32, pin_memory=True))
         _, nl_pin, ln_pin = st
         nl_pin.copy_(nlines, non_blocking=True)
         ln_pin.copy_(lines, non_blocking=True)
@@ -235,88 +240,100 @@ class PagePipeline:
         return x, angles
 
     # ------------------------------------------------------------------ host input (the e2e path)
+    @staticmethod
+    def _new_out(res: PageBatchResult) -> Dict[str, torch.Tensor]:
+        return {"pages": torch.empty(res.pages.shape, dtype=torch.uint8, pin_memory=True),
+                "binary": torch.empty(res.binary.shape, dtype=torch.uint8, pin_memory=True)}
+
     def run_host(self, pages_host: torch.Tensor, out_host: Optional[Dict[str, torch.Tensor]] = None,
                  profile: bool = False):
         """pages_host: (pinned) CPU uint8 [N,H,W,3].  Copies the rasters to the device, runs the
         chain and copies back what a caller consumes: deskewed rasters, binary masks and angles.
-        Returns (out_host dict, PageBatchResult, h2d_bytes, d2h_bytes)."""
+        Returns (out_host dict, PageBatchResult, h2d_bytes, d2h_bytes); ``out_host`` is freshly allocated
+        (owned by the caller) unless one is passed in."""
         if pages_host.is_cuda:
             raise TypeError("run_host needs a host tensor")
-        dev = self.device or torch.device("cuda", torch.cuda.current_device())
-        x = pages_host.to(dev, non_blocking=True)
-        res = self.run_device(x, profile=profile)
-        if out_host is None:
-            out_host = {
-                "pages": torch.empty(res.pages.shape, dtype=torch.uint8, pin_memory=True),
-                "binary": torch.empty(res.binary.shape, dtype=torch.uint8, pin_memory=True),
-            }
-        out_host["pages"].copy_(res.pages, non_blocking=True)
-        out_host["binary"].copy_(res.binary, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        dev = self._dev()
+        with torch.cuda.device(dev):
+            x = pages_host.to(dev, non_blocking=True)
+            res = self.run_device(x, profile=profile)
+            if out_host is None:
+                out_host = self._new_out(res)
+            out_host["pages"].copy_(res.pages, non_blocking=True)
+            out_host["binary"].copy_(res.binary, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
         out_host["angles"] = res.angles
         h2d = pages_host.numel()
         d2h = res.pages.numel() + res.binary.numel() + res.angles.nbytes
         return out_host, res, h2d, d2h
 
-    def run_host_stream(self, host_batches, profile: bool = False):
+    def run_host_stream(self, host_batches, profile: bool = False, keep: int = 2):
         """Streaming form of ``run_host`` for a sequence of (pinned) host batches: the H2D copy of
         batch i+1 is enqueued on a copy stream before batch i is processed, so raster upload overlaps
         the kernels of the previous batch (double-buffered device input).  Yields
-        ``(out_host, PageBatchResult, h2d_bytes, d2h_bytes)`` per batch, results complete in host memory."""
-        dev = self.device or torch.device("cuda", torch.cuda.current_device())
-        comp = torch.cuda.current_stream(dev)
-        st = getattr(self, "_stream_state", None)
-        if st is None or st["dev"] != dev:  # copy stream + double buffer live as long as the pipeline object
-            st = self._stream_state = {"dev": dev, "copy": torch.cuda.Stream(dev), "buf": [None, None], "free": [None, None],
-                                       "out": None}
-        copy_stream = st["copy"]
-        it = iter(host_batches)
-        dev_buf = st["buf"]         # persistent double buffer for the rasters (no allocator traffic per batch)
-        ready = [None, None]        # H2D of slot k finished (recorded on the copy stream)
-        free = st["free"]           # kernels that read slot k finished (recorded on the compute stream)
-        host_of = [None, None]
+        ``(out_host, PageBatchResult, h2d_bytes, d2h_bytes)`` per batch, results complete in host memory.
 
-        def issue(k, hb):
-            if hb.is_cuda:
-                raise TypeError("run_host_stream needs host tensors")
-            if dev_buf[k] is None or dev_buf[k].shape != hb.shape:
-                dev_buf[k] = torch.empty(hb.shape, dtype=torch.uint8, device=dev)
-                free[k] = None
-            with torch.cuda.stream(copy_stream):
-                if free[k] is not None:
-                    copy_stream.wait_event(free[k])
-                dev_buf[k].copy_(hb, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            ready[k] = ev
-            host_of[k] = hb
+        Lifetime of a yielded result: the pinned ``out_host`` buffers rotate over ``keep`` slots, so batch i's
+        host results stay intact until the generator has been advanced ``keep`` more times (``keep=2``: a consumer
+        may still hold batch i while it receives batch i+1).  The device tensors of ``PageBatchResult`` are fresh
+        allocations and follow the usual torch lifetime; the rasters never alias the reused upload slot.  Copy what
+        must live longer (or raise ``keep``)."""
+        dev = self._dev()
+        keep = max(1, int(keep))
+        with torch.cuda.device(dev):
+            comp = torch.cuda.current_stream(dev)
+            st = getattr(self._tls, "stream_state", None)
+            if st is None or st["dev"] != dev:  # copy stream + double buffer live as long as the (pipeline, thread) pair
+                st = self._tls.stream_state = {"dev": dev, "copy": torch.cuda.Stream(dev), "buf": [None, None],
+                                               "free": [None, None], "out": []}
+            copy_stream = st["copy"]
+            it = iter(host_batches)
+            dev_buf = st["buf"]         # persistent double buffer for the rasters (no allocator traffic per batch)
+            ready = [None, None]        # H2D of slot k finished (recorded on the copy stream)
+            free = st["free"]           # kernels that read slot k finished (recorded on the compute stream)
+            host_of = [None, None]
 
-        cur_hb = next(it, None)
-        if cur_hb is None:
-            return
-        issue(0, cur_hb)
-        i = 0
-        out_host = st["out"]  # pinned result buffers are kept too: cudaHostAlloc costs ~100 ms per call otherwise
-        while cur_hb is not None:
-            k = i & 1
-            nxt = next(it, None)
-            if nxt is not None:
-                issue(k ^ 1, nxt)  # upload of the next batch overlaps this batch's kernels
-            comp.wait_event(ready[k])
-            res = self.run_device(dev_buf[k], profile=profile)
-            fe = torch.cuda.Event()
-            fe.record(comp)
-            free[k] = fe
-            if out_host is None or out_host["pages"].shape != res.pages.shape:
-                out_host = st["out"] = {
-                    "pages": torch.empty(res.pages.shape, dtype=torch.uint8, pin_memory=True),
-                    "binary": torch.empty(res.binary.shape, dtype=torch.uint8, pin_memory=True),
-                }
-            out_host["pages"].copy_(res.pages, non_blocking=True)
-            out_host["binary"].copy_(res.binary, non_blocking=True)
-            comp.synchronize()
-            out_host["angles"] = res.angles
-            hb = host_of[k]
-            yield out_host, res, hb.numel(), res.pages.numel() + res.binary.numel() + res.angles.nbytes
-            cur_hb = nxt
-            i += 1
+            def issue(k, hb):
+                if hb.is_cuda:
+                    raise TypeError("run_host_stream needs host tensors")
+                if dev_buf[k] is None or dev_buf[k].shape != hb.shape:
+                    dev_buf[k] = torch.empty(hb.shape, dtype=torch.uint8, device=dev)
+                    free[k] = None
+                with torch.cuda.stream(copy_stream):
+                    if free[k] is not None:
+                        copy_stream.wait_event(free[k])
+                    dev_buf[k].copy_(hb, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                ready[k] = ev
+                host_of[k] = hb
+
+            cur_hb = next(it, None)
+            if cur_hb is None:
+                return
+            issue(0, cur_hb)
+            i = 0
+            outs = st["out"]  # pinned result slots are kept too: cudaHostAlloc costs ~100 ms per call otherwise
+            while cur_hb is not None:
+                k = i & 1
+                nxt = next(it, None)
+                if nxt is not None:
+                    issue(k ^ 1, nxt)  # upload of the next batch overlaps this batch's kernels
+                comp.wait_event(ready[k])
+                res = self.run_device(dev_buf[k], profile=profile)
+                if res.pages.data_ptr() == dev_buf[k].data_ptr():
+                    res.pages = res.pages.clone()   # nothing resized or rotated: do not hand out the reused upload slot
+                fe = torch.cuda.Event()
+                fe.record(comp)
+                free[k] = fe
+                if len(outs) != keep or outs[0]["pages"].shape != res.pages.shape or outs[0]["binary"].shape != res.binary.shape:
+                    outs[:] = [self._new_out(res) for _ in range(keep)]
+                out_host = outs[i % keep]
+                out_host["pages"].copy_(res.pages, non_blocking=True)
+                out_host["binary"].copy_(res.binary, non_blocking=True)
+                comp.synchronize()
+                out_host["angles"] = res.angles
+                hb = host_of[k]
+                yield out_host, res, hb.numel(), res.pages.numel() + res.binary.numel() + res.angles.nbytes
+                cur_hb = nxt
+                i += 1

@@ -55,6 +55,25 @@ def _hwc(img):
     return img, img.shape[0], img.shape[1], img.shape[2]
 
 
+def resize_nearest(plane, out_w: int, out_h: int):
+    """Pillow's Image.resize on mode "P" / "1" objects (image_preprocessing.py:110 reaches it for those modes):
+    the filter is forced to NEAREST; Geometry.c ImagingScaleAffine maps output x to (int)(a/2 + x*a) with the
+    products accumulated by repeated addition in double.  Pure-Python table, numpy gather."""
+    plane = _u8(plane)
+
+    def tab(n_in, n_out):
+        a = n_in / n_out
+        xo = 0.0 + a * 0.5
+        t = np.empty(n_out, np.int64)
+        for x in range(n_out):
+            t[x] = -1 if xo < 0.0 else int(xo)
+            xo += a
+        return t
+
+    xi, yi = tab(plane.shape[1], out_w), tab(plane.shape[0], out_h)
+    return plane[yi][:, xi]
+
+
 # --- A1 ---------------------------------------------------------------------
 def target_size(width: int, height: int, max_dim: int):
     """image_preprocessing.py:97-105 (int() truncation)."""

@@ -1,0 +1,104 @@
+"""CPU pins for the parts of the oracle that the reference itself cannot pin.
+
+a15 det resize+normalize and a17 CTC greedy decode are upstream PaddleOCR ops that the reference neither vendors
+nor calls: "parity unpinned" by the reference.  What CAN be pinned without it is pinned here:
+the C restatement against the libraries upstream builds on (cv2.resize + NumPy; NumPy argmax/max/mean), and the
+drop-in goldens produced by the unmodified reference against the oracle's composition of its own stages.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from dropin_images import MAX_DIM, image_in_mode  # noqa: E402
+
+GOLD = json.load(open(os.path.join(HERE, "golden", "dropin_golden.json")))
+
+
+@pytest.mark.parametrize("h,w", [(960, 678), (2000, 1413), (501, 333), (64, 1999), (31, 17)])
+def test_det_resize_normalize_equals_cv2_resize_plus_numpy(oracle, h, w):
+    """upstream DetResizeForTest('max', 960) + NormalizeImage + ToCHWImage, exact."""
+    import cv2
+
+    rng = np.random.default_rng(h * 7 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got, shape = oracle.det_resize_normalize(img, 960)
+    ratio = 960.0 / max(h, w) if max(h, w) > 960 else 1.0
+    rh, rw = int(h * ratio), int(w * ratio)
+    rh, rw = max(int(round(rh / 32) * 32), 32), max(int(round(rw / 32) * 32), 32)
+    r = cv2.resize(img, (rw, rh))
+    mean = np.array([0.485, 0.456, 0.406], np.float32).reshape(1, 1, 3)
+    std = np.array([0.229, 0.224, 0.225], np.float32).reshape(1, 1, 3)
+    want = ((r.astype("float32") * np.float32(1.0 / 255.0) - mean) / std).transpose(2, 0, 1)
+    assert got.shape == want.shape == (3, rh, rw)
+    assert np.array_equal(got, want)                      # bit-equal float32
+    assert tuple(shape) == (h, w, rh / h, rw / w)
+
+
+def test_ctc_greedy_equals_numpy(oracle):
+    """upstream CTCLabelDecode: argmax (first max wins), max, drop repeats / blank, mean."""
+    rng = np.random.default_rng(0)
+    n, t, c = 37, 40, 211
+    logits = rng.normal(size=(n, t, c)).astype(np.float32) * 3
+    # planted repeats, blanks and exact ties
+    logits[:, 5] = logits[:, 4]
+    logits[:, 9, 0] = 50
+    logits[:, 10, 0] = 50
+    p = np.exp(logits - logits.max(-1, keepdims=True))
+    p = (p / p.sum(-1, keepdims=True)).astype(np.float32)
+    p[:, 20, 7] = p[:, 20, 3] = p[:, 20].max(-1) + np.float32(0.25)      # tie: index 3 wins
+    idx, pos, ln, conf = oracle.ctc_greedy(p)
+    am, mx = p.argmax(2), p.max(2)
+    for b in range(n):
+        keep = [k for k in range(t) if am[b, k] != 0 and (k == 0 or am[b, k] != am[b, k - 1])]
+        assert ln[b] == len(keep)
+        assert idx[b, :ln[b]].tolist() == am[b, keep].tolist()
+        assert pos[b, :ln[b]].tolist() == keep
+        want = float(np.mean(mx[b, keep])) if keep else 0.0
+        assert abs(float(conf[b]) - want) <= 1e-6
+
+
+def test_resize_nearest_equals_pillow_and_reference_golden(oracle):
+    from PIL import Image
+
+    rng = np.random.default_rng(2)
+    for (h, w, oh, ow) in [(877, 620, 600, 424), (3508, 2480, 960, 678), (100, 333, 47, 200), (17, 13, 5, 4)]:
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        im = Image.frombytes("P", (w, h), a.tobytes())
+        want = np.frombuffer(im.resize((ow, oh), Image.Resampling.LANCZOS).tobytes(), np.uint8).reshape(oh, ow)
+        assert np.array_equal(oracle.resize_nearest(a, ow, oh), want)
+    # the reference's own resize_if_needed on a mode-P page (golden from the unmodified module)
+    import hashlib
+
+    case = [c for c in GOLD["cases"] if c["kind"] == "mode" and c["mode"] == "P" and c["method"] == "resize_if_needed"][0]
+    p = image_in_mode(oracle, "P", 0)
+    idx = np.frombuffer(p.tobytes(), np.uint8).reshape(p.size[1], p.size[0])
+    tw, th = oracle.target_size(p.size[0], p.size[1], MAX_DIM)
+    assert [tw, th] == case["want"]["size"]
+    assert hashlib.sha256(oracle.resize_nearest(idx, tw, th).tobytes()).hexdigest() == case["want"]["sha"]
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["kind"] == "optimize_for_ocr"],
+                         ids=lambda c: f"{c['mode']}-{c['seed']}-{'+'.join(c['kwargs'])}")
+def test_oracle_composition_reproduces_reference_optimize_for_ocr_flags(oracle, case):
+    """reference optimize_for_ocr :191-242 with every flag, restated as a composition of oracle stages."""
+    import hashlib
+
+    kw = dict(apply_contrast=True, apply_sharpness=True, apply_denoise=False, grayscale=False)
+    kw.update(case["kwargs"])
+    img = np.asarray(image_in_mode(oracle, case["mode"], case["seed"]))
+    tw, th = oracle.target_size(img.shape[1], img.shape[0], MAX_DIM)
+    x = oracle.resize_lanczos(img, tw, th)
+    if kw["grayscale"] and x.ndim == 3:
+        x = oracle.gray_pil(x)
+    if kw["apply_denoise"]:
+        x = oracle.median3(x)
+    if kw["apply_contrast"]:
+        x = oracle.contrast(x, 1.2)
+    if kw["apply_sharpness"]:
+        x = oracle.sharpness(x, 1.1)
+    assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == case["want"]["sha"]
