@@ -206,6 +206,11 @@ int lumina_jpeg_encode_rgb(const uint8_t *d_rgb, int n, int h, int w, int qualit
 /* A4-like text page, seeded by page index; identical bytes to the host
  * generator in include/lumina_synth.h compiled for the CPU. */
 int lumina_synth_pages_u8(uint8_t *d_dst, int n, int h, int w, uint64_t seed0, void *stream);
+/* DB probability maps [n][h][w] f32 (map m seeded by seed0 + m: ~one text box per 60x30 cell, soft borders,
+ * holes) and CTC posteriors [n][t][c] f32 (crop i seeded by crop0 + i: winner 0.9 per step, planted blanks,
+ * repeats and exact ties) -- BASELINE.json configs[2..4]; same floats as the host build of lumina_synth.h. */
+int lumina_synth_prob_maps_f32(float *d_dst, int n, int h, int w, uint64_t seed0, void *stream);
+int lumina_synth_ctc_f32(float *d_dst, int n, int t, int c, uint64_t crop0, uint32_t seed, void *stream);
 
 #ifdef __cplusplus
 }

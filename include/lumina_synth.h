@@ -104,4 +104,52 @@ LSYN_HD uint8_t lsyn_pixel(const lsyn_page_t *p, int32_t x, int32_t y, int ch) {
     val += (ns * 7) >> 8; /* sigma ~ 4 */
     return (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
 }
+
+/* ---- synthetic DB probability map ---------------------------------------------------
+ * One text box per 60x30 cell (960x960 -> 512 cells, ~496 boxes): width 18-52, height 10-16, half of them
+ * sheared by up to ~7 degrees, filled U(0.75,0.99) with a softened 1-px border (x0.55, still above thresh 0.3),
+ * one in eight of the larger ones with an interior hole (a hole contour for findContours); background
+ * U(0,0.12).  Integer decisions, one float multiply per pixel: identical floats on host and device. */
+LSYN_HD float lsyn_prob(int w, uint32_t seed, int x, int y) {
+    const uint32_t px = lsyn_hash3(seed ^ 0x1234567u, (uint32_t)(y * w + x), 0u);
+    const float bg = (float)(px & 0xffffu) * (0.12f / 65536.0f);
+    const int ci = x / 60, cj = y / 30;
+    const uint32_t hc = lsyn_hash3(seed, 0x5000u + (uint32_t)cj, (uint32_t)ci);
+    if ((hc & 31u) == 0u) return bg;                               /* empty cell */
+    const int bw = 18 + (int)((hc >> 5) % 35u), bh = 10 + (int)((hc >> 11) % 7u);
+    const int cx = ci * 60 + 30 + (int)((hc >> 14) % 5u) - 2, cy = cj * 30 + 15 + (int)((hc >> 17) % 5u) - 2;
+    const int t = ((hc >> 31) & 1u) ? (int)((hc >> 20) % 33u) - 16 : 0;   /* shear, Q7 */
+    const int dx = x - cx, dy = y - cy;
+    int u = dx * 128 + dy * t, v = dy * 128 - dx * t;
+    if (u < 0) u = -u;
+    if (v < 0) v = -v;
+    if (u > bw * 64 || v > bh * 64) return bg;
+    if (((hc >> 27) & 7u) == 0u && bw >= 24 && bh >= 12) {         /* interior hole */
+        const int hx = 1 + (int)((hc >> 30) & 1u);
+        if (dx >= -hx && dx <= hx && dy >= -1 && dy <= 1) return bg * 0.75f;
+    }
+    float val = 0.75f + (float)(px >> 16) * (0.24f / 65536.0f);
+    if (u > bw * 64 - 128 || v > bh * 64 - 128) val = val * 0.55f;
+    return val;
+}
+
+/* ---- synthetic CTC posteriors --------------------------------------------------------
+ * [n][T][C] float32: per step a peaked distribution (winner 0.9, the rest U(0, 2^-15)), class 0 = blank one
+ * step in five, one step in four repeats the previous step's class, one in sixteen plants an exact tie with a
+ * second class (numpy's first-index rule decides). */
+LSYN_HD uint32_t lsyn_ctc_base(uint32_t seed, int C, uint32_t n, int t) {
+    const uint32_t hb = lsyn_hash3(seed, n, (uint32_t)t);
+    return (hb % 5u == 0u) ? 0u : 1u + (hb >> 3) % (uint32_t)(C - 1);
+}
+LSYN_HD void lsyn_ctc_step(uint32_t seed, int C, uint32_t n, int t, uint32_t *win, uint32_t *tie) {
+    const uint32_t hb = lsyn_hash3(seed, n, (uint32_t)t);
+    uint32_t wn = (t > 0 && ((hb >> 24) & 3u) == 0u) ? lsyn_ctc_base(seed, C, n, t - 1) : lsyn_ctc_base(seed, C, n, t);
+    *win = wn;
+    *tie = (((hb >> 26) & 15u) == 0u) ? (wn + 1u + (hb >> 8) % 97u) % (uint32_t)C : wn;
+}
+LSYN_HD float lsyn_ctc_value(uint32_t seed, int T, uint32_t n, int t, uint32_t c, uint32_t win, uint32_t tie) {
+    if (c == win || c == tie) return 0.9f;
+    const uint32_t hv = lsyn_hash3(seed ^ 0x9e3779b9u, n * (uint32_t)T + (uint32_t)t, c);
+    return (float)(hv & 0xffffu) * (1.0f / 2147483648.0f);
+}
 #endif

@@ -67,6 +67,8 @@ PROTOTYPES = {
     "lumina_jpeg_workspace_bytes": (_Z, [_I, _I, _I]),
     "lumina_jpeg_encode_rgb": (_I, [_P, _I, _I, _I, _I, _I, _P, _Z, _P, _P, _Z, _P]),
     "lumina_synth_pages_u8": (_I, [_P, _I, _I, _I, C.c_uint64, _P]),
+    "lumina_synth_prob_maps_f32": (_I, [_P, _I, _I, _I, C.c_uint64, _P]),
+    "lumina_synth_ctc_f32": (_I, [_P, _I, _I, _I, C.c_uint64, C.c_uint32, _P]),
 }
 
 _lib = None

@@ -222,7 +222,7 @@ class ImagePreprocessor:
             return self._to_pil(ops.resize_lanczos(self._to_device(image), new_w, new_h))
         if image.mode in ("P", "1"):      # Pillow's Image.resize forces NEAREST for these two modes
             idx = image if image.mode == "P" else image.convert("L")        # palette indices / 0-255 bytes
-            plane = torch.from_numpy(np.frombuffer(idx.tobytes(), np.uint8).reshape(1, height, width)).to(self.device)
+            plane = torch.from_numpy(np.frombuffer(bytearray(idx.tobytes()), np.uint8).reshape(1, height, width)).to(self.device)
             raw = ops.resize_nearest(plane, new_w, new_h)[0].cpu().numpy().tobytes()
             if image.mode == "1":
                 return Image.frombytes("L", (new_w, new_h), raw).convert("1", dither=Image.Dither.NONE)
@@ -465,7 +465,7 @@ class ImagePreprocessor:
                            min_quality: int = 30) -> bytes:
         """Reference :496-557 for one PIL image; the JPEG encoding itself runs on the GPU
         and returns the bytes Pillow's encoder would."""
-        if image.mode in ("RGBA", "P", "L"):
+        if image.mode in ("RGBA", "P", "L", "RGBX"):   # RGBX: Pillow's JPEG writer reads it as RGB (pad dropped)
             image = image.convert("RGB")
         if image.mode != "RGB":
             raise OSError(f"cannot write mode {image.mode} as JPEG")   # Pillow's own error for unsupported modes

@@ -435,6 +435,25 @@ def synth_pages(n: int, h: int = 3508, w: int = 2480, seed0: int = 0, device="cu
     return out
 
 
+def synth_prob_maps(n: int, h: int = 960, w: int = 960, seed0: int = 0, device="cuda", out: Optional[torch.Tensor] = None):
+    """Synthetic DB probability maps [n,h,w] f32 generated in HBM (identical floats to oracle.synth_prob_map_grid)."""
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _chk(_L().lumina_synth_prob_maps_f32(_ptr(out), n, h, w, C.c_uint64(seed0), _stream()))
+    return out
+
+
+def synth_ctc(n: int, t: int = 40, c: int = 6625, crop0: int = 0, seed: int = 1, device="cuda",
+              out: Optional[torch.Tensor] = None):
+    """Synthetic CTC posteriors [n,t,c] f32 generated in HBM (identical floats to oracle.synth_ctc)."""
+    if out is None:
+        out = torch.empty((n, t, c), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _chk(_L().lumina_synth_ctc_f32(_ptr(out), n, t, c, C.c_uint64(crop0), C.c_uint32(seed), _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------- a16
 @_on_tensor_device
 def db_mask_ccl(pred: torch.Tensor, thresh: float = 0.3):

@@ -280,3 +280,17 @@ def synth_page(h: int, w: int, seed: int):
 def synth_skew_deg(h: int, w: int, seed: int) -> float:
     lib().orc_synth_skew_deg.restype = C.c_double
     return float(lib().orc_synth_skew_deg(h, w, C.c_uint64(seed)))
+
+
+def synth_prob_map_grid(h: int = 960, w: int = 960, seed: int = 0):
+    """Host build of the device generator ops.synth_prob_maps (one map, seed = seed0 + map index)."""
+    out = np.empty((h, w), np.float32)
+    lib().orc_synth_prob_map(_p(out), h, w, C.c_uint64(seed))
+    return out
+
+
+def synth_ctc(n: int, t: int = 40, c: int = 6625, crop0: int = 0, seed: int = 1):
+    """Host build of the device generator ops.synth_ctc."""
+    out = np.empty((n, t, c), np.float32)
+    lib().orc_synth_ctc(_p(out), n, t, c, C.c_uint64(crop0), C.c_uint32(seed))
+    return out

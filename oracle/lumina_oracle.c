@@ -760,3 +760,20 @@ ORC_API double orc_synth_skew_deg(int h, int w, uint64_t seed) {
     lsyn_page_init(&p, h, w, seed);
     return atan2((double)p.sinq, (double)p.cosq) * 180.0 / M_PI;
 }
+
+/* host builds of the synthetic DB probability map / CTC posterior generators (include/lumina_synth.h) */
+ORC_API void orc_synth_prob_map(float *dst, int h, int w, uint64_t seed64) {
+    const uint32_t seed = (uint32_t)(seed64 ^ (seed64 >> 32)) * 2654435761u + 777u;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) dst[(size_t)y * w + x] = lsyn_prob(w, seed, x, y);
+}
+ORC_API void orc_synth_ctc(float *dst, int n, int T, int C, uint64_t crop0, uint32_t seed) {
+    for (int i = 0; i < n; i++)
+        for (int t = 0; t < T; t++) {
+            uint32_t win, tie;
+            const uint32_t nn = (uint32_t)(crop0 + (uint64_t)i);
+            lsyn_ctc_step(seed, C, nn, t, &win, &tie);
+            float *o = dst + ((size_t)i * T + t) * C;
+            for (int c = 0; c < C; c++) o[c] = lsyn_ctc_value(seed, T, nn, t, (uint32_t)c, win, tie);
+        }
+}
