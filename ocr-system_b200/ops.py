@@ -427,9 +427,11 @@ def ctc_greedy(probs: torch.Tensor):
     return idx, pos, ln, conf
 
 
-def synth_pages(n: int, h: int = 3508, w: int = 2480, seed0: int = 0, device="cuda") -> torch.Tensor:
+def synth_pages(n: int, h: int = 3508, w: int = 2480, seed0: int = 0, device="cuda",
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Synthetic A4 text pages generated in HBM (identical bytes to oracle.synth_page)."""
-    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
     with torch.cuda.device(out.device):
         _chk(_L().lumina_synth_pages_u8(_ptr(out), n, h, w, C.c_uint64(seed0), _stream()))
     return out
