@@ -202,6 +202,33 @@ int lumina_jpeg_encode_rgb(const uint8_t *d_rgb, int n, int h, int w, int qualit
                            size_t out_stride, int64_t *h_sizes, void *d_workspace, size_t workspace_bytes,
                            void *stream);
 
+/* ---- "next" row: page ingest -- baseline JPEG decode in HBM ---- */
+/* image_preprocessing.py:57-75 (load_image / load_image_bytes: Image.open(...)) and services/ocr_service.py:494-496,
+ * 716-718 (the engine is handed files / bytes).  Replaces Pillow's JpegDecode.c -> libjpeg-turbo (Huffman decode,
+ * islow IDCT, fancy upsampling, YCbCr->RGB): the raster equals np.asarray(Image.open(file)) byte for byte, mode
+ * "RGB" (channels 3) or "L" (channels 1) as Pillow reports it.  Subset: 8-bit baseline / extended-sequential
+ * Huffman, one interleaved scan, grayscale or YCbCr with 4:4:4 / 4:2:2 / 4:2:0 sampling, restart intervals.
+ * Anything else (progressive, arithmetic, CMYK, RGB-tagged, 4:4:0, multi-scan) returns LUMINA_E_UNSUPPORTED from
+ * the probe / the batch call and stays on the host codec, which is what the reference uses for every file. */
+typedef struct lumina_jpeg_info {
+    int32_t width, height, channels; /* channels: 1 (mode "L") or 3 (mode "RGB") */
+    int32_t hs, vs;                  /* luma sampling factors: 1x1 = 4:4:4, 2x1 = 4:2:2, 2x2 = 4:2:0 */
+} lumina_jpeg_info;
+/* Host-only header parse.  LUMINA_OK / LUMINA_E_UNSUPPORTED / LUMINA_E_INVALID (malformed). */
+int lumina_jpeg_probe(const uint8_t *h_file, size_t len, lumina_jpeg_info *info);
+/* Device scratch for n files of one geometry whose sizes add up to total_file_bytes; host staging for the
+ * per-page tables (pinned memory lets the call stay asynchronous). */
+size_t lumina_jpeg_decode_workspace_bytes(int n, int h, int w, int channels, int hs, int vs, size_t total_file_bytes);
+size_t lumina_jpeg_decode_stage_bytes(int n);
+/* Decodes n files (file i = h_blob[h_offsets[i] .. h_offsets[i+1]), all w x h x channels with the same sampling)
+ * into d_out [n][h][w][channels].  The call parses the headers on the host, enqueues the upload of the files and
+ * tables and five kernels on `stream`, and returns; h_blob and h_stage must stay untouched until the stream has
+ * passed this call.  d_status [n] int32 (device): 0 = page decoded, 1 = the entropy-coded data did not contain
+ * exactly the blocks the header announces (truncated / corrupt file: decode that page on the host). */
+int lumina_jpeg_decode_batch(const uint8_t *h_blob, const int64_t *h_offsets, int n, int h, int w, int channels,
+                             uint8_t *d_out, int32_t *d_status, void *h_stage, void *d_workspace,
+                             size_t workspace_bytes, void *stream);
+
 /* ---- synthetic workloads (bench/test inputs generated in HBM) ------------ */
 /* A4-like text page, seeded by page index; identical bytes to the host
  * generator in include/lumina_synth.h compiled for the CPU. */

@@ -66,6 +66,10 @@ PROTOTYPES = {
     "lumina_reading_order": (_I, [_P, _P, _P, _I, _I, _D, _I, _P, _P, _P, _P, _P, _P]),
     "lumina_jpeg_workspace_bytes": (_Z, [_I, _I, _I]),
     "lumina_jpeg_encode_rgb": (_I, [_P, _I, _I, _I, _I, _I, _P, _Z, _P, _P, _Z, _P]),
+    "lumina_jpeg_probe": (_I, [_P, _Z, _P]),
+    "lumina_jpeg_decode_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I, _Z]),
+    "lumina_jpeg_decode_stage_bytes": (_Z, [_I]),
+    "lumina_jpeg_decode_batch": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "lumina_synth_pages_u8": (_I, [_P, _I, _I, _I, C.c_uint64, _P]),
     "lumina_synth_prob_maps_f32": (_I, [_P, _I, _I, _I, C.c_uint64, _P]),
     "lumina_synth_ctc_f32": (_I, [_P, _I, _I, _I, C.c_uint64, C.c_uint32, _P]),

@@ -591,3 +591,97 @@ def jpeg_encode(pages: torch.Tensor, quality: int = 95, optimize: bool = False):
     if any(f is None for f in files):
         raise _abi.LuminaError("a JPEG file exceeded the output buffer")
     return files
+
+
+# --------------------------------------------------------------------------- next row 8f.3
+class JpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32), ("hs", C.c_int32), ("vs", C.c_int32)]
+
+
+def jpeg_probe(data) -> Optional[JpegInfo]:
+    """Header parse of one file (bytes / bytearray / uint8 ndarray).  None when the file is not a JPEG the device
+    decodes (progressive, CMYK, ... or not a JPEG at all): such a file stays on the host codec, which is what the
+    reference uses for every file (image_preprocessing.py:63,72)."""
+    buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data
+    info = JpegInfo()
+    rc = _L().lumina_jpeg_probe(buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(info))
+    return info if rc == 0 else None
+
+
+class JpegDecoder:
+    """Batched baseline-JPEG decode in HBM (load_image / load_image_bytes, image_preprocessing.py:57-75): the files
+    cross PCIe, the rasters are produced on the device and equal ``np.asarray(Image.open(f))`` byte for byte.
+    Keeps its device workspace and a ring of pinned table-staging buffers, so a stream of batches allocates
+    nothing after the first call."""
+
+    RING = 4
+
+    def __init__(self):
+        self._ws = None
+        self._stage = []      # [(pinned tensor, event or None)]
+        self._turn = 0
+        self._blob = None     # pinned staging for callers that hand over Python bytes
+
+    def pack(self, files):
+        """list of bytes -> (pinned uint8 blob, int64 offsets [n+1]).  The blob is this decoder's own staging
+        buffer: valid until the next ``pack``."""
+        offs = np.zeros(len(files) + 1, np.int64)
+        np.cumsum([len(f) for f in files], out=offs[1:])
+        total = int(offs[-1])
+        if self._blob is None or self._blob.numel() < total:
+            self._blob = torch.empty(max(total, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        view = self._blob.numpy()
+        for f, o in zip(files, offs[:-1]):
+            view[o:o + len(f)] = np.frombuffer(f, np.uint8)
+        return self._blob[:total], offs
+
+    def decode(self, blob: torch.Tensor, offsets: np.ndarray, device=None, info: Optional[JpegInfo] = None):
+        """blob: CPU uint8 tensor holding the files back to back (pinned memory keeps the call asynchronous),
+        offsets int64 [n+1].  Returns (pages CUDA uint8 [N,H,W,C], status CUDA int32 [N]); enqueued on the
+        current stream of ``device``.  The blob must stay untouched until that stream has passed this call."""
+        if blob.is_cuda or blob.dtype != torch.uint8:
+            raise TypeError("JpegDecoder.decode needs a CPU uint8 tensor holding the files")
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = offsets.size - 1
+        if n <= 0:
+            raise ValueError("empty batch")
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        base = blob.numpy()
+        if info is None:
+            info = jpeg_probe(base[int(offsets[0]):int(offsets[1])])
+            if info is None:
+                raise _abi.LuminaError("page 0 is not a JPEG the device decoder covers")
+        h, w, c = int(info.height), int(info.width), int(info.channels)
+        total = int(offsets[-1] - offsets[0])
+        with torch.cuda.device(dev):
+            wsb = int(_L().lumina_jpeg_decode_workspace_bytes(n, h, w, c, info.hs, info.vs, total))
+            if self._ws is None or self._ws.numel() < wsb or self._ws.device != dev:
+                self._ws = None
+                self._ws = torch.empty(wsb + wsb // 8, dtype=torch.uint8, device=dev)
+            sb = int(_L().lumina_jpeg_decode_stage_bytes(n))
+            if len(self._stage) != self.RING or self._stage[0][0].numel() < sb:
+                self._stage = [[torch.empty(sb, dtype=torch.uint8, pin_memory=True), None] for _ in range(self.RING)]
+            slot = self._stage[self._turn % self.RING]
+            self._turn += 1
+            if slot[1] is not None:
+                slot[1].synchronize()   # the upload that last read this staging slot has finished
+            pages = torch.empty((n, h, w, c), dtype=torch.uint8, device=dev)
+            status = torch.empty(n, dtype=torch.int32, device=dev)
+            _chk(_L().lumina_jpeg_decode_batch(C.c_void_p(blob.data_ptr()), offsets.ctypes.data_as(C.c_void_p), n, h, w, c,
+                                               _ptr(pages), _ptr(status), C.c_void_p(slot[0].data_ptr()), _ptr(self._ws),
+                                               int(self._ws.numel()), _stream()))
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            slot[1] = ev
+        return pages, status
+
+
+def jpeg_decode(files, device=None):
+    """One-shot form: list of JPEG files (bytes) of one geometry -> CUDA uint8 [N,H,W,C] (synchronises)."""
+    d = JpegDecoder()
+    blob, offs = d.pack(files)
+    pages, status = d.decode(blob, offs, device)
+    bad = torch.nonzero(status).flatten().tolist()
+    if bad:
+        raise _abi.LuminaError(f"corrupt entropy-coded data in pages {bad}")
+    return pages

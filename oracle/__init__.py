@@ -21,8 +21,8 @@ _SO = os.path.join(_HERE, "liblumina_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "lumina_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("lumina_oracle.c", "jpeg_decode.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -294,3 +294,22 @@ def synth_ctc(n: int, t: int = 40, c: int = 6625, crop0: int = 0, seed: int = 1)
     out = np.empty((n, t, c), np.float32)
     lib().orc_synth_ctc(_p(out), n, t, c, C.c_uint64(crop0), C.c_uint32(seed))
     return out
+
+
+# --- ingest: baseline JPEG decode (load_image / load_image_bytes) ------------
+def jpeg_decode(data: bytes):
+    """image_preprocessing.py:57-75: Image.open(...) on a baseline JPEG (libjpeg-turbo islow IDCT, fancy
+    upsampling, YCbCr->RGB) -> HxWx3 (or HxW for grayscale files).  None when the file is outside the
+    restated subset (progressive, CMYK, 4:4:0 ...); ValueError when it is malformed."""
+    buf = np.frombuffer(data, np.uint8)
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().orc_jpeg_decode(_p(buf), C.c_size_t(buf.size), None, C.byref(w), C.byref(h), C.byref(c))
+    if rc == -4:
+        return None
+    if rc:
+        raise ValueError("malformed JPEG")
+    out = np.empty((h.value, w.value, c.value), np.uint8)
+    rc = lib().orc_jpeg_decode(_p(buf), C.c_size_t(buf.size), _p(out), C.byref(w), C.byref(h), C.byref(c))
+    if rc:
+        raise ValueError("malformed JPEG")
+    return out[:, :, 0] if c.value == 1 else out
