@@ -40,6 +40,7 @@ UNIT = "pages/s"
 MIN_TIMED_S = 2.0
 DB_KW = dict(thresh=0.3, box_thresh=0.6, unclip_ratio=1.5, max_candidates=1000)
 CTC_T, CTC_C = 40, 6625
+JPEG_Q = 75   # Pillow's default quality: the file form of a page for e2e_compressed
 
 
 def _peaks():
@@ -123,6 +124,33 @@ def host_pages(n: int, seed0: int = 0):
     O.build()
     with mp.get_context("fork").Pool(min(n, os.cpu_count() or 1)) as pool:
         return pool.map(_gen_page, range(seed0, seed0 + n))
+
+
+def _enc_page(page):
+    import io
+
+    from PIL import Image
+
+    b = io.BytesIO()
+    Image.fromarray(page).save(b, "JPEG", quality=JPEG_Q)
+    return b.getvalue()
+
+
+def cpu_reference_rate_from_files(sample_pages: int, max_dim: int, steps: int = 1):
+    """Same as cpu_reference_rate, but every page-task starts from the page's JPEG file (quality JPEG_Q) and calls
+    the reference's load_image_bytes first -- the CPU side of e2e_compressed."""
+    import multiprocessing as mp
+
+    from oracle import reference_port as RP
+
+    cores = os.cpu_count() or 1
+    distinct = host_pages(min(sample_pages, 2 * cores))
+    with mp.get_context("fork").Pool(min(len(distinct), cores)) as pool:
+        files = pool.map(_enc_page, distinct)
+    tasks = [files[i % len(files)] for i in range(sample_pages)]
+    ts = [RP.run_pool(tasks, max_dim, False, cores)[0] for _ in range(steps)]
+    dt = sum(ts) / len(ts)
+    return sample_pages / dt, dt, cores
 
 
 def cpu_reference_rate(sample_pages: int, max_dim: int, steps: int = 1, warmup: int = 0):
@@ -231,6 +259,10 @@ def main_reference(args):
     def chain_line():
         sample = args.cpu_sample or 8 * cores
         rate, dt, _ = cpu_reference_rate(sample, args.max_dim, steps=args.steps, warmup=min(args.warmup, 1))
+        frate, _fdt, _ = cpu_reference_rate_from_files(sample, args.max_dim, steps=max(1, min(args.steps, 3)))
+        base["e2e_compressed"] = {"value": frate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                  "note": f"same page-tasks starting from the page's JPEG file (quality {JPEG_Q}): the "
+                                          "reference's load_image_bytes (Pillow decode) + the chain"}
         return dict(base, metric=METRIC, value=rate, unit=UNIT, ms_per_step=dt * 1e3, dtype="u8", config=_workload2(args),
                     cpu_baseline={"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                   "sample": f"{sample} synthetic A4 pages per step, one page per task, "
@@ -482,6 +514,35 @@ def bench_chain(cx: Ctx):
     e2e_ms = cx.max_over_ranks(g0.elapsed_time(g1))
     del host_pool
 
+    # ---- (d) e2e_compressed: the pages start as baseline-JPEG FILES in pinned host memory (what load_image_bytes is
+    # handed); files -> HBM -> device decode -> stream-pipelined chain -> results in host memory ---------------
+    enc_pool, file_bytes = [], 0
+    packer = ops.JpegDecoder()
+    for p in range(P):
+        files = []
+        for j in range(0, B, 16):   # the device encoder writes Pillow's byte stream (tests/test_jpeg.py)
+            files += ops.jpeg_encode(pool[p][j:j + 16], quality=JPEG_Q)
+        blob, offs = packer.pack(files)
+        enc_pool.append((blob.clone().pin_memory(), offs))
+        file_bytes += int(offs[-1])
+    del packer
+    torch.cuda.synchronize()
+    for _ in pipe.run_encoded_stream([enc_pool[i % P] for i in range(3)]):
+        pass
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    launches0 = ops.launch_count()
+    for i, (_out, _res, _h2d, d2h_c) in enumerate(pipe.run_encoded_stream(enc_pool[i % P] for i in range(W + Ke + 2))):
+        if i == W - 1:
+            c0.record()
+        if i == W + Ke - 1:
+            c1.record()
+    torch.cuda.synchronize()
+    cx.barrier()
+    e2ec_ms = cx.max_over_ranks(c0.elapsed_time(c1))
+    launches_c = (ops.launch_count() - launches0) // (W + Ke + 2)
+    del enc_pool
+
     if rank != 0:
         return None
     peak, peak_src = _peaks()
@@ -516,6 +577,13 @@ def bench_chain(cx: Ctx):
                 "note": "steady state of PagePipeline.run_host_stream over rotating distinct pinned batches: host rasters -> "
                         "HBM -> chain -> results in host memory for every batch; the upload of batch i+1 overlaps the "
                         "kernels of batch i"},
+        "e2e_compressed": {"value": world * B * Ke / (e2ec_ms / 1e3), "unit": UNIT,
+                           "h2d_bytes_per_step": int(file_bytes // P), "d2h_bytes_per_step": int(d2h_c),
+                           "ms_per_step": e2ec_ms / Ke, "timed_steps": Ke, "gpu_launches_per_step": int(launches_c),
+                           "note": f"steady state of PagePipeline.run_encoded_stream: the same pages as baseline-JPEG files "
+                                   f"(quality {JPEG_Q}, 4:2:0, what Pillow's save() writes) in pinned host memory -> HBM -> "
+                                   "device decode (raster == Pillow's, byte for byte) -> stream-pipelined chain -> results in "
+                                   "host memory; the reference side of this is load_image_bytes + the chain"},
         "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_unp),
         "clocks": clocks,
         "roofline": {

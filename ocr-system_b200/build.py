@@ -51,6 +51,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd.append("-fmad=false")
         if os.environ.get("LUMINA_PPHT_PROFILE") and src == "k_ppht.cu":
             cmd.append("-DLUMINA_PPHT_PROFILE=1")  # per-phase clock64 ticks in the stats buffer (tools/ppht_stats.py)
+        if src == "k_jpegd.cu":  # experiment knobs (sub-sequence length / CTA size of the entropy kernel)
+            for k in ("LUMINA_JD_SWL", "LUMINA_JD_CHUNK"):
+                if os.environ.get(k):
+                    cmd.append(f"-D{k}={os.environ[k]}")
         cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

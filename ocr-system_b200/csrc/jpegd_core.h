@@ -31,10 +31,18 @@
 #define JD_MAX_TABLES 6 /* distinct (class, id) tables a 3-component scan can select */
 #define JD_MAX_SLOTS 6  /* blocks per MCU: 4:2:0 -> Y Y Y Y Cb Cr */
 
+#define JD_SUB_BITS 6   /* second-level tables resolve code bits 11..16 */
+#ifndef JD_MAX_SUB
+#define JD_MAX_SUB 16   /* 10-bit prefixes with longer codes a table may have before it falls back to the ladder */
+#endif
+
 struct JdHuff {
-    uint16_t lut[1 << JD_LUT_BITS]; /* (length << 8) | symbol for codes of <= JD_LUT_BITS bits, else 0 */
-    int32_t maxcode[18];            /* jdhuff.c jpeg_make_d_derived_tbl: largest code of length l, -1 if none */
-    int32_t valoff[17];             /* vals index = code + valoff[l] */
+    /* first level, indexed by the next 10 bits: (length << 8) | symbol for codes of <= 10 bits; 0x8000 | n for a
+     * prefix of longer codes (n = second-level table, 0xFF = walk the maxcode ladder); 0 = no such code */
+    uint16_t lut[1 << JD_LUT_BITS];
+    uint16_t lut2[JD_MAX_SUB << JD_SUB_BITS]; /* indexed by n * 64 + the following 6 bits: (length << 8) | symbol, or 0 */
+    int32_t maxcode[18];                      /* jdhuff.c jpeg_make_d_derived_tbl: largest code of length l, -1 if none */
+    int32_t valoff[17];                       /* vals index = code + valoff[l] */
     uint8_t vals[256];
 };
 
@@ -50,6 +58,12 @@ struct JdPageHdr {
     uint16_t mcux, mcuy;
     uint8_t ncomp, hs, vs, bpm, ntab, pad0, pad1, pad2;
     uint8_t slot_comp[8], slot_dc[8], slot_ac[8]; /* per block slot of an MCU: component, DC table, AC table */
+    /* DC differences / predictions are kept per component: block (mcu m, slot s) -> slot_dcbase[s] + m * slot_cnt[s] */
+    uint8_t slot_cnt[8];
+    uint32_t slot_dcbase[8];
+    uint32_t dc_off[4];   /* first element of component c (multiples of 8), dc_off[ncomp] = elements per page */
+    uint32_t tile_off;    /* first 16 KB tile of this page in the unstuff kernels' grid */
+    uint32_t n_tiles;
 };
 
 struct JdPage {
@@ -69,38 +83,72 @@ static const uint8_t kJdZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32
 
 // ------------------------------------------------------------------------------------------------------------
 // Bit window over the big-endian word stream: peek32(p) = the 32 bits that start at bit p.
+// Word i of a page's stream.  (A layout transposed inside chunks of 256 sub-sequences -- neighbouring threads reading
+// neighbouring words -- was measured slower on B200: the 4-byte scatter writes of the unstuff pass leave partially
+// written L2 sectors and the decoder's lanes drift apart by several words; the linear layout keeps each thread on its
+// own 32-byte sectors, which it re-uses 8 times.)
+#define JD_CHUNK_LOG2 8
+JD_HD uint32_t jd_word_index(uint32_t i, uint32_t swl) {
+    (void)swl;
+    return i;
+}
+
 struct JdBits {
     const uint32_t *w;
-    uint32_t wi, w0, w1;
-    JD_HD void init(const uint32_t *words, uint32_t p) {
+    uint32_t swl;
+    uint32_t wi, w0, w1, w2; /* words wi, wi+1 and (loaded one refill ahead of its use) wi+2 */
+    JD_HD uint32_t ld(uint32_t i) const { return w[jd_word_index(i, swl)]; }
+    JD_HD void init(const uint32_t *words, uint32_t sub_words_log2, uint32_t p) {
         w = words;
+        swl = sub_words_log2;
         wi = p >> 5;
-        w0 = w[wi];
-        w1 = w[wi + 1];
+        w0 = ld(wi);
+        w1 = ld(wi + 1);
+        w2 = ld(wi + 2);
     }
     JD_HD uint32_t peek32(uint32_t p) {
         uint32_t i = p >> 5;
         if (i != wi) {
-            w0 = (i == wi + 1) ? w1 : w[i];
-            w1 = w[i + 1];
+            if (i == wi + 1) {
+                w0 = w1;
+                w1 = w2;
+            } else {
+                w0 = ld(i);
+                w1 = ld(i + 1);
+            }
+            w2 = ld(i + 2);
             wi = i;
         }
         uint32_t s = p & 31;
+#ifdef __CUDA_ARCH__
+        return __funnelshift_l(w1, w0, s);
+#else
         return s ? (w0 << s) | (w1 >> (32 - s)) : w0;
+#endif
     }
 };
 
-// One Huffman symbol from the 32-bit window v: returns (length << 8) | symbol.  Codes longer than the LUT walk
-// jdhuff.c's maxcode ladder; an impossible prefix (only reachable while a thread is still out of step, or in a
-// corrupt file) decodes as symbol 0 of length 16, as libjpeg's "corrupt data" path does.
+// One Huffman symbol from the 32-bit window v: returns (length << 8) | symbol.  An impossible prefix (only
+// reachable while a thread is still out of step, or in a corrupt file) decodes as symbol 0 of length 16, as
+// libjpeg's "corrupt data" path does.
 JD_HD uint32_t jd_symbol(const JdHuff &t, uint32_t v) {
     uint32_t e = t.lut[v >> (32 - JD_LUT_BITS)];
-    if (e) return e;
-    for (int l = JD_LUT_BITS + 1; l <= 16; l++) {
-        int32_t code = (int32_t)(v >> (32 - l));
-        if (code <= t.maxcode[l]) return ((uint32_t)l << 8) | t.vals[(code + t.valoff[l]) & 255];
+    if (e & 0x8000u) {
+        const uint32_t n = e & 0xFFu;
+        if (n != 0xFFu) {
+            e = t.lut2[(n << JD_SUB_BITS) | ((v >> (32 - JD_LUT_BITS - JD_SUB_BITS)) & ((1u << JD_SUB_BITS) - 1u))];
+        } else {
+            e = 0;
+            for (int l = JD_LUT_BITS + 1; l <= 16; l++) {
+                int32_t code = (int32_t)(v >> (32 - l));
+                if (code <= t.maxcode[l]) {
+                    e = ((uint32_t)l << 8) | t.vals[(code + t.valoff[l]) & 255];
+                    break;
+                }
+            }
+        }
     }
-    return 16u << 8;
+    return e ? e : (16u << 8);
 }
 
 JD_HD int jd_extend(uint32_t r, int s) { return (int)r < (1 << (s - 1)) ? (int)r - (1 << s) + 1 : (int)r; }
@@ -115,10 +163,10 @@ struct JdSubResult {
 // Decodes the symbols that start in [entry.p, end_bit).  `rst` = restart boundaries of this page (bit positions
 // in the unstuffed stream, ascending, n_rst of them); total_bits = length of the stream.  With WRITE, block
 // `blk0 + completed` receives its AC coefficients in natural order (coef, 64 int16 per block, pre-zeroed) and its
-// DC *difference* (dcdiff, one int16 per block); blocks >= nblk_total are dropped.
+// DC *difference* (dcdiff, one int16 per block, laid out per component: see JdPageHdr); blocks >= nblk_total are dropped.
 template <bool WRITE>
 JD_HD JdSubResult jd_decode_sub(const JdPageHdr &pg, const JdHuff *tabs, const uint8_t *zz, const uint32_t *words,
-                                uint32_t total_bits, const uint32_t *rst, int n_rst, JdState entry, uint32_t end_bit,
+                                uint32_t sub_words_log2, uint32_t total_bits, const uint32_t *rst, int n_rst, JdState entry, uint32_t end_bit,
                                 int32_t blk0, int32_t nblk_total, int16_t *coef, int16_t *dcdiff) {
     JdSubResult res;
     uint32_t p = entry.p, slot = entry.sk & 255, k = entry.sk >> 8;
@@ -144,14 +192,20 @@ JD_HD JdSubResult jd_decode_sub(const JdPageHdr &pg, const JdHuff *tabs, const u
     const uint32_t bpm = pg.bpm;
     const int32_t blocks_per_interval = (int32_t)(pg.restart_interval * bpm);
     JdBits bits;
-    bits.init(words, p);
+    bits.init(words, sub_words_log2, p);
     int32_t blk = blk0;
+    /* (dc table | ac table << 4) of every block slot in one register: no memory access at a block end */
+    unsigned long long slotmap = 0;
+    for (uint32_t i = 0; i < bpm; i++) slotmap |= (unsigned long long)(pg.slot_dc[i] | (pg.slot_ac[i] << 4)) << (8 * i);
+    uint32_t tsel = (uint32_t)(slotmap >> (8 * slot));
+    const JdHuff *t_dc = tabs + (tsel & 15u), *t_ac = tabs + ((tsel >> 4) & 15u);
+    uint32_t mcu = WRITE ? (uint32_t)(blk0 - (int32_t)slot) / bpm : 0u; /* MCU of the current block */
     while (p < end_bit) {
-        uint32_t v = bits.peek32(p);
-        const JdHuff &t = tabs[k == 0 ? pg.slot_dc[slot] : pg.slot_ac[slot]];
-        uint32_t e = jd_symbol(t, v);
-        uint32_t len = e >> 8, sym = e & 255, s = sym & 15, r = k == 0 ? 0 : sym >> 4;
-        uint32_t tot = len + s;
+        const uint32_t v = bits.peek32(p);
+        const bool is_dc = k == 0;
+        const uint32_t e = jd_symbol(is_dc ? *t_dc : *t_ac, v);
+        const uint32_t len = e >> 8, sym = e & 255, s = sym & 15, r = is_dc ? 0 : sym >> 4;
+        const uint32_t tot = len + s;
         if (p + tot > limit) {
             if (limit >= total_bits) { /* ran into the end of the scan */
                 p = total_bits;
@@ -166,37 +220,32 @@ JD_HD JdSubResult jd_decode_sub(const JdPageHdr &pg, const JdHuff *tabs, const u
             abs_base = ri * blocks_per_interval;
             nb = 0;
             blk = abs_base;
+            mcu = (uint32_t)ri * pg.restart_interval;
+            tsel = (uint32_t)slotmap;
+            t_dc = tabs + (tsel & 15u);
+            t_ac = tabs + ((tsel >> 4) & 15u);
             continue;
         }
-        int val = 0;
-        if (s) val = jd_extend((v << len) >> (32 - s), (int)s);
         p += tot;
-        if (k == 0) {
-            if (WRITE && blk < nblk_total) dcdiff[blk] = (int16_t)val;
-            k = 1;
-        } else if (s) {
+        if (s | (uint32_t)is_dc) {
+            const int val = s ? jd_extend((v << len) >> (32 - s), (int)s) : 0;
             k += r;
-            if (WRITE && blk < nblk_total) coef[(size_t)blk * 64 + (k < 64 ? zz[k] : 63)] = (int16_t)val;
+            if (WRITE && blk < nblk_total) {
+                if (is_dc) dcdiff[pg.slot_dcbase[slot] + mcu * pg.slot_cnt[slot]] = (int16_t)val;
+                else coef[(size_t)blk * 64 + (k < 64 ? zz[k] : 63)] = (int16_t)val;
+            }
             k++;
-        } else if (r == 15) {
-            k += 16;
         } else {
-            k = 64;
+            k = r == 15 ? k + 16 : 64;
         }
         if (k >= 64) {
             k = 0;
             nb++;
             blk++;
-            if (++slot == bpm) slot = 0;
-        }
-        if (p == limit && limit < total_bits) { /* landed exactly on a restart boundary */
-            ri++;
-            limit = ri < n_rst ? rst[ri] : total_bits;
-            slot = 0;
-            k = 0;
-            abs_base = ri * blocks_per_interval;
-            nb = 0;
-            blk = abs_base;
+            if (++slot == bpm) slot = 0, mcu++;
+            tsel = (uint32_t)(slotmap >> (8 * slot));
+            t_dc = tabs + (tsel & 15u);
+            t_ac = tabs + ((tsel >> 4) & 15u);
         }
     }
     res.exit.p = p;
@@ -311,14 +360,26 @@ static inline int jd_rd16(const uint8_t *p) { return (p[0] << 8) | p[1]; }
 static inline void jd_build_huff(const uint8_t *bits /*[17]*/, const uint8_t *vals, JdHuff *t) {
     memset(t, 0, sizeof *t);
     memcpy(t->vals, vals, 256);
-    int code = 0, k = 0;
+    int code = 0, k = 0, nsub = 0;
     for (int l = 1; l <= 16; l++) {
         if (bits[l]) {
             t->valoff[l] = k - code;
             for (int i = 0; i < bits[l]; i++, k++, code++) {
-                if (l <= JD_LUT_BITS && code < (1 << l)) {
+                if (code >= (1 << l)) continue; /* over-subscribed table: jdhuff.c rejects it; never matched here */
+                const uint16_t ent = (uint16_t)((l << 8) | vals[k & 255]);
+                if (l <= JD_LUT_BITS) {
                     int first = code << (JD_LUT_BITS - l), cnt = 1 << (JD_LUT_BITS - l);
-                    for (int j = 0; j < cnt; j++) t->lut[first + j] = (uint16_t)((l << 8) | vals[k & 255]);
+                    for (int j = 0; j < cnt; j++) t->lut[first + j] = ent;
+                } else {
+                    int prefix = code >> (l - JD_LUT_BITS);
+                    uint16_t &slot = t->lut[prefix];
+                    if (slot == 0) slot = (uint16_t)(0x8000 | (nsub < JD_MAX_SUB ? nsub++ : 0xFF));
+                    if (!(slot & 0x8000)) continue; /* prefix already taken by a shorter code: malformed */
+                    int n = slot & 0xFF;
+                    if (n == 0xFF) continue;
+                    int rest = l - JD_LUT_BITS; /* 1..6 bits behind the prefix */
+                    int first = (code & ((1 << rest) - 1)) << (JD_SUB_BITS - rest), cnt = 1 << (JD_SUB_BITS - rest);
+                    for (int j = 0; j < cnt; j++) t->lut2[(n << JD_SUB_BITS) + first + j] = ent;
                 }
             }
             t->maxcode[l] = code - 1;
@@ -478,5 +539,19 @@ static inline int jd_parse(const uint8_t *f, size_t len, JdInfo *info, JdPage *p
     }
     ph->bpm = (uint8_t)slot;
     ph->ntab = (uint8_t)ntab;
+    {
+        const uint32_t nmcu = (uint32_t)ph->mcux * ph->mcuy;
+        uint32_t off = 0;
+        for (int i = 0, sl = 0; i < nc; i++) {
+            const int cnt = (i == 0) ? ch[0] * cv[0] : 1;
+            ph->dc_off[i] = off;
+            for (int b = 0; b < cnt; b++, sl++) {
+                ph->slot_cnt[sl] = (uint8_t)cnt;
+                ph->slot_dcbase[sl] = off + (uint32_t)b;
+            }
+            off += (nmcu * (uint32_t)cnt + 7u) & ~7u;
+        }
+        ph->dc_off[nc] = off;
+    }
     return 0;
 }

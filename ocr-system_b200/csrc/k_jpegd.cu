@@ -4,7 +4,7 @@
 // and backend/services/ocr_service.py:494-496,716-718 (the engine is handed files / bytes).  Today those bytes
 // are decoded by Pillow -> libjpeg-turbo on one host core (65-90 ms per A4 page) and the 26 MB raster crosses
 // PCIe; here the *file* crosses PCIe (1-2 MB) and is decoded in HBM to the same raster, byte for byte:
-//   jpegd_unstuff_kernel   scan bytes -> big-endian word stream without 0xFF00 stuffing / RSTn markers
+//   jpegd_unstuff_*_kernel scan bytes -> big-endian word stream without 0xFF00 stuffing / RSTn markers (count, scatter)
 //   jpegd_entropy_kernel   self-synchronising parallel Huffman decode (jpegd_core.h), one launch: sub-sequence
 //                          decode from guessed states, in-CTA propagation of exit states, CTA-to-CTA chain with
 //                          provisional / final hand-over, block-index scan, coefficient write
@@ -20,8 +20,15 @@
 
 namespace lumina {
 
-constexpr int kJdSubBits = 1024;     // sub-sequence length (bits of unstuffed stream)
-constexpr int kJdChunk = 256;        // sub-sequences (threads) per CTA of the entropy kernel
+#ifndef LUMINA_JD_SWL
+#define LUMINA_JD_SWL 7
+#endif
+constexpr uint32_t kJdSwl = LUMINA_JD_SWL;   // log2(32-bit words per sub-sequence)
+constexpr int kJdSubBits = 32 << kJdSwl;     // sub-sequence length (bits of unstuffed stream)
+#ifndef LUMINA_JD_CHUNK
+#define LUMINA_JD_CHUNK 256
+#endif
+constexpr int kJdChunk = LUMINA_JD_CHUNK;        // sub-sequences (threads) per CTA of the entropy kernel
 constexpr int kUnstuffThreads = 1024;
 
 __constant__ uint8_t c_jd_zz[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -30,8 +37,8 @@ __constant__ uint8_t c_jd_zz[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 
 
 // ---- workspace carve-up (host) -------------------------------------------------------------------------------
 struct JdLayout {
-    size_t blob, pages, stream, stream_bits, n_rst, rst, chain, chain_base, ticket, coef, dc, planes, total;
-    size_t stream_words, blob_bytes, nblk, plane_bytes;
+    size_t blob, pages, stream, stream_bits, n_rst, rst, tiles, chain, chain_base, ticket, coef, dc, planes, total;
+    size_t stream_words, blob_bytes, nblk, plane_bytes, dc_stride;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -44,9 +51,14 @@ static JdLayout jd_layout(int n, int h, int w, int channels, int hs, int vs, siz
     L.plane_bytes = L.nblk * 64;
     L.blob_bytes = align_up(total_file_bytes + 64, 256);
     // every page's stream region: its stuffed length rounded up + 16 bytes of zero padding, in words
-    L.stream_words = (total_file_bytes + (size_t)n * 32) / 4 + 64;
+    L.stream_words = total_file_bytes / 4 + (size_t)n * 16 + 64;
     size_t max_cta = (total_file_bytes * 8) / ((size_t)kJdSubBits * kJdChunk) + 2 * (size_t)n + 8;
     size_t max_rst = (size_t)n * (size_t)mcux * mcuy + 8;
+    size_t max_tiles = total_file_bytes / (kUnstuffThreads * 16) + 2 * (size_t)n + 8;
+    {
+        size_t nmcu = (size_t)mcux * mcuy, cnt0 = channels == 1 ? 1 : (size_t)hs * vs;
+        L.dc_stride = (nmcu * cnt0 + 7) / 8 * 8 + (channels == 1 ? 0 : 2 * ((nmcu + 7) / 8 * 8));
+    }
     size_t o = 0;
     L.blob = o, o += L.blob_bytes;
     L.pages = o, o += align_up((size_t)n * sizeof(JdPage), 256);
@@ -54,118 +66,190 @@ static JdLayout jd_layout(int n, int h, int w, int channels, int hs, int vs, siz
     L.stream_bits = o, o += align_up((size_t)n * 4, 256);
     L.n_rst = o, o += align_up((size_t)n * 4, 256);
     L.rst = o, o += align_up(max_rst * 4, 256);
+    L.tiles = o, o += align_up(max_tiles * sizeof(uint64_t), 256);
     L.chain = o, o += align_up(max_cta * 8, 256);
     L.chain_base = o, o += align_up(max_cta * 4, 256);
     L.ticket = o, o += 256;
     L.coef = o, o += align_up((size_t)n * L.nblk * 128, 256);
-    L.dc = o, o += align_up((size_t)n * L.nblk * 2, 256);
+    L.dc = o, o += align_up((size_t)n * L.dc_stride * 2, 256);
     L.planes = o, o += align_up((size_t)n * L.plane_bytes, 256);
     L.total = o;
     return L;
 }
 
 // ---- 1. unstuff ----------------------------------------------------------------------------------------------
-// One CTA per page walks the scan in tiles of 16 KB (16 bytes per thread).  A byte is dropped when it is the
-// 0x00 behind a 0xFF, a fill 0xFF, or part of an RSTn marker; the first other marker ends the scan.
-__global__ void __launch_bounds__(kUnstuffThreads) jpegd_unstuff_kernel(const uint8_t *__restrict__ blob,
-                                                                        const JdPage *__restrict__ pages,
-                                                                        uint32_t *__restrict__ stream,
-                                                                        uint32_t *__restrict__ stream_bits,
-                                                                        uint32_t *__restrict__ rst,
-                                                                        uint32_t *__restrict__ n_rst) {
-    const JdPageHdr &pg = pages[blockIdx.x].h;
+// A byte is dropped when it is the 0x00 behind a 0xFF, a fill 0xFF, or part of an RSTn marker; the first other
+// marker ends the scan.  Two launches over 16 KB tiles (16 bytes per thread): count (kept bytes, restart markers,
+// terminating marker per tile), then scatter at the tile's offset (sum over the page's earlier tiles).
+struct JdTile {
+    uint32_t counts; /* kept bytes | restart markers << 16 */
+    uint32_t term;   /* position of the terminating marker in this tile (virtual stream coordinates), ~0 if none */
+};
+
+struct JdClass {
+    uint32_t keep, rmask, term, wv[4];
+};
+
+__device__ __forceinline__ JdClass jd_classify(const uint8_t *src, uint32_t pos, uint32_t lead, uint32_t vlen) {
+    JdClass c;
+    c.keep = c.rmask = 0;
+    c.term = 0xFFFFFFFFu;
+    c.wv[0] = c.wv[1] = c.wv[2] = c.wv[3] = 0;
+    if (pos >= vlen) return c;
+    const uint4 v = *reinterpret_cast<const uint4 *>(src + pos);
+    c.wv[0] = v.x, c.wv[1] = v.y, c.wv[2] = v.z, c.wv[3] = v.w;
+    uint32_t prev = (pos > lead) ? src[pos - 1] : 0u;
+    const uint32_t next = (pos + 16 < vlen) ? src[pos + 16] : 0xD9u;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        uint32_t b = (c.wv[j >> 2] >> (8 * (j & 3))) & 255u;
+        uint32_t nx = j < 15 ? (c.wv[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 255u : next;
+        if (pos + j + 1 >= vlen) nx = 0xD9u;
+        const bool valid = pos + j >= lead && pos + j < vlen;
+        if (!valid) b = 0u;
+        bool k;
+        if (b == 0xFFu) {
+            k = nx == 0u;
+            const bool isr = nx >= 0xD0u && nx <= 0xD7u;
+            if (valid && isr) c.rmask |= 1u << j;
+            if (valid && !k && !isr && nx != 0xFFu && c.term == 0xFFFFFFFFu) c.term = pos + j;
+        } else {
+            k = prev != 0xFFu;
+        }
+        if (valid && k) c.keep |= 1u << j;
+        prev = b;
+    }
+    return c;
+}
+
+// tile -> page (tiles are page-major; pages are few)
+__device__ __forceinline__ int jd_page_of_tile(const JdPage *pages, int n_pages, uint32_t tile) {
+    int lo = 0, hi = n_pages - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (pages[mid].h.tile_off <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// block-wide exclusive scan of a packed (low 16 | high 16) counter; *total = sum over the CTA
+__device__ __forceinline__ uint32_t jd_block_excl_scan(uint32_t mine, uint32_t *s_warp, uint32_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = s_warp[lane], ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, ti, d);
+            if (lane >= d) ti += u;
+        }
+        s_warp[lane] = ti - t;
+        if (lane == 31) s_warp[32] = ti;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return incl - mine + s_warp[wid];
+}
+
+__global__ void __launch_bounds__(kUnstuffThreads) jpegd_unstuff_count_kernel(const uint8_t *__restrict__ blob,
+                                                                              const JdPage *__restrict__ pages,
+                                                                              int n_pages, JdTile *__restrict__ tiles) {
+    const int page = jd_page_of_tile(pages, n_pages, blockIdx.x);
+    const JdPageHdr &pg = pages[page].h;
     const uint32_t abase = pg.scan_off & ~15u, lead = pg.scan_off - abase, vlen = lead + pg.scan_len;
-    const uint8_t *src = blob + abase;
+    const uint32_t pos = (blockIdx.x - pg.tile_off) * (kUnstuffThreads * 16) + threadIdx.x * 16;
+    __shared__ uint32_t s_term, s_warp[33];
+    if (threadIdx.x == 0) s_term = 0xFFFFFFFFu;
+    __syncthreads();
+    JdClass c = jd_classify(blob + abase, pos, lead, vlen);
+    if (c.term != 0xFFFFFFFFu) atomicMin(&s_term, c.term);
+    __syncthreads();
+    const uint32_t tpos = s_term;
+    if (tpos != 0xFFFFFFFFu && pos + 16 > tpos) {
+        const uint32_t m = tpos <= pos ? 0u : (1u << (tpos - pos)) - 1u;
+        c.keep &= m, c.rmask &= m;
+    }
+    uint32_t total;
+    jd_block_excl_scan((uint32_t)__popc(c.keep) | ((uint32_t)__popc(c.rmask) << 16), s_warp, &total);
+    if (threadIdx.x == 0) {
+        tiles[blockIdx.x].counts = total;
+        tiles[blockIdx.x].term = tpos;
+    }
+}
+
+__global__ void __launch_bounds__(kUnstuffThreads) jpegd_unstuff_scatter_kernel(
+    const uint8_t *__restrict__ blob, const JdPage *__restrict__ pages, int n_pages, const JdTile *__restrict__ tiles,
+    uint32_t *__restrict__ stream, uint32_t *__restrict__ stream_bits, uint32_t *__restrict__ rst,
+    uint32_t *__restrict__ n_rst) {
+    const int page = jd_page_of_tile(pages, n_pages, blockIdx.x);
+    const JdPageHdr &pg = pages[page].h;
+    const uint32_t abase = pg.scan_off & ~15u, lead = pg.scan_off - abase, vlen = lead + pg.scan_len;
+    const uint32_t my_tile = blockIdx.x - pg.tile_off;
+    const uint32_t pos = my_tile * (kUnstuffThreads * 16) + threadIdx.x * 16;
+    __shared__ uint32_t s_warp[33], s_base[2], s_dead;
+    // offset of this tile = sum over the page's earlier tiles (a few hundred at most); dead if one of them ended the scan
+    {
+        uint32_t kept = 0, nr = 0, dead = 0;
+        for (uint32_t t = threadIdx.x; t < my_tile; t += kUnstuffThreads) {
+            const JdTile ti = tiles[pg.tile_off + t];
+            kept += ti.counts & 0xFFFFu, nr += ti.counts >> 16;
+            dead |= ti.term != 0xFFFFFFFFu;
+        }
+        if (threadIdx.x == 0) s_base[0] = s_base[1] = s_dead = 0;
+        __syncthreads();
+        if (kept | nr | dead) {
+            atomicAdd(&s_base[0], kept);
+            atomicAdd(&s_base[1], nr);
+            if (dead) s_dead = 1;
+        }
+        __syncthreads();
+    }
+    if (s_dead) return;
+    const uint32_t base_bytes = s_base[0], base_rst = s_base[1];
+    const uint32_t tpos = tiles[blockIdx.x].term;
+    JdClass c = jd_classify(blob + abase, pos, lead, vlen);
+    if (tpos != 0xFFFFFFFFu && pos + 16 > tpos) {
+        const uint32_t m = tpos <= pos ? 0u : (1u << (tpos - pos)) - 1u;
+        c.keep &= m, c.rmask &= m;
+    }
+    uint32_t total;
+    const uint32_t excl = jd_block_excl_scan((uint32_t)__popc(c.keep) | ((uint32_t)__popc(c.rmask) << 16), s_warp, &total);
     uint8_t *dst = reinterpret_cast<uint8_t *>(stream + pg.stream_word_off);
     uint32_t *rpos = rst + pg.rst_off;
     const uint32_t nrmax = pg.n_rst_max;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_term;
-    __shared__ uint32_t s_tile_total;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t run_bytes = 0, run_rst = 0;
-    for (uint32_t tile = 0; tile < vlen; tile += kUnstuffThreads * 16) {
-        if (tid == 0) s_term = 0xFFFFFFFFu;
-        __syncthreads();
-        const uint32_t pos = tile + tid * 16;
-        uint32_t keep = 0, rmask = 0, term = 0xFFFFFFFFu;
-        uint32_t wv[4] = {0, 0, 0, 0};
-        if (pos < vlen) {
-            uint4 v = *reinterpret_cast<const uint4 *>(src + pos);
-            wv[0] = v.x, wv[1] = v.y, wv[2] = v.z, wv[3] = v.w;
-            uint32_t prev = (pos > lead) ? src[pos - 1] : 0u;
-            uint32_t next = (pos + 16 < vlen) ? src[pos + 16] : 0xD9u;
+    uint32_t ob = base_bytes + (excl & 0xFFFFu), orst = base_rst + (excl >> 16);
+    if (c.keep == 0xFFFFu && (ob & 3u) == 0u) {   // the common case: 16 kept bytes landing on a word boundary
+        uint4 o;
+        o.x = __byte_perm(c.wv[0], 0, 0x0123), o.y = __byte_perm(c.wv[1], 0, 0x0123);
+        o.z = __byte_perm(c.wv[2], 0, 0x0123), o.w = __byte_perm(c.wv[3], 0, 0x0123);
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+        const uint32_t wi = ob >> 2;
+        d32[jd_word_index(wi, kJdSwl)] = o.x, d32[jd_word_index(wi + 1, kJdSwl)] = o.y;
+        d32[jd_word_index(wi + 2, kJdSwl)] = o.z, d32[jd_word_index(wi + 3, kJdSwl)] = o.w;
+    } else if (c.keep | c.rmask) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                uint32_t c = (wv[j >> 2] >> (8 * (j & 3))) & 255u;
-                uint32_t nx = j < 15 ? (wv[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 255u : next;
-                if (pos + j + 1 >= vlen) nx = 0xD9u;
-                bool valid = pos + j >= lead && pos + j < vlen;
-                if (!valid) c = 0u;
-                bool k;
-                if (c == 0xFFu) {
-                    k = nx == 0u;
-                    bool isr = nx >= 0xD0u && nx <= 0xD7u;
-                    if (valid && isr) rmask |= 1u << j;
-                    if (valid && !k && !isr && nx != 0xFFu && term == 0xFFFFFFFFu) term = pos + j;
-                } else {
-                    k = prev != 0xFFu;
-                }
-                if (valid && k) keep |= 1u << j;
-                prev = c;
+        for (int j = 0; j < 16; j++) {
+            if (c.keep & (1u << j)) {
+                dst[(jd_word_index(ob >> 2, kJdSwl) << 2) | ((ob & 3u) ^ 3u)] = (uint8_t)((c.wv[j >> 2] >> (8 * (j & 3))) & 255u);
+                ob++;
+            } else if (c.rmask & (1u << j)) {
+                if (orst < nrmax) rpos[orst] = ob * 8u;
+                orst++;
             }
         }
-        if (term != 0xFFFFFFFFu) atomicMin(&s_term, term);
-        __syncthreads();
-        const uint32_t tpos = s_term;
-        if (tpos != 0xFFFFFFFFu && pos + 16 > tpos) {
-            uint32_t m = tpos <= pos ? 0u : (1u << (tpos - pos)) - 1u;
-            keep &= m;
-            rmask &= m;
-        }
-        // block exclusive scan of (kept bytes | restart markers << 16)
-        uint32_t mine = (uint32_t)__popc(keep) | ((uint32_t)__popc(rmask) << 16), incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t t = s_warp[lane], ti = t;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t u = __shfl_up_sync(0xffffffffu, ti, d);
-                if (lane >= d) ti += u;
-            }
-            s_warp[lane] = ti - t;
-            if (lane == 31) s_tile_total = ti;
-        }
-        __syncthreads();
-        const uint32_t excl = incl - mine + s_warp[wid];
-        uint32_t ob = run_bytes + (excl & 0xFFFFu), orst = run_rst + (excl >> 16);
-        if (keep | rmask) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (keep & (1u << j)) {
-                    dst[ob ^ 3u] = (uint8_t)((wv[j >> 2] >> (8 * (j & 3))) & 255u);
-                    ob++;
-                } else if (rmask & (1u << j)) {
-                    if (orst < nrmax) rpos[orst] = ob * 8u;
-                    orst++;
-                }
-            }
-        }
-        const uint32_t tot = s_tile_total;
-        run_bytes += tot & 0xFFFFu;
-        run_rst += tot >> 16;
-        __syncthreads();
-        if (tpos != 0xFFFFFFFFu) break;
     }
-    if (tid == 0) {
-        stream_bits[blockIdx.x] = run_bytes * 8u;
-        n_rst[blockIdx.x] = run_rst < nrmax ? run_rst : nrmax;
+    // the tile that ends the scan (or the page's last tile) publishes the totals
+    if (threadIdx.x == 0 && (tpos != 0xFFFFFFFFu || my_tile + 1 == pg.n_tiles)) {
+        const uint32_t bytes = base_bytes + (total & 0xFFFFu), nr = base_rst + (total >> 16);
+        stream_bits[page] = bytes * 8u;
+        n_rst[page] = nr < nrmax ? nr : nrmax;
     }
 }
 
@@ -199,7 +283,7 @@ __global__ void __launch_bounds__(kJdChunk) jpegd_entropy_kernel(const JdPage *_
                                                                  unsigned long long *chain, int32_t *chain_base,
                                                                  uint32_t *ticket, int16_t *__restrict__ coef,
                                                                  int16_t *__restrict__ dcdiff, int32_t nblk_total,
-                                                                 int32_t *__restrict__ status) {
+                                                                 uint32_t dc_stride, int32_t *__restrict__ status) {
     __shared__ JdHuff s_tab[JD_MAX_TABLES];
     __shared__ JdPageHdr s_hdr;
     __shared__ uint8_t s_zz[64];
@@ -245,12 +329,12 @@ __global__ void __launch_bounds__(kJdChunk) jpegd_entropy_kernel(const JdPage *_
     const uint32_t sub = chunk * kJdChunk + t;
     const uint32_t end_bit = (sub + 1) * kJdSubBits;
     int16_t *pcoef = coef + (size_t)page * nblk_total * 64;
-    int16_t *pdc = dcdiff + (size_t)page * nblk_total;
+    int16_t *pdc = dcdiff + (size_t)page * dc_stride;
 
     // round 0: guessed entry (exact for the first sub-sequence of the page)
     JdState used = {sub * (uint32_t)kJdSubBits, 0u};
     {
-        JdSubResult r = jd_decode_sub<false>(s_hdr, s_tab, s_zz, words, total_bits, prst, nr, used, end_bit, 0,
+        JdSubResult r = jd_decode_sub<false>(s_hdr, s_tab, s_zz, words, kJdSwl, total_bits, prst, nr, used, end_bit, 0,
                                              nblk_total, nullptr, nullptr);
         s_E[0][t] = r.exit;
         s_N[t] = r.nblocks;
@@ -268,7 +352,7 @@ __global__ void __launch_bounds__(kJdChunk) jpegd_entropy_kernel(const JdPage *_
                 JdState en = s_E[cur][t - 1];
                 if (!jd_same(en, used)) {
                     used = en;
-                    JdSubResult r = jd_decode_sub<false>(s_hdr, s_tab, s_zz, words, total_bits, prst, nr, en, end_bit, 0,
+                    JdSubResult r = jd_decode_sub<false>(s_hdr, s_tab, s_zz, words, kJdSwl, total_bits, prst, nr, en, end_bit, 0,
                                                          nblk_total, nullptr, nullptr);
                     s_N[t] = r.nblocks;
                     s_B[t] = r.abs_base;
@@ -342,7 +426,7 @@ __global__ void __launch_bounds__(kJdChunk) jpegd_entropy_kernel(const JdPage *_
             int flags = 0;  // bit 0: thread 0's exit state changed, bit 1: thread 0 decoded again (its block count may differ)
             if (t == 0 && !jd_same(x, used)) {
                 used = x;
-                JdSubResult r = jd_decode_sub<false>(s_hdr, s_tab, s_zz, words, total_bits, prst, nr, x, end_bit, 0,
+                JdSubResult r = jd_decode_sub<false>(s_hdr, s_tab, s_zz, words, kJdSwl, total_bits, prst, nr, x, end_bit, 0,
                                                      nblk_total, nullptr, nullptr);
                 s_N[0] = r.nblocks;
                 s_B[0] = r.abs_base;
@@ -380,7 +464,7 @@ __global__ void __launch_bounds__(kJdChunk) jpegd_entropy_kernel(const JdPage *_
     {
         JdState e = t == 0 ? used : s_E[cur][t - 1];
         int32_t blk0 = my_excl.has_abs ? my_excl.val : base_in + my_excl.val;
-        jd_decode_sub<true>(s_hdr, s_tab, s_zz, words, total_bits, prst, nr, e, end_bit, blk0, nblk_total, pcoef, pdc);
+        jd_decode_sub<true>(s_hdr, s_tab, s_zz, words, kJdSwl, total_bits, prst, nr, e, end_bit, blk0, nblk_total, pcoef, pdc);
     }
     if (t == 0 && chunk + 1 == s_hdr.n_cta) {
         int32_t total = chunk_total.has_abs ? chunk_total.val : base_in + chunk_total.val;
@@ -389,63 +473,82 @@ __global__ void __launch_bounds__(kJdChunk) jpegd_entropy_kernel(const JdPage *_
 }
 
 // ---- 3. DC prediction ----------------------------------------------------------------------------------------
-// grid (ncomp, pages).  Element e of component c = block (e / cnt_c) * bpm + off_c + e % cnt_c; the running sum
-// restarts at every MCU whose index is a multiple of the restart interval.
+// grid (ncomp, pages).  Component c's differences are contiguous (dc_off[c], MCU-major, cnt_c blocks per MCU);
+// the running sum restarts at every MCU whose index is a multiple of the restart interval.  8 elements per
+// thread and step (one 128-bit load), CTA-wide segmented scan, carry from step to step.
 __global__ void __launch_bounds__(1024) jpegd_dc_kernel(const JdPage *__restrict__ pages, int16_t *__restrict__ dc,
-                                                       int32_t nblk_total) {
+                                                       uint32_t dc_stride) {
     const JdPageHdr &pg = pages[blockIdx.y].h;
     const int c = blockIdx.x;
-    const int cnt = c == 0 ? (pg.ncomp == 1 ? 1 : pg.hs * pg.vs) : 1;
-    const int off = c == 0 ? 0 : (pg.hs * pg.vs + c - 1);
-    const int bpm = pg.bpm, ri = (int)pg.restart_interval;
-    const int nmcu = pg.mcux * pg.mcuy;
-    int16_t *d = dc + (size_t)blockIdx.y * nblk_total;
+    const uint32_t cnt = c == 0 ? (pg.ncomp == 1 ? 1u : (uint32_t)pg.hs * pg.vs) : 1u;
+    const uint32_t n = (uint32_t)pg.mcux * pg.mcuy * cnt;
+    const uint32_t seg = pg.restart_interval ? pg.restart_interval * cnt : 0xFFFFFFFFu;  // elements per restart interval
+    int16_t *d = dc + (size_t)blockIdx.y * dc_stride + pg.dc_off[c];
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int per = (nmcu + 1023) / 1024;  // MCUs per thread
-    const int m0 = min(t * per, nmcu), m1 = min(m0 + per, nmcu);
-    int sum = 0, reset = 0;
-    for (int m = m0; m < m1; m++) {
-        if (ri && m % ri == 0) sum = 0, reset = 1;
-        for (int j = 0; j < cnt; j++) sum += d[(size_t)m * bpm + off + j];
-    }
-    // segmented exclusive scan over threads
-    __shared__ int s_v[32], s_f[32];
-    int v = sum, f = reset;
-#pragma unroll
-    for (int k = 1; k < 32; k <<= 1) {
-        int pv = __shfl_up_sync(0xffffffffu, v, k), pf = __shfl_up_sync(0xffffffffu, f, k);
-        if (lane >= k) {
-            if (!f) v += pv;
-            f |= pf;
-        }
-    }
-    if (lane == 31) s_v[wid] = v, s_f[wid] = f;
+    __shared__ int s_v[32], s_f[32], s_carry;
+    if (t == 0) s_carry = 0;
     __syncthreads();
-    if (wid == 0) {
-        int wv = s_v[lane], wf = s_f[lane];
+    for (uint32_t base = 0; base < n; base += 8192) {
+        const uint32_t e0 = base + t * 8;
+        int x[8];
+        int f = 0, v = 0;
+        if (e0 < n) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(d + e0);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int k = 1; k < 32; k <<= 1) {
-            int pv = __shfl_up_sync(0xffffffffu, wv, k), pf = __shfl_up_sync(0xffffffffu, wf, k);
-            if (lane >= k) {
-                if (!wf) wv += pv;
-                wf |= pf;
+            for (int j = 0; j < 8; j++) {
+                int val = (int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+                if (e0 + j >= n) val = 0;
+                if ((e0 + j) % seg == 0) v = 0, f = 1;
+                v += val;
+                x[j] = v;   // running sum inside the thread (relative to its start or the last reset)
             }
         }
-        s_v[lane] = wv, s_f[lane] = wf;
-    }
-    __syncthreads();
-    // exclusive prefix for this thread = (inclusive of lane-1 within the warp) combined with the warps before
-    int ev = __shfl_up_sync(0xffffffffu, v, 1), ef = __shfl_up_sync(0xffffffffu, f, 1);
-    if (lane == 0) ev = 0, ef = 0;
-    if (wid > 0 && !ef) ev += s_v[wid - 1];
-    int pred = ev;
-    for (int m = m0; m < m1; m++) {
-        if (ri && m % ri == 0) pred = 0;
-        for (int j = 0; j < cnt; j++) {
-            size_t i = (size_t)m * bpm + off + j;
-            pred += d[i];
-            d[i] = (int16_t)pred;
+        // segmented inclusive scan of (f, v) over the CTA
+        int sv = v, sf = f;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            int pv = __shfl_up_sync(0xffffffffu, sv, k), pf = __shfl_up_sync(0xffffffffu, sf, k);
+            if (lane >= k) {
+                if (!sf) sv += pv;
+                sf |= pf;
+            }
         }
+        if (lane == 31) s_v[wid] = sv, s_f[wid] = sf;
+        __syncthreads();
+        const int carry = s_carry;
+        if (wid == 0) {
+            int wv = s_v[lane], wf = s_f[lane];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                int pv = __shfl_up_sync(0xffffffffu, wv, k), pf = __shfl_up_sync(0xffffffffu, wf, k);
+                if (lane >= k) {
+                    if (!wf) wv += pv;
+                    wf |= pf;
+                }
+            }
+            s_v[lane] = wv, s_f[lane] = wf;
+        }
+        __syncthreads();
+        // exclusive prefix of this thread: lanes before it in the warp, warps before it, the carry of earlier steps
+        int ev = __shfl_up_sync(0xffffffffu, sv, 1), ef = __shfl_up_sync(0xffffffffu, sf, 1);
+        if (lane == 0) ev = 0, ef = 0;
+        if (wid > 0 && !ef) ev += s_v[wid - 1], ef |= s_f[wid - 1];
+        if (!ef) ev += carry;
+        if (e0 < n) {
+            uint32_t o[4] = {0, 0, 0, 0};
+            bool past_reset = false;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if ((e0 + j) % seg == 0) past_reset = true;
+                const int val = past_reset ? x[j] : x[j] + ev;
+                o[j >> 1] |= ((uint32_t)val & 0xFFFFu) << (16 * (j & 1));
+            }
+            *reinterpret_cast<uint4 *>(d + e0) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+        if (t == 1023) s_carry = s_f[31] ? s_v[31] : s_v[31] + carry;
+        __syncthreads();
     }
 }
 
@@ -454,7 +557,7 @@ __global__ void __launch_bounds__(1024) jpegd_dc_kernel(const JdPage *__restrict
 __global__ void __launch_bounds__(128) jpegd_idct_kernel(const JdPage *__restrict__ pages,
                                                          const int16_t *__restrict__ coef,
                                                          const int16_t *__restrict__ dc, uint8_t *__restrict__ planes,
-                                                         int32_t nblk_total) {
+                                                         int32_t nblk_total, uint32_t dc_stride) {
     const int page = blockIdx.y;
     const JdPage &gp = pages[page];
     __shared__ uint16_t s_q[3][64];
@@ -473,8 +576,17 @@ __global__ void __launch_bounds__(128) jpegd_idct_kernel(const JdPage *__restric
     else c = 2, idx -= n0 + n1, wb = wb1, plane_off = (size_t)(n0 + n1) * 64;
     by = idx / wb, bx = idx - by * wb;
     int blk;
-    if (c == 0) blk = ((by / vs) * pg.mcux + bx / hs) * pg.bpm + (by % vs) * hs + bx % hs;
-    else blk = (by * pg.mcux + bx) * pg.bpm + hs * vs + c - 1;
+    uint32_t dci;
+    if (c == 0) {
+        const int m = (by / vs) * pg.mcux + bx / hs, j = (by % vs) * hs + bx % hs;
+        blk = m * pg.bpm + j;
+        dci = pg.dc_off[0] + (uint32_t)(m * hs * vs + j);
+    } else {
+        const int m = by * pg.mcux + bx;
+        blk = m * pg.bpm + hs * vs + c - 1;
+        dci = pg.dc_off[c] + (uint32_t)m;
+    }
+    const int16_t dcv = dc[(size_t)page * dc_stride + dci];
     const uint4 *src = reinterpret_cast<const uint4 *>(coef + ((size_t)page * nblk_total + blk) * 64);
     const uint16_t *q = s_q[c];
     int32_t ws[64];
@@ -487,7 +599,7 @@ __global__ void __launch_bounds__(128) jpegd_idct_kernel(const JdPage *__restric
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 int16_t cv = (int16_t)((wv[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
-                if (r == 0 && j == 0) cv = dc[(size_t)page * nblk_total + blk];
+                if (r == 0 && j == 0) cv = dcv;
                 in[r * 8 + j] = (int32_t)(int16_t)(cv * (int32_t)q[r * 8 + j]);
             }
         }
@@ -631,7 +743,7 @@ LUMINA_API int lumina_jpeg_decode_batch(const uint8_t *h_blob, const int64_t *h_
     const size_t total_bytes = (size_t)(h_offsets[n] - h_offsets[0]);
     LUMINA_REQUIRE(total_bytes < (1ull << 31), "batch blob too large (2 GiB limit)");
     int hs = 1, vs = 1;
-    uint32_t word_off = 0, cta_off = 0, rst_off = 0;
+    uint32_t word_off = 0, cta_off = 0, rst_off = 0, tile_off = 0;
     for (int i = 0; i < n; i++) {
         JdInfo ji;
         const size_t off = (size_t)(h_offsets[i] - h_offsets[0]), len = (size_t)(h_offsets[i + 1] - h_offsets[i]);
@@ -646,7 +758,7 @@ LUMINA_API int lumina_jpeg_decode_batch(const uint8_t *h_blob, const int64_t *h_
         JdPageHdr &ph = hp[i].h;
         ph.scan_off += (uint32_t)off;
         ph.stream_word_off = word_off;
-        word_off += (ph.scan_len + 3) / 4 + 4;
+        word_off += (ph.scan_len + 3) / 4 + 8;
         ph.cta_off = cta_off;
         ph.n_cta = (uint32_t)(((size_t)ph.scan_len * 8 + (size_t)kJdSubBits * kJdChunk - 1) / ((size_t)kJdSubBits * kJdChunk));
         if (ph.n_cta == 0) ph.n_cta = 1;
@@ -655,6 +767,9 @@ LUMINA_API int lumina_jpeg_decode_batch(const uint8_t *h_blob, const int64_t *h_
         const uint32_t nmcu = (uint32_t)ph.mcux * ph.mcuy;
         ph.n_rst_max = ph.restart_interval ? (nmcu - 1) / ph.restart_interval : 0;
         rst_off += ph.n_rst_max;
+        ph.tile_off = tile_off;
+        ph.n_tiles = ((ph.scan_off & 15u) + ph.scan_len + kUnstuffThreads * 16 - 1) / (kUnstuffThreads * 16);
+        tile_off += ph.n_tiles;
     }
     const JdLayout L = jd_layout(n, h, w, channels, hs, vs, total_bytes);
     if (workspace_bytes < L.total)
@@ -667,6 +782,7 @@ LUMINA_API int lumina_jpeg_decode_batch(const uint8_t *h_blob, const int64_t *h_
     uint32_t *d_bits = reinterpret_cast<uint32_t *>(ws + L.stream_bits);
     uint32_t *d_nrst = reinterpret_cast<uint32_t *>(ws + L.n_rst);
     uint32_t *d_rst = reinterpret_cast<uint32_t *>(ws + L.rst);
+    JdTile *d_tiles = reinterpret_cast<JdTile *>(ws + L.tiles);
     unsigned long long *d_chain = reinterpret_cast<unsigned long long *>(ws + L.chain);
     int32_t *d_chain_base = reinterpret_cast<int32_t *>(ws + L.chain_base);
     uint32_t *d_ticket = reinterpret_cast<uint32_t *>(ws + L.ticket);
@@ -683,14 +799,16 @@ LUMINA_API int lumina_jpeg_decode_batch(const uint8_t *h_blob, const int64_t *h_
     LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.chain, 0, L.coef - L.chain, st));
     LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.coef, 0, L.planes - L.coef, st));
 
-    jpegd_unstuff_kernel<<<n, kUnstuffThreads, 0, st>>>(d_blob, d_pages, d_stream, d_bits, d_rst, d_nrst);
-    LUMINA_KERNEL_CHECK("jpegd_unstuff_kernel");
+    jpegd_unstuff_count_kernel<<<tile_off, kUnstuffThreads, 0, st>>>(d_blob, d_pages, n, d_tiles);
+    LUMINA_KERNEL_CHECK("jpegd_unstuff_count_kernel");
+    jpegd_unstuff_scatter_kernel<<<tile_off, kUnstuffThreads, 0, st>>>(d_blob, d_pages, n, d_tiles, d_stream, d_bits, d_rst, d_nrst);
+    LUMINA_KERNEL_CHECK("jpegd_unstuff_scatter_kernel");
     jpegd_entropy_kernel<<<cta_off, kJdChunk, 0, st>>>(d_pages, n, d_stream, d_bits, d_rst, d_nrst, d_chain, d_chain_base,
-                                                      d_ticket, d_coef, d_dc, nblk, d_status);
+                                                      d_ticket, d_coef, d_dc, nblk, (uint32_t)L.dc_stride, d_status);
     LUMINA_KERNEL_CHECK("jpegd_entropy_kernel");
-    jpegd_dc_kernel<<<dim3(channels, n), 1024, 0, st>>>(d_pages, d_dc, nblk);
+    jpegd_dc_kernel<<<dim3(channels, n), 1024, 0, st>>>(d_pages, d_dc, (uint32_t)L.dc_stride);
     LUMINA_KERNEL_CHECK("jpegd_dc_kernel");
-    jpegd_idct_kernel<<<dim3(div_up(nblk, 128), n), 128, 0, st>>>(d_pages, d_coef, d_dc, d_planes, nblk);
+    jpegd_idct_kernel<<<dim3(div_up(nblk, 128), n), 128, 0, st>>>(d_pages, d_coef, d_dc, d_planes, nblk, (uint32_t)L.dc_stride);
     LUMINA_KERNEL_CHECK("jpegd_idct_kernel");
     const long long groups = (long long)n * h * ((w + 15) / 16);
     jpegd_colour_kernel<<<(unsigned)div_up(groups, 256), 256, 0, st>>>(d_pages, d_planes, d_out, n, h, w, channels, nblk);

@@ -239,6 +239,57 @@ class PagePipeline:
             x = ops.warp_affine_cubic(x, mats, apply)
         return x, angles
 
+    # ------------------------------------------------------------------ encoded input (files cross PCIe, not rasters)
+    def run_encoded_stream(self, encoded_batches, profile: bool = False, keep: int = 2):
+        """The e2e path for *files*: ``encoded_batches`` yields ``(blob, offsets)`` -- a (pinned) CPU uint8 tensor
+        holding the baseline-JPEG files of one batch back to back and the int64 offsets [n+1] -- i.e. what
+        ``load_image_bytes`` (image_preprocessing.py:70-75) is handed, batched.  The files are uploaded (1-2 MB
+        per A4 page instead of the 26 MB raster) and decoded in HBM on a side stream (``ops.JpegDecoder``: the
+        raster equals Pillow's), then go through the stream-pipelined chain (``run_device_stream``); the results a
+        caller consumes (deskewed rasters, masks, angles) are copied back to pinned host memory.  Yields
+        ``(out_host, PageBatchResult, h2d_bytes, d2h_bytes)`` per batch, complete in host memory; ``out_host``
+        rotates over ``keep`` slots as in ``run_host_stream``.  A page whose entropy-coded data is corrupt raises
+        ``LuminaError`` (decode such a file on the host, as the reference does)."""
+        dev = self._dev()
+        keep = max(1, int(keep))
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            st = getattr(self._tls, "enc_state", None)
+            if st is None or st["dev"] != dev:
+                st = self._tls.enc_state = {"dev": dev, "stream": torch.cuda.Stream(dev, priority=-1),
+                                            "dec": ops.JpegDecoder(), "out": []}
+            dec_stream, dec = st["stream"], st["dec"]
+            meta = []
+
+            def decoded():
+                for blob, offs in encoded_batches:
+                    with torch.cuda.stream(dec_stream):
+                        pages, status = dec.decode(blob, offs, dev)
+                        ev = torch.cuda.Event()
+                        ev.record(dec_stream)
+                    main.wait_event(ev)            # run_device_stream's streams wait for `main`
+                    pages.record_stream(main)
+                    status.record_stream(main)
+                    meta.append((status, int(offs[-1] - offs[0])))
+                    yield pages
+
+            outs = st["out"]
+            for i, res in enumerate(self.run_device_stream(decoded(), profile=profile)):
+                status, nbytes = meta.pop(0)
+                if len(outs) != keep or outs[0]["pages"].shape != res.pages.shape or outs[0]["binary"].shape != res.binary.shape:
+                    outs[:] = [dict(self._new_out(res), status=torch.empty(status.shape, dtype=torch.int32, pin_memory=True))
+                               for _ in range(keep)]
+                out_host = outs[i % keep]
+                out_host["pages"].copy_(res.pages, non_blocking=True)
+                out_host["binary"].copy_(res.binary, non_blocking=True)
+                out_host["status"].copy_(status, non_blocking=True)
+                main.synchronize()
+                bad = np.nonzero(out_host["status"].numpy())[0]
+                if bad.size:
+                    raise ops._abi.LuminaError(f"corrupt entropy-coded data in pages {bad.tolist()} of batch {i}")
+                out_host["angles"] = res.angles
+                yield out_host, res, nbytes, res.pages.numel() + res.binary.numel() + res.angles.nbytes + 4 * status.numel()
+
     # ------------------------------------------------------------------ host input (the e2e path)
     @staticmethod
     def _new_out(res: PageBatchResult) -> Dict[str, torch.Tensor]:

@@ -119,11 +119,23 @@ def det_resize_normalize(img: np.ndarray, limit: int = 960):
     return x.transpose(2, 0, 1), (h, w, rh / h, rw / w)
 
 
-def page_chain(page: np.ndarray, max_dim: int = 960, enhance: bool = False):
+def load_image_bytes(image_bytes: bytes) -> Image.Image:
+    """image_preprocessing.py:70-75."""
+    import io
+
+    image = Image.open(io.BytesIO(image_bytes))
+    if image.mode not in ('RGB', 'L'):
+        image = image.convert('RGB')
+    return image
+
+
+def page_chain(page, max_dim: int = 960, enhance: bool = False):
     """The bench workload (BASELINE.json configs[1]) on one page, reference calls only:
-    resize -> deskew -> [contrast 1.2, sharpness 1.1] -> gray -> adaptive binarize -> det normalize.
+    [load_image_bytes when `page` is an encoded file] -> resize -> deskew -> [contrast 1.2, sharpness 1.1] ->
+    gray -> adaptive binarize -> det normalize.
     Returns (deskewed RGB u8, angle, gray u8, binary u8, normalized CHW f32)."""
-    img = resize_if_needed(Image.fromarray(page), max_dim)
+    img = load_image_bytes(page) if isinstance(page, (bytes, bytearray)) else Image.fromarray(page)
+    img = resize_if_needed(img, max_dim)
     img, angle = deskew(img)
     if enhance:
         img = enhance_sharpness(enhance_contrast(img, 1.2), 1.1)

@@ -31,8 +31,11 @@ int jdh_decode(const uint8_t *f, size_t len, int sub_bits, uint8_t *out, int *wh
         else break;
     }
     uint32_t total_bits = (uint32_t)bytes.size() * 8;
-    std::vector<uint32_t> words(bytes.size() / 4 + 4, 0);
-    for (size_t i = 0; i < bytes.size(); i++) words[i >> 2] |= (uint32_t)bytes[i] << (24 - 8 * (i & 3));
+    uint32_t swl = 0;
+    while ((32u << swl) < (uint32_t)sub_bits) swl++;
+    const size_t chunk_words = (size_t)1 << (swl + JD_CHUNK_LOG2);
+    std::vector<uint32_t> words(((bytes.size() / 4 + 4) / chunk_words + 1) * chunk_words, 0);
+    for (size_t i = 0; i < bytes.size(); i++) words[jd_word_index((uint32_t)(i >> 2), swl)] |= (uint32_t)bytes[i] << (24 - 8 * (i & 3));
     int n_rst = (int)rst.size();
     if (!pg->h.restart_interval) n_rst = 0;
     // ---- sync rounds ----
@@ -45,7 +48,7 @@ int jdh_decode(const uint8_t *f, size_t len, int sub_bits, uint8_t *out, int *wh
     int nblk_total = pg->h.mcux * pg->h.mcuy * pg->h.bpm;
     for (int i = 0; i < n_sub; i++) {
         JdState e = {(uint32_t)i * S, 0};
-        JdSubResult r = jd_decode_sub<false>(pg->h, pg->tab, kJdZigzag, words.data(), total_bits, rst.data(), n_rst, e,
+        JdSubResult r = jd_decode_sub<false>(pg->h, pg->tab, kJdZigzag, words.data(), swl, total_bits, rst.data(), n_rst, e,
                                              (i + 1) * S, 0, nblk_total, nullptr, nullptr);
         E[i] = r.exit; N[i] = r.nblocks; B[i] = r.abs_base;
     }
@@ -59,7 +62,7 @@ int jdh_decode(const uint8_t *f, size_t len, int sub_bits, uint8_t *out, int *wh
             JdState e = E[i - 1];
             if (rounds == 1 && e.p == (uint32_t)i * S && e.sk == 0) continue;
             redec++;
-            JdSubResult r = jd_decode_sub<false>(pg->h, pg->tab, kJdZigzag, words.data(), total_bits, rst.data(), n_rst, e,
+            JdSubResult r = jd_decode_sub<false>(pg->h, pg->tab, kJdZigzag, words.data(), swl, total_bits, rst.data(), n_rst, e,
                                                  (i + 1) * S, 0, nblk_total, nullptr, nullptr);
             N[i] = r.nblocks; B[i] = r.abs_base;
             if (r.exit.p != E[i].p || r.exit.sk != E[i].sk) { E2[i] = r.exit; chg2[i] = 1; any = true; }
@@ -74,11 +77,11 @@ int jdh_decode(const uint8_t *f, size_t len, int sub_bits, uint8_t *out, int *wh
     int32_t run = 0;
     for (int i = 0; i < n_sub; i++) { base[i] = run; run = B[i] >= 0 ? B[i] + N[i] : run + N[i]; }
     // ---- write pass ----
-    std::vector<int16_t> coef((size_t)nblk_total * 64, 0), dc(nblk_total, 0);
+    std::vector<int16_t> coef((size_t)nblk_total * 64, 0), dc(pg->h.dc_off[pg->h.ncomp], 0);
     long long verified = 0;
     for (int i = 0; i < n_sub; i++) {
         JdState e = i ? E[i - 1] : JdState{0, 0};
-        JdSubResult r = jd_decode_sub<true>(pg->h, pg->tab, kJdZigzag, words.data(), total_bits, rst.data(), n_rst, e,
+        JdSubResult r = jd_decode_sub<true>(pg->h, pg->tab, kJdZigzag, words.data(), swl, total_bits, rst.data(), n_rst, e,
                                             (i + 1) * S, base[i], nblk_total, coef.data(), dc.data());
         verified += (r.exit.p == E[i].p && r.exit.sk == E[i].sk);
     }
@@ -91,8 +94,9 @@ int jdh_decode(const uint8_t *f, size_t len, int sub_bits, uint8_t *out, int *wh
             if (pg->h.restart_interval && m % pg->h.restart_interval == 0) pred[0] = pred[1] = pred[2] = 0;
             for (int sl = 0; sl < pg->h.bpm; sl++) {
                 int c = pg->h.slot_comp[sl];
-                pred[c] += dc[m * pg->h.bpm + sl];
-                dc[m * pg->h.bpm + sl] = (int16_t)pred[c];
+                int16_t &d = dc[pg->h.slot_dcbase[sl] + (size_t)m * pg->h.slot_cnt[sl]];
+                pred[c] += d;
+                d = (int16_t)pred[c];
             }
         }
     }
@@ -113,7 +117,8 @@ int jdh_decode(const uint8_t *f, size_t len, int sub_bits, uint8_t *out, int *wh
             int bx = (m % pg->h.mcux) * (c == 0 ? hs : 1) + (c == 0 ? sub % hs : 0);
             int by = (m / pg->h.mcux) * (c == 0 ? vs : 1) + (c == 0 ? sub / hs : 0);
             int32_t ws[64], in[64];
-            for (int i = 0; i < 64; i++) in[i] = (int16_t)((i ? coef[(size_t)blk * 64 + i] : dc[blk]) * pg->qt[c][i]);
+            for (int i = 0; i < 64; i++)
+                in[i] = (int16_t)((i ? coef[(size_t)blk * 64 + i] : dc[pg->h.slot_dcbase[sl] + (size_t)m * pg->h.slot_cnt[sl]]) * pg->qt[c][i]);
             for (int col = 0; col < 8; col++) {
                 int32_t o[8];
                 jd_idct_1d(in[col], in[8 + col], in[16 + col], in[24 + col], in[32 + col], in[40 + col], in[48 + col],

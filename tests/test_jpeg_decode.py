@@ -100,15 +100,19 @@ def test_oracle_decoder_reports_files_outside_the_subset(oracle):
         oracle.jpeg_decode(b"\xff\xd8\xff\xd9")
 
 
-@pytest.fixture(scope="module")
-def J():
+def _build_host(name, *flags):
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
-    so = os.path.join(HERE, "_build", "libjpegd_host.so")
+    so = os.path.join(HERE, "_build", name)
     src = os.path.join(HERE, "jpegd_host.cpp")
     hdr = os.path.join(HERE, "..", "ocr-system_b200", "csrc", "jpegd_core.h")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, src])
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", *flags, "-o", so, src])
     return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def J():
+    return _build_host("libjpegd_host.so")
 
 
 def _host_decode(J, data, sub_bits):
@@ -134,6 +138,17 @@ def test_parallel_schedule_on_the_host_equals_pillow(J):
             assert st[3] == st[1], (key, sub_bits, st)     # every exit state confirmed by the write pass
             n += 1
     assert n > 2000
+
+
+def test_long_codes_without_second_level_tables_walk_the_ladder():
+    """JD_MAX_SUB = 1: only one 10-bit prefix gets a second-level table, every other long code takes the maxcode
+    ladder (the fallback for unusual optimised tables)."""
+    J1 = _build_host("libjpegd_host_sub1.so", "-DJD_MAX_SUB=1")
+    rng = np.random.default_rng(5)
+    for q, opt in ((100, False), (97, True), (60, False)):
+        d = _save(_img(rng, 120, 168, "noise"), quality=q, optimize=opt, subsampling=2)
+        got, st = _host_decode(J1, d, 1024)
+        assert np.array_equal(got, _pil(d)) and st[3] == st[1]
 
 
 def test_parallel_schedule_on_a_full_a4_page(J, oracle):
@@ -209,3 +224,37 @@ def test_gpu_decoder_flags_truncated_files_and_rejects_other_formats(cuda, oracl
         ops.jpeg_decode([b.getvalue()])
     with pytest.raises(_abi.LuminaError):          # mixed geometries in one batch
         ops.jpeg_decode([good, _save(oracle.synth_page(300, 400, 1), quality=75)])
+
+
+@pytest.mark.gpu
+def test_run_encoded_stream_every_batch_equals_the_chain_on_pillow_rasters(cuda, oracle):
+    """The e2e path for files: what comes back for batch i is the chain applied to Pillow's decode of batch i's
+    files (and a consumer may hold batch i-1 while batch i is produced)."""
+    import torch
+    from ocr_system_b200 import ops
+    from ocr_system_b200.pipeline import PagePipeline
+
+    h, w, nb, bs = 1000, 720, 4, 3
+    batches, refs = [], []
+    packer = ops.JpegDecoder()
+    for b in range(nb):
+        files = [_save(oracle.synth_page(h, w, 10 * b + i), quality=75) for i in range(bs)]
+        blob, offs = packer.pack(files)
+        batches.append((blob.clone().pin_memory(), offs))
+        refs.append(np.stack([_pil(f) for f in files]))
+    pipe = PagePipeline(max_dimension=480, device=cuda)
+    held = None
+    for i, (out, res, h2d, d2h) in enumerate(pipe.run_encoded_stream(batches)):
+        want = pipe.run_device(torch.from_numpy(refs[i]).to(cuda))
+        torch.cuda.synchronize()
+        assert h2d == int(batches[i][1][-1])
+        assert np.array_equal(out["pages"].numpy(), want.pages.cpu().numpy()), i
+        assert np.array_equal(out["binary"].numpy(), want.binary.cpu().numpy()), i
+        assert np.array_equal(out["angles"], want.angles), i
+        # and against the CPU oracle for the first page of the batch
+        tw, th = oracle.target_size(w, h, 480)
+        ref_img, ref_angle, _ = oracle.deskew(oracle.resize_lanczos(refs[i][0], tw, th))
+        assert out["angles"][0] == ref_angle and np.array_equal(out["pages"].numpy()[0], ref_img)
+        if held is not None:   # keep=2: the previous batch's host results are still intact
+            assert np.array_equal(held[0]["pages"].numpy(), held[1])
+        held = (out, out["pages"].numpy().copy())
