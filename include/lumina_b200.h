@@ -165,6 +165,12 @@ int lumina_db_postprocess(const float *d_pred, int n, int h, int w, float thresh
                           double unclip_ratio, int max_candidates, int min_size, const int32_t *h_src_hw,
                           int32_t *d_boxes, float *d_scores, int32_t *d_counts, void *d_workspace,
                           size_t workspace_bytes, void *stream);
+/* flags bit 0: use_dilation=True (the mask is dilated by upstream's 2x2 kernel before the contours are taken;
+ * scores still come from the undilated probabilities). */
+int lumina_db_postprocess_ex(const float *d_pred, int n, int h, int w, float thresh, double box_thresh,
+                             double unclip_ratio, int max_candidates, int min_size, int flags,
+                             const int32_t *h_src_hw, int32_t *d_boxes, float *d_scores, int32_t *d_counts,
+                             void *d_workspace, size_t workspace_bytes, void *stream);
 /* Stage outputs for parity tests: binary mask {0,1} + 8-connected labels
  * (label = min raster index of the component + 1, 0 = background).
  * workspace >= align256(n*h*w) + 4*n*h*w bytes. */

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "lumina_ctc_greedy": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "lumina_db_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "lumina_db_postprocess": (_I, [_P, _I, _I, _I, _F, _D, _D, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "lumina_db_postprocess_ex": (_I, [_P, _I, _I, _I, _F, _D, _D, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "lumina_db_mask_ccl": (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "lumina_reading_order": (_I, [_P, _P, _P, _I, _I, _D, _I, _P, _P, _P, _P, _P, _P]),
     "lumina_jpeg_workspace_bytes": (_Z, [_I, _I, _I]),

@@ -61,6 +61,27 @@ __global__ void __launch_bounds__(256) db_mask_kernel(const float *__restrict__ 
     }
 }
 
+// use_dilation=True (upstream: cv2.dilate(mask, [[1,1],[1,1]]), anchor (1,1), pixels outside the map ignored):
+// mask(x, y) = OR of (pred > thresh) over x-1..x, y-1..y.  4 pixels per thread.
+__global__ void __launch_bounds__(256) db_mask_dilate_kernel(const float *__restrict__ pred, uint8_t *__restrict__ mask, int n,
+                                                             int h, int w, float thresh) {
+    const int groups = (w + 3) >> 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n * h * groups) return;
+    const int g = (int)(gid % groups);
+    const long long row = gid / groups;
+    const int y = (int)(row % h);
+    const float *cur = pred + (size_t)row * w, *up = cur - w;
+    const int x0 = g * 4;
+    bool left = false;   // column x0 - 1 (this row or the one above)
+    if (x0 > 0) left = cur[x0 - 1] > thresh || (y > 0 && up[x0 - 1] > thresh);
+    for (int i = 0; i < 4 && x0 + i < w; i++) {
+        const bool here = cur[x0 + i] > thresh || (y > 0 && up[x0 + i] > thresh);
+        mask[(size_t)row * w + x0 + i] = (left || here) ? 1 : 0;
+        left = here;
+    }
+}
+
 // ---- 2. two-class union-find labelling ----------------------------------------------
 __global__ void __launch_bounds__(256) db_ccl_init_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h,
                                                           int w, long long nseg_total) {
@@ -273,10 +294,10 @@ struct DbParams {
 
 // merged coverage intervals of one mask row.  Deliberately out of line: inlined into the candidate
 // kernel nvcc 12.9 produced wrong interval bounds for x-major edges (caught by the parity test).
-__device__ __noinline__ int db_row_intervals(const DbgPt *q4, int ry, int *lo, int *hi) {
+__device__ __noinline__ int db_row_intervals(const DbgPt *q4, int ry, int mw, int mh, int *lo, int *hi) {
     DbgPt q[4] = {q4[0], q4[1], q4[2], q4[3]};
     int l[5] = {0, 0, 0, 0, 0}, h[5] = {-1, -1, -1, -1, -1};
-    int c = dbg_row_cover(q, ry, l, h);
+    int c = dbg_row_cover(q, ry, mw, mh, l, h);
     c = dbg_merge(l, h, c);
     for (int i = 0; i < 5; i++) { lo[i] = l[i]; hi[i] = h[i]; }
     return c;
@@ -411,7 +432,7 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_cand_score_kernel(const DbPa
     int cnt = 0;
     for (int ry = 0; ry < mh; ry++) {
         int lo[5], hi[5];
-        const int c = db_row_intervals(q, ry, lo, hi);
+        const int c = db_row_intervals(q, ry, mw, mh, lo, hi);
         const float *prow = P + (size_t)(ymin + ry) * p.w + xmin;
         for (int i = 0; i < c; i++) {
             const int a = max(lo[i], 0), b = min(hi[i], mw - 1);
@@ -533,10 +554,17 @@ __global__ void __launch_bounds__(256) db_export_labels_kernel(const uint8_t *__
     labels_out[g] = fg ? labels[g] + 1 : 0;
 }
 
-static int db_label(const float *d_pred, int n, int h, int w, float thresh, uint8_t *mask, int *labels, cudaStream_t st) {
+static int db_label(const float *d_pred, int n, int h, int w, float thresh, uint8_t *mask, int *labels, cudaStream_t st,
+                    bool dilate = false) {
     const size_t px = (size_t)n * h * w;
-    db_mask_kernel<<<(unsigned)((px / 4 + 256) / 256), 256, 0, st>>>(d_pred, mask, px, thresh);
-    LUMINA_KERNEL_CHECK("db_mask_kernel");
+    if (dilate) {
+        const long long groups = (long long)n * h * ((w + 3) / 4);
+        db_mask_dilate_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(d_pred, mask, n, h, w, thresh);
+        LUMINA_KERNEL_CHECK("db_mask_dilate_kernel");
+    } else {
+        db_mask_kernel<<<(unsigned)((px / 4 + 256) / 256), 256, 0, st>>>(d_pred, mask, px, thresh);
+        LUMINA_KERNEL_CHECK("db_mask_kernel");
+    }
     const long long nseg = (long long)n * h * ((w + 31) / 32);
     db_ccl_init_kernel<<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, st>>>(mask, labels, h, w, nseg);
     LUMINA_KERNEL_CHECK("db_ccl_init_kernel");
@@ -561,6 +589,15 @@ LUMINA_API int lumina_db_postprocess(const float *d_pred, int n, int h, int w, f
                                      double unclip_ratio, int max_candidates, int min_size, const int32_t *h_src_hw,
                                      int32_t *d_boxes, float *d_scores, int32_t *d_counts, void *d_workspace,
                                      size_t workspace_bytes, void *stream) {
+    return lumina_db_postprocess_ex(d_pred, n, h, w, thresh, box_thresh, unclip_ratio, max_candidates, min_size, 0, h_src_hw,
+                                    d_boxes, d_scores, d_counts, d_workspace, workspace_bytes, stream);
+}
+
+LUMINA_API int lumina_db_postprocess_ex(const float *d_pred, int n, int h, int w, float thresh, double box_thresh,
+                                        double unclip_ratio, int max_candidates, int min_size, int flags,
+                                        const int32_t *h_src_hw, int32_t *d_boxes, float *d_scores, int32_t *d_counts,
+                                        void *d_workspace, size_t workspace_bytes, void *stream) {
+    LUMINA_REQUIRE((flags & ~1) == 0, "unknown flag");
     LUMINA_REQUIRE(d_pred && h_src_hw && d_boxes && d_scores && d_counts && d_workspace, "null pointer");
     LUMINA_REQUIRE(n > 0 && h > 0 && w > 0 && max_candidates > 0, "empty batch");
     LUMINA_REQUIRE((long long)h * w < (1LL << 30), "map too large");
@@ -575,7 +612,7 @@ LUMINA_API int lumina_db_postprocess(const float *d_pred, int n, int h, int w, f
     int *src_hw_dev = (int *)(ws + L.total);
     LUMINA_CUDA_TRY(cudaMemcpyAsync(src_hw_dev, h_src_hw, (size_t)n * 2 * 4, cudaMemcpyHostToDevice, st));
     LUMINA_CUDA_TRY(cudaMemsetAsync(ws + L.poolctr_off, 0, (size_t)n * 4, st));
-    int rc = db_label(d_pred, n, h, w, thresh, mask, labels, st);
+    int rc = db_label(d_pred, n, h, w, thresh, mask, labels, st, (flags & 1) != 0);
     if (rc != LUMINA_OK) return rc;
     LUMINA_REQUIRE(n <= 65535, "batch too large for grid");
     db_candidates_kernel<<<n, 1024, 0, st>>>(mask, labels, (int *)(ws + L.cand_off), (int *)(ws + L.bbox_off),

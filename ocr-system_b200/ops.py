@@ -476,9 +476,10 @@ def db_mask_ccl(pred: torch.Tensor, thresh: float = 0.3):
 
 @_on_tensor_device
 def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: float = 0.7,
-                   unclip_ratio: float = 2.0, max_candidates: int = 1000, min_size: int = 3):
+                   unclip_ratio: float = 2.0, max_candidates: int = 1000, min_size: int = 3, use_dilation: bool = False):
     """DBPostProcess core on [N,H,W] float32 maps -> (boxes [N,max_candidates,4,2] int32,
-    scores [N,max_candidates] f32, counts [N] int32), all on the device."""
+    scores [N,max_candidates] f32, counts [N] int32), all on the device.  ``use_dilation``: upstream's 2x2 mask
+    dilation before the contours are taken."""
     if not pred.is_cuda or pred.dtype != torch.float32 or pred.dim() != 3:
         raise TypeError("db_postprocess expects a CUDA float32 [N,H,W] tensor")
     p = pred.contiguous()
@@ -489,9 +490,10 @@ def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: 
     counts = torch.empty(n, dtype=torch.int32, device=p.device)
     wsb = int(_L().lumina_db_workspace_bytes(n, h, w, int(max_candidates)))
     ws = _ws(wsb, p.device)
-    _chk(_L().lumina_db_postprocess(_ptr(p), n, h, w, float(np.float32(thresh)), float(box_thresh), float(unclip_ratio),
-                                    int(max_candidates), int(min_size), hw.ctypes.data_as(C.c_void_p), _ptr(boxes),
-                                    _ptr(scores), _ptr(counts), _ptr(ws), wsb, _stream()))
+    _chk(_L().lumina_db_postprocess_ex(_ptr(p), n, h, w, float(np.float32(thresh)), float(box_thresh), float(unclip_ratio),
+                                       int(max_candidates), int(min_size), 1 if use_dilation else 0,
+                                       hw.ctypes.data_as(C.c_void_p), _ptr(boxes), _ptr(scores), _ptr(counts), _ptr(ws), wsb,
+                                       _stream()))
     return boxes, scores, counts
 
 

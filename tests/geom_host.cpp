@@ -20,6 +20,13 @@ int geom_min_area_rect_ex(const int *pts, int n, int start_mode, int sx, int sy,
     out5[0] = r.cx; out5[1] = r.cy; out5[2] = r.w; out5[3] = r.h; out5[4] = r.angle;
     return hn;
 }
+// calipers on a hull given as-is (cv::convexHull's vertex order): isolates dbg_min_area_rect from the hull construction
+void geom_min_area_rect_hull(const int *hull_pts, int n, float *out5) {
+    std::vector<DbgPt> h(n);
+    for (int i = 0; i < n; i++) { h[i].x = hull_pts[2 * i]; h[i].y = hull_pts[2 * i + 1]; }
+    DbgRect r = dbg_min_area_rect(h.data(), n);
+    out5[0] = r.cx; out5[1] = r.cy; out5[2] = r.w; out5[3] = r.h; out5[4] = r.angle;
+}
 int geom_min_area_rect(const int *pts, int n, float *out5) {
     std::vector<DbgPt> p(n), hull(n + 2);
     for (int i = 0; i < n; i++) { p[i].x = pts[2 * i]; p[i].y = pts[2 * i + 1]; }
@@ -28,6 +35,12 @@ int geom_min_area_rect(const int *pts, int n, float *out5) {
     DbgRect r = dbg_min_area_rect(hull.data(), hn);
     out5[0] = r.cx; out5[1] = r.cy; out5[2] = r.w; out5[3] = r.h; out5[4] = r.angle;
     return hn;
+}
+void geom_box_points(const float *rect5, float *out8) {
+    DbgRect r = {rect5[0], rect5[1], rect5[2], rect5[3], rect5[4]};
+    DbgPtF o[4];
+    dbg_box_points(r, o);
+    for (int i = 0; i < 4; i++) { out8[2 * i] = o[i].x; out8[2 * i + 1] = o[i].y; }
 }
 float geom_mini_box(const float *rect5, float *out8) {
     DbgRect r = {rect5[0], rect5[1], rect5[2], rect5[3], rect5[4]};
@@ -42,7 +55,7 @@ void geom_fill_quad(const int *quad8, int h, int w, unsigned char *mask) {
     for (int i = 0; i < 4; i++) { q[i].x = quad8[2 * i]; q[i].y = quad8[2 * i + 1]; }
     for (int y = 0; y < h; y++) {
         int lo[5], hi[5];
-        int c = dbg_row_cover(q, y, lo, hi);
+        int c = dbg_row_cover(q, y, w, h, lo, hi);
         c = dbg_merge(lo, hi, c);
         for (int i = 0; i < c; i++)
             for (int x = (lo[i] < 0 ? 0 : lo[i]); x <= hi[i] && x < w; x++) mask[(size_t)y * w + x] = 1;
@@ -96,7 +109,7 @@ int geom_candidate(const int *pts, int n, int hole, int sx, int sy, const float 
     double sum = 0; long cnt = 0;
     for (int ry = 0; ry < mh; ry++) {
         int lo[5], hi[5];
-        int c = dbg_merge(lo, hi, dbg_row_cover(q, ry, lo, hi));
+        int c = dbg_merge(lo, hi, dbg_row_cover(q, ry, mw, mh, lo, hi));
         for (int i = 0; i < c; i++) {
             int a = lo[i] < 0 ? 0 : lo[i], b = hi[i] > mw - 1 ? mw - 1 : hi[i];
             for (int x = a; x <= b; x++) { sum += pred[(size_t)(yminb + ry) * w + xmin + x]; cnt++; }
