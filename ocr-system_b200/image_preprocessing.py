@@ -455,6 +455,12 @@ class ImagePreprocessor:
                 logger.info(f"Compressed to {len(out[i]) / 1024 / 1024:.2f}MB after resize to {(new_w, new_h)}")
         return out  # type: ignore[return-value]
 
+    def _jpeg_decoder(self) -> "ops.JpegDecoder":
+        d = getattr(self._tls, "jpeg_dec", None)   # workspace + pinned staging are per calling thread
+        if d is None:
+            d = self._tls.jpeg_dec = ops.JpegDecoder()
+        return d
+
     def _jpeg_encoder(self) -> "ops.JpegEncoder":
         enc = getattr(self._tls, "jpeg", None)     # workspace + cached DCT: one per calling thread
         if enc is None:
@@ -519,14 +525,45 @@ class ImagePreprocessor:
         Pages are grouped by (size, mode) -- the pages of one PDF share both -- and every group goes through the
         device chain and the JPEG ladder as one batch; results come back in input order and are the same bytes the
         per-page call returns."""
-        imgs = [self._open(im) for im in images]
+        out: List[Optional[bytes]] = [None] * len(images)
+        # Encoded inputs (bytes / paths): baseline JPEG files are decoded in HBM (ops.JpegDecoder: the raster equals
+        # Pillow's, so the result is the same bytes) -- the file crosses PCIe instead of the raster and no host core
+        # runs libjpeg.  Pillow still parses the header (lazy open: no pixel is decoded) for the EXIF orientation;
+        # tagged images, other formats and JPEG flavours outside the device subset take the host codec below.
+        imgs: List[Optional[Image.Image]] = [None] * len(images)
+        enc_groups = {}
+        for i, src in enumerate(images):
+            data = None
+            if isinstance(src, bytes):
+                data = src
+            elif isinstance(src, (str, Path)) and str(src).lower().endswith((".jpg", ".jpeg")) and Path(src).exists():
+                data = Path(src).read_bytes()
+            info = ops.jpeg_probe(data) if data is not None and data[:2] == b"\xff\xd8" else None
+            if info is not None and Image.open(io.BytesIO(data)).getexif().get(0x0112) not in (2, 3, 4, 5, 6, 7, 8):
+                enc_groups.setdefault((info.width, info.height, info.channels, info.hs, info.vs), []).append((i, data, info))
+            else:
+                imgs[i] = self._open(src)
+        for key, members in enc_groups.items():
+            dec = self._jpeg_decoder()
+            blob, offs = dec.pack([d for _, d, _ in members])
+            x, status = dec.decode(blob, offs, self.device, members[0][2])
+            bad = status.cpu().numpy()            # synchronises: the packed blob may be reused afterwards
+            ok = [j for j in range(len(members)) if bad[j] == 0]
+            for j in range(len(members)):
+                if bad[j] != 0:                   # truncated / corrupt entropy data: Pillow's tolerant decoder takes it
+                    imgs[members[j][0]] = self._open(members[j][1])
+            if ok:
+                xs = x if len(ok) == len(members) else x[torch.as_tensor(ok, device=x.device)]
+                xs, _ = self.preprocess_device(xs, apply_deskew, apply_binarize, apply_contrast, apply_sharpness)
+                for j, b in zip(ok, self.compress_pages_for_azure(xs, target_size_mb=target_size_mb)):
+                    out[members[j][0]] = b
         # EXIF orientation (reference :171-173): pages without the tag -- every rasterised PDF page -- are used as
         # they are (exif_transpose would only copy them); the rare tagged image takes the per-image GPU transpose
-        imgs = [im if im.getexif().get(0x0112) not in (2, 3, 4, 5, 6, 7, 8) else self.auto_orient(im) for im in imgs]
-        out: List[Optional[bytes]] = [None] * len(imgs)
+        imgs = [im if im is None or im.getexif().get(0x0112) not in (2, 3, 4, 5, 6, 7, 8) else self.auto_orient(im) for im in imgs]
         groups = {}
         for i, im in enumerate(imgs):
-            groups.setdefault((im.size, im.mode), []).append(i)
+            if im is not None:
+                groups.setdefault((im.size, im.mode), []).append(i)
         for ((w, h), mode), idx in groups.items():
             if mode not in ("RGB", "L"):   # rare: such objects take the per-image path
                 for i in idx:

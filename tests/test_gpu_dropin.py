@@ -276,3 +276,83 @@ def test_resize_nearest_kernel_equals_pillow(oracle, cuda):
         im = Image.frombytes("P", (w, h), a.tobytes())
         assert np.array_equal(got, np.frombuffer(im.resize((ow, oh), Image.Resampling.LANCZOS).tobytes(), np.uint8).reshape(oh, ow))
         assert np.array_equal(got, oracle.resize_nearest(a, ow, oh))
+
+
+# ---------------------------------------------------------------------------------------------- OCRService adapter (f4)
+class _StubOCRService:
+    """The reference's page loop restated for the test (backend/services/ocr_service.py:604-627 calling :398-417):
+    pdf_to_images, then per page preprocess_for_azure(image, apply_deskew=, apply_binarize=, target_size_mb=) and the
+    (here: fake) Azure call.  `module` plays the role of `services.ocr_service` (it owns `image_preprocessor`)."""
+
+    def __init__(self, module, apply_deskew=True, apply_binarize=False, target_size_mb=2.0):
+        self.m, self._apply_deskew, self._apply_binarize, self._target_size_mb = module, apply_deskew, apply_binarize, target_size_mb
+        self.sent = []
+
+    def _analyze_with_azure(self, data: bytes):
+        self.sent.append(data)
+        return {"content": f"page of {len(data)} bytes"}
+
+    def _process_single_image_sync(self, image, page_number=1):
+        b = self.m.image_preprocessor.preprocess_for_azure(image, apply_deskew=self._apply_deskew,
+                                                           apply_binarize=self._apply_binarize,
+                                                           target_size_mb=self._target_size_mb)
+        return {"page_number": page_number, "processed_image_bytes": b, "result": self._analyze_with_azure(b)}
+
+    def process_pdf_as_images_sync(self, pdf_path):
+        images = self.m.image_preprocessor.pdf_to_images(pdf_path)
+        return [self._process_single_image_sync(im, i) for i, im in enumerate(images, start=1)]
+
+
+@pytest.mark.parametrize("binarize", [False, True])
+def test_ocr_service_page_loop_becomes_one_batched_submission(oracle, cuda, binarize):
+    import types
+
+    from PIL import Image
+
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+    from ocr_system_b200.ocr_service_adapter import install
+
+    inner = ImagePreprocessor(max_dimension=600)
+    pages = [Image.fromarray(oracle.synth_page(1000, 720, 40 + i)) for i in range(5)]
+    inner.pdf_to_images = lambda pdf_path, dpi=None: pages          # poppler is not in the image: the rasteriser is stubbed
+    module = types.SimpleNamespace(image_preprocessor=None)
+    proxy = install(module, inner)
+    svc = _StubOCRService(module, apply_binarize=binarize, target_size_mb=0.2)
+    out = svc.process_pdf_as_images_sync("document.pdf")
+    assert proxy.batched_calls == 1 and len(out) == 5
+    for i, o in enumerate(out):
+        want = inner.preprocess_for_azure(pages[i], apply_deskew=True, apply_binarize=binarize, target_size_mb=0.2)
+        assert o["processed_image_bytes"] == want and svc.sent[i] == want, i
+    # an image the adapter never saw takes the per-image path; proxy attributes fall through to the drop-in
+    other = Image.fromarray(oracle.synth_page(500, 400, 3))
+    assert module.image_preprocessor.preprocess_for_azure(other) == inner.preprocess_for_azure(other)
+    assert proxy.batched_calls == 1 and proxy.max_dimension == 600
+
+
+def test_preprocess_pages_for_azure_decodes_jpeg_bytes_on_the_device(oracle, cuda):
+    """bytes inputs: baseline JPEG files go through the device decoder, everything else through the host codec;
+    either way the result is what the per-page call on Pillow's decode returns."""
+    import io
+
+    from PIL import Image
+
+    from ocr_system_b200 import ops
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+
+    ip_ = ImagePreprocessor(max_dimension=600)
+
+    def enc(a, fmt="JPEG", **kw):
+        b = io.BytesIO()
+        Image.fromarray(a).save(b, fmt, **kw)
+        return b.getvalue()
+
+    p = [oracle.synth_page(1000, 720, 60 + i) for i in range(4)]
+    files = [enc(p[0], quality=75), enc(p[1], quality=90, optimize=True), enc(p[2], quality=75, progressive=True),
+             enc(p[3], "PNG"), enc(np.asarray(Image.fromarray(p[0]).convert("L")), quality=80), enc(p[1][:800], quality=75)]
+    assert [ops.jpeg_probe(f) is not None for f in files] == [True, True, False, False, True, True]
+    launches = ops.launch_count()
+    got = ip_.preprocess_pages_for_azure(files, target_size_mb=0.2)
+    assert ops.launch_count() > launches
+    for i, f in enumerate(files):
+        want = ip_.preprocess_for_azure(Image.open(io.BytesIO(f)), target_size_mb=0.2)
+        assert got[i] == want, i
