@@ -239,35 +239,70 @@ __device__ __forceinline__ int db_slot_of(const int *L, int p) {
 }
 
 // ---- 4. bounding boxes of the candidates' point sets -----------------------------------
+// Only outline pixels of a foreground component (a 4-neighbour is background or the map edge) and background pixels
+// next to foreground (hole borders) can move a box.  The byte mask decides that first -- 4 pixels per thread, the rows
+// above / below as one 32-bit load each -- and only those pixels chase their labels and issue atomics.
+__device__ __forceinline__ void db_bbox_update(int *B, int slot, int x, int y) {
+    atomicMin(&B[slot * 4 + 0], x); atomicMin(&B[slot * 4 + 1], y);
+    atomicMax(&B[slot * 4 + 2], x); atomicMax(&B[slot * 4 + 3], y);
+}
+
 __global__ void __launch_bounds__(256) db_bbox_kernel(const uint8_t *__restrict__ mask, const int *__restrict__ labels,
-                                                      int *__restrict__ bbox, int h, int w, int maxc, long long total_px) {
+                                                      int *__restrict__ bbox, int h, int w, int maxc, long long total_groups) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_px) return;
-    const long long hw = (long long)h * w;
-    const int page = (int)(g / hw);
-    const int idx = (int)(g - (long long)page * hw);
+    if (g >= total_groups) return;
+    const int groups = (w + 3) >> 2;
+    const long long row = g / groups;
+    const int x0 = (int)(g - row * groups) * 4;
+    const int page = (int)(row / h), y = (int)(row - (long long)page * h);
+    const size_t hw = (size_t)h * w;
     const uint8_t *M = mask + (size_t)page * hw;
     const int *L = labels + (size_t)page * hw;
     int *B = bbox + (size_t)page * maxc * 4;
-    const int y = idx / w, x = idx - y * w;
-    const int slot = db_slot_of(L, idx);
-    if (slot < 0) return;
-    if (M[idx] & 1) {
-        // only pixels on the component's outline can move the box
-        const bool inner = x > 0 && x < w - 1 && y > 0 && y < h - 1 && (M[idx - 1] & 1) && (M[idx + 1] & 1) &&
-                           (M[idx - w] & 1) && (M[idx + w] & 1);
-        if (inner) return;
-        atomicMin(&B[slot * 4 + 0], x); atomicMin(&B[slot * 4 + 1], y);
-        atomicMax(&B[slot * 4 + 2], x); atomicMax(&B[slot * 4 + 3], y);
+    const uint8_t *cur = M + (size_t)y * w;
+    // fg bits of this row for x0-1 .. x0+4 (bit k+1 = pixel x0+k), and of the rows above / below for x0 .. x0+3
+    uint32_t c = 0, up = 0, dn = 0;
+    const bool vec = (w & 3) == 0;
+    if (vec) {
+        const uint32_t wc = *reinterpret_cast<const uint32_t *>(cur + x0) & 0x01010101u;
+        c = ((wc & 1u) | ((wc >> 7) & 2u) | ((wc >> 14) & 4u) | ((wc >> 21) & 8u)) << 1;
+        if (y > 0) {
+            const uint32_t wu = *reinterpret_cast<const uint32_t *>(cur - w + x0) & 0x01010101u;
+            up = (wu & 1u) | ((wu >> 7) & 2u) | ((wu >> 14) & 4u) | ((wu >> 21) & 8u);
+        }
+        if (y < h - 1) {
+            const uint32_t wd = *reinterpret_cast<const uint32_t *>(cur + w + x0) & 0x01010101u;
+            dn = (wd & 1u) | ((wd >> 7) & 2u) | ((wd >> 14) & 4u) | ((wd >> 21) & 8u);
+        }
     } else {
-        // hole pixel: its 4-adjacent foreground pixels are the hole border's point set
-        const int nx[4] = {x - 1, x + 1, x, x}, ny[4] = {y, y, y - 1, y + 1};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (nx[k] < 0 || nx[k] >= w || ny[k] < 0 || ny[k] >= h) continue;
-            if (!(M[ny[k] * w + nx[k]] & 1)) continue;
-            atomicMin(&B[slot * 4 + 0], nx[k]); atomicMin(&B[slot * 4 + 1], ny[k]);
-            atomicMax(&B[slot * 4 + 2], nx[k]); atomicMax(&B[slot * 4 + 3], ny[k]);
+        for (int k = 0; k < 4 && x0 + k < w; k++) {
+            c |= (uint32_t)(cur[x0 + k] & 1) << (k + 1);
+            if (y > 0) up |= (uint32_t)(cur[x0 + k - w] & 1) << k;
+            if (y < h - 1) dn |= (uint32_t)(cur[x0 + k + w] & 1) << k;
+        }
+    }
+    if (x0 > 0) c |= cur[x0 - 1] & 1u;
+    if (x0 + 4 < w) c |= (uint32_t)(cur[x0 + 4] & 1) << 5;
+    const int nvalid = min(4, w - x0);
+    for (int k = 0; k < nvalid; k++) {
+        const int x = x0 + k, idx = y * w + x;
+        const bool fg = (c >> (k + 1)) & 1u;
+        const bool l = (c >> k) & 1u, r = (c >> (k + 2)) & 1u, u = (up >> k) & 1u, d = (dn >> k) & 1u;
+        if (fg) {
+            const bool inner = x > 0 && x < w - 1 && y > 0 && y < h - 1 && l && r && u && d;
+            if (inner) continue;
+            const int slot = db_slot_of(L, idx);
+            if (slot >= 0) db_bbox_update(B, slot, x, y);
+        } else {
+            // hole pixel: its 4-adjacent foreground pixels are the hole border's point set
+            const bool fl = x > 0 && l, fr = x < w - 1 && r, fu = u, fd = d;   // up / dn are already 0 outside the map
+            if (!(fl | fr | fu | fd)) continue;
+            const int slot = db_slot_of(L, idx);
+            if (slot < 0) continue;
+            if (fl) db_bbox_update(B, slot, x - 1, y);
+            if (fr) db_bbox_update(B, slot, x + 1, y);
+            if (fu) db_bbox_update(B, slot, x, y - 1);
+            if (fd) db_bbox_update(B, slot, x, y + 1);
         }
     }
 }
@@ -428,15 +463,16 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_cand_score_kernel(const DbPa
 #pragma unroll
     for (int i = 0; i < 4; i++) { q[i].x = (int)(bxs[i] - (float)xmin); q[i].y = (int)(bys[i] - (float)ymin); }
     const int mh = ymax - ymin + 1, mw = xmax - xmin + 1;
+    // a lane owns a mask row: its coverage intervals (serial integer geometry, now 32 rows at a time) and its sum
     double sum = 0.0;
     int cnt = 0;
-    for (int ry = 0; ry < mh; ry++) {
+    for (int ry = lane; ry < mh; ry += 32) {
         int lo[5], hi[5];
         const int c = db_row_intervals(q, ry, mw, mh, lo, hi);
         const float *prow = P + (size_t)(ymin + ry) * p.w + xmin;
         for (int i = 0; i < c; i++) {
             const int a = max(lo[i], 0), b = min(hi[i], mw - 1);
-            for (int x = a + lane; x <= b; x += 32) { sum += (double)__ldg(prow + x); cnt++; }
+            for (int x = a; x <= b; x++) { sum += (double)__ldg(prow + x); cnt++; }
         }
     }
 #pragma unroll
@@ -618,9 +654,9 @@ LUMINA_API int lumina_db_postprocess_ex(const float *d_pred, int n, int h, int w
     db_candidates_kernel<<<n, 1024, 0, st>>>(mask, labels, (int *)(ws + L.cand_off), (int *)(ws + L.bbox_off),
                                              (int *)(ws + L.ncand_off), h, w, max_candidates);
     LUMINA_KERNEL_CHECK("db_candidates_kernel");
-    const size_t px = (size_t)n * h * w;
-    db_bbox_kernel<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(mask, labels, (int *)(ws + L.bbox_off), h, w, max_candidates,
-                                                                  (long long)px);
+    const long long bgroups = (long long)n * h * ((w + 3) / 4);
+    db_bbox_kernel<<<(unsigned)((bgroups + 255) / 256), 256, 0, st>>>(mask, labels, (int *)(ws + L.bbox_off), h, w, max_candidates,
+                                                                       bgroups);
     LUMINA_KERNEL_CHECK("db_bbox_kernel");
     DbParams p;
     p.pred = d_pred; p.mask = mask; p.labels = labels;
