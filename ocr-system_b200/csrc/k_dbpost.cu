@@ -83,6 +83,47 @@ __global__ void __launch_bounds__(256) db_mask_dilate_kernel(const float *__rest
 }
 
 // ---- 2. two-class union-find labelling ----------------------------------------------
+// class bits (fg = 1) of 4 consecutive pixels from one aligned 32-bit load of the byte mask
+__device__ __forceinline__ uint32_t db_class4(const uint8_t *p) {
+    const uint32_t wv = *reinterpret_cast<const uint32_t *>(p) & 0x01010101u;
+    return (wv & 1u) | ((wv >> 7) & 2u) | ((wv >> 14) & 4u) | ((wv >> 21) & 8u);
+}
+
+// Two-class row runs: every pixel starts labelled with the first pixel of its run (same class) inside its aligned
+// 32-pixel segment.  4 pixels per thread (one 32-bit mask load, one 128-bit label store); the 8 lanes of a segment
+// assemble its 32 class bits with three xor-shuffles.  Requires w % 4 == 0 (else the scalar kernel below).
+__global__ void __launch_bounds__(256) db_ccl_init4_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h,
+                                                           int w, long long total_groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int groups = (w + 31) >> 5 << 3;          // lanes per row, padded to whole segments (8 lanes each)
+    const bool active = g < total_groups;
+    const long long row = active ? g / groups : 0;
+    const int q = active ? (int)(g - row * groups) : 0;   // 4-pixel group inside the row
+    const int x0 = q * 4;
+    const bool in = active && x0 < w;
+    const size_t base = (size_t)row * w;                   // rows are contiguous over the batch
+    uint32_t bits = in ? db_class4(mask + base + x0) : 0u;
+    const int sub = q & 7;                                 // position of this lane inside its 32-pixel segment
+    uint32_t seg = bits << (4 * sub);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        seg |= __shfl_xor_sync(0xffffffffu, seg, o);
+    }
+    if (!in) return;
+    const int idx0 = (int)(((size_t)row % h) * w) + x0;    // page-relative index of the first pixel
+    int out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int pos = 4 * sub + k;
+        const uint32_t c = (seg >> pos) & 1u;
+        const uint32_t same = c ? seg : ~seg;              // pixels of my class
+        const uint32_t below = ~same & ((1u << pos) - 1u); // other-class pixels before me in the segment
+        const int start = below ? 32 - __clz(below) : 0;
+        out[k] = idx0 + k - (pos - start);
+    }
+    *reinterpret_cast<int4 *>(labels + base + x0) = make_int4(out[0], out[1], out[2], out[3]);
+}
+
 __global__ void __launch_bounds__(256) db_ccl_init_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h,
                                                           int w, long long nseg_total) {
     const int lane = threadIdx.x & 31;
@@ -107,28 +148,87 @@ __global__ void __launch_bounds__(256) db_ccl_init_kernel(const uint8_t *__restr
     }
 }
 
+// 4 pixels per thread: the classes of this row and the row above come from two word loads (+ the three bytes left /
+// right of them); labels are only touched where a union is due (a few per cent of the pixels).
 __global__ void __launch_bounds__(256) db_ccl_merge_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h,
-                                                           int w, long long total_px) {
+                                                           int w, long long total_groups) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_px) return;
-    const long long hw = (long long)h * w;
-    const int page = (int)(g / hw);
-    const int idx = (int)(g - (long long)page * hw);
+    if (g >= total_groups) return;
+    const int groups = (w + 3) >> 2;
+    const long long row = g / groups;
+    const int x0 = (int)(g - row * groups) * 4;
+    const int page = (int)(row / h), y = (int)(row - (long long)page * h);
+    const size_t hw = (size_t)h * w;
     const uint8_t *M = mask + (size_t)page * hw;
     int *L = labels + (size_t)page * hw;
-    const int c = M[idx] & 1;
-    const int y = idx / w, x = idx - y * w;
-    if ((x & 31) == 0 && x > 0 && (M[idx - 1] & 1) == c) ccl_union(L, idx, idx - 1);
-    if (y > 0) {
-        const int up = idx - w;
-        if ((M[up] & 1) == c) {
-            const bool left_same = x > 0 && (M[idx - 1] & 1) == c;
-            const bool upleft_same = x > 0 && (M[up - 1] & 1) == c;
-            if (!(left_same && upleft_same)) ccl_union(L, idx, up);
-        } else if (c == 1) {  // foreground is 8-connected
-            if (x > 0 && (M[up - 1] & 1)) ccl_union(L, idx, up - 1);
-            if (x + 1 < w && (M[up + 1] & 1)) ccl_union(L, idx, up + 1);
+    const uint8_t *cur = M + (size_t)y * w;
+    // bit k+1 = class of pixel x0+k; bit 0 = pixel x0-1; bit 5 = pixel x0+4 (row above only)
+    uint32_t c = 0, u = 0;
+    if ((w & 3) == 0) {
+        c = db_class4(cur + x0) << 1;
+        if (y > 0) u = db_class4(cur - w + x0) << 1;
+    } else {
+        for (int k = 0; k < 4 && x0 + k < w; k++) {
+            c |= (uint32_t)(cur[x0 + k] & 1) << (k + 1);
+            if (y > 0) u |= (uint32_t)(cur[x0 + k - w] & 1) << (k + 1);
         }
+    }
+    if (x0 > 0) {
+        c |= cur[x0 - 1] & 1u;
+        if (y > 0) u |= cur[x0 - 1 - w] & 1u;
+    }
+    if (y > 0 && x0 + 4 < w) u |= (uint32_t)(cur[x0 + 4 - w] & 1) << 5;
+    const int nvalid = min(4, w - x0);
+    for (int k = 0; k < nvalid; k++) {
+        const int x = x0 + k, idx = y * w + x;
+        const uint32_t cc = (c >> (k + 1)) & 1u;
+        const bool left_same = x > 0 && ((c >> k) & 1u) == cc;
+        if ((x & 31) == 0 && left_same) ccl_union(L, idx, idx - 1);
+        if (y > 0) {
+            const int up = idx - w;
+            if (((u >> (k + 1)) & 1u) == cc) {
+                const bool upleft_same = x > 0 && ((u >> k) & 1u) == cc;
+                if (!(left_same && upleft_same)) ccl_union(L, idx, up);
+            } else if (cc == 1u) {  // foreground is 8-connected
+                if (x > 0 && ((u >> k) & 1u)) ccl_union(L, idx, up - 1);
+                if (x + 1 < w && ((u >> (k + 2)) & 1u)) ccl_union(L, idx, up + 1);
+            }
+        }
+    }
+}
+
+// flatten, 4 pixels per thread (128-bit label load / store; neighbours of a run share the root that was just found)
+__global__ void __launch_bounds__(256) db_ccl_flatten4_kernel(uint8_t *__restrict__ mask, int *__restrict__ labels, int h, int w,
+                                                              long long total_groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_groups) return;
+    const int groups = w >> 2;
+    const long long row = g / groups;
+    const int x0 = (int)(g - row * groups) * 4;
+    const int page = (int)(row / h), y = (int)(row - (long long)page * h);
+    const size_t hw = (size_t)h * w;
+    uint8_t *M = mask + (size_t)page * hw;
+    int *L = labels + (size_t)page * hw;
+    const int idx0 = y * w + x0;
+    const int4 lv = *reinterpret_cast<const int4 *>(L + idx0);
+    const int lab[4] = {lv.x, lv.y, lv.z, lv.w};
+    const uint32_t cls = db_class4(M + idx0);
+    int out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k > 0 && lab[k] == lab[k - 1]) { out[k] = out[k - 1]; continue; }
+        int a = lab[k], p = a == idx0 + k ? a : L[a];
+        while (p != a) { a = p; p = L[a]; }
+        out[k] = a;
+    }
+    *reinterpret_cast<int4 *>(L + idx0) = make_int4(out[0], out[1], out[2], out[3]);
+    if (y == 0 || y == h - 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (!((cls >> k) & 1u)) M[out[k]] = 2;    // same value from every writer
+    } else {
+        if (x0 == 0 && !(cls & 1u)) M[out[0]] = 2;
+        if (x0 + 4 == w && !((cls >> 3) & 1u)) M[out[3]] = 2;
     }
 }
 
@@ -602,13 +702,26 @@ static int db_label(const float *d_pred, int n, int h, int w, float thresh, uint
         LUMINA_KERNEL_CHECK("db_mask_kernel");
     }
     const long long nseg = (long long)n * h * ((w + 31) / 32);
-    db_ccl_init_kernel<<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, st>>>(mask, labels, h, w, nseg);
-    LUMINA_KERNEL_CHECK("db_ccl_init_kernel");
+    if ((w & 3) == 0) {
+        const long long igroups = (long long)n * h * (((w + 31) >> 5) << 3);
+        db_ccl_init4_kernel<<<(unsigned)((igroups + 255) / 256), 256, 0, st>>>(mask, labels, h, w, igroups);
+        LUMINA_KERNEL_CHECK("db_ccl_init4_kernel");
+    } else {
+        db_ccl_init_kernel<<<(unsigned)((nseg * 32 + 255) / 256), 256, 0, st>>>(mask, labels, h, w, nseg);
+        LUMINA_KERNEL_CHECK("db_ccl_init_kernel");
+    }
     const unsigned gpx = (unsigned)((px + 255) / 256);
-    db_ccl_merge_kernel<<<gpx, 256, 0, st>>>(mask, labels, h, w, (long long)px);
+    const long long mgroups = (long long)n * h * ((w + 3) / 4);
+    db_ccl_merge_kernel<<<(unsigned)((mgroups + 255) / 256), 256, 0, st>>>(mask, labels, h, w, mgroups);
     LUMINA_KERNEL_CHECK("db_ccl_merge_kernel");
-    db_ccl_flatten_kernel<<<gpx, 256, 0, st>>>(mask, labels, h, w, (long long)px);
-    LUMINA_KERNEL_CHECK("db_ccl_flatten_kernel");
+    if ((w & 3) == 0) {
+        const long long fgroups = (long long)n * h * (w >> 2);
+        db_ccl_flatten4_kernel<<<(unsigned)((fgroups + 255) / 256), 256, 0, st>>>(mask, labels, h, w, fgroups);
+        LUMINA_KERNEL_CHECK("db_ccl_flatten4_kernel");
+    } else {
+        db_ccl_flatten_kernel<<<gpx, 256, 0, st>>>(mask, labels, h, w, (long long)px);
+        LUMINA_KERNEL_CHECK("db_ccl_flatten_kernel");
+    }
     return LUMINA_OK;
 }
 
