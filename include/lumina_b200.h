@@ -98,6 +98,16 @@ int lumina_binarize_u8(const uint8_t *d_src, uint8_t *d_dst, size_t npx, int c, 
  * images as 4 bytes per pixel (R, G, B, pad); npx such pixels -> tightly packed R, G, B. */
 int lumina_rgbx_to_rgb_u8(const uint8_t *d_src, uint8_t *d_dst, size_t npx, void *stream);
 
+/* ---- north_star extras: Otsu and Sauvola binarisation (not called by the reference) ---------- */
+/* Otsu: per-page threshold as cv2.threshold(gray, 0, 255, THRESH_BINARY | THRESH_OTSU) computes it (bit-equal);
+ * d_thresh [n] int32 receives it, d_dst [n][h][w] {0,255} the mask (may be NULL); d_hist_scratch: n * 256 uint32. */
+int lumina_otsu_u8(const uint8_t *d_gray, uint8_t *d_dst, int n, int h, int w, int32_t *d_thresh,
+                   uint32_t *d_hist_scratch, void *stream);
+/* Sauvola: dst = 255 where x > m * (1 + k * (s / R - 1)), m / s = mean / standard deviation of the
+ * window x window neighbourhood clipped to the page (exact integer sums, float64 formula); window odd, 3..49. */
+int lumina_sauvola_u8(const uint8_t *d_gray, uint8_t *d_dst, int n, int h, int w, int window, double k, double R,
+                      void *stream);
+
 /* ---- a9  adaptive_binarize :462-494 (cv2.adaptiveThreshold GAUSSIAN 11,C) */
 /* c==3: fused PIL gray.  dst [n][h][w] in {0,255}. */
 int lumina_adaptive_gauss11_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, int cval,
@@ -137,6 +147,14 @@ void lumina_rotation_matrix_host(double cx, double cy, double angle_deg, double 
  * chunks); pages with h_apply[i]==0 are copied unchanged (|angle|<0.5 etc). */
 int lumina_warp_affine_cubic_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c,
                                 const double *h_m6, const uint8_t *h_apply, void *stream);
+
+/* ---- flag-gated alternative to a10's angle: projection-profile skew estimate (north_star) ---- */
+/* NOT what the reference computes (:402-428 HoughLinesP + median): a tolerance-certified estimate of the same
+ * angle (degrees, sign as the reference: positive = text descends to the right) from the Canny edge maps
+ * [n][h][w]; the caller applies the reference's gates (:433-439) and rotation.  d_angles [n] f64. */
+size_t lumina_skew_workspace_bytes(int n);
+int lumina_skew_estimate_fast(const uint8_t *d_edges, int n, int h, int w, double *d_angles, void *d_workspace,
+                              size_t workspace_bytes, void *stream);
 
 /* ---- a15 [upstream PaddleOCR] DetResizeForTest + NormalizeImage + ToCHW - */
 void lumina_det_target_size(int h, int w, int limit_side_len, int *out_h, int *out_w);

@@ -19,7 +19,7 @@ SO = os.path.join(HERE, "liblumina_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off"]
 # float32 evaluation order is part of the spec for these files: never contract to FMA
-NO_FMA = {"k_stencil.cu", "k_det.cu", "k_point.cu", "k_ppht.cu", "k_dbpost.cu", "k_ctc.cu"}
+NO_FMA = {"k_stencil.cu", "k_det.cu", "k_point.cu", "k_ppht.cu", "k_dbpost.cu", "k_ctc.cu", "k_binarize.cu"}
 
 
 def _nvcc() -> str:

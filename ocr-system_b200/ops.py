@@ -235,6 +235,34 @@ def binarize(pages: torch.Tensor, threshold: int = 128) -> torch.Tensor:
 
 
 @_on_tensor_device
+def otsu_binarize(gray: torch.Tensor):
+    """Per-page Otsu threshold + mask of gray planes [N,H,W] (cv2.threshold(..., THRESH_BINARY | THRESH_OTSU), bit-equal).
+    Returns (mask uint8 {0,255} [N,H,W], thresholds int32 [N])."""
+    if not gray.is_cuda or gray.dtype != torch.uint8 or gray.dim() != 3:
+        raise TypeError("otsu_binarize expects a CUDA uint8 [N,H,W] tensor")
+    g = gray.contiguous()
+    n, h, w = g.shape
+    out = torch.empty_like(g)
+    thr = torch.empty(n, dtype=torch.int32, device=g.device)
+    hist = torch.empty(n * 256, dtype=torch.int32, device=g.device)
+    _chk(_L().lumina_otsu_u8(_ptr(g), _ptr(out), n, h, w, _ptr(thr), _ptr(hist), _stream()))
+    return out, thr
+
+
+@_on_tensor_device
+def sauvola_binarize(gray: torch.Tensor, window: int = 25, k: float = 0.2, r: float = 128.0) -> torch.Tensor:
+    """Sauvola local threshold of gray planes [N,H,W]: 255 where x > m * (1 + k * (s / r - 1)) over a
+    window x window neighbourhood clipped to the page (integral images per tile in shared memory)."""
+    if not gray.is_cuda or gray.dtype != torch.uint8 or gray.dim() != 3:
+        raise TypeError("sauvola_binarize expects a CUDA uint8 [N,H,W] tensor")
+    g = gray.contiguous()
+    n, h, w = g.shape
+    out = torch.empty_like(g)
+    _chk(_L().lumina_sauvola_u8(_ptr(g), _ptr(out), n, h, w, int(window), float(k), float(r), _stream()))
+    return out
+
+
+@_on_tensor_device
 def adaptive_binarize(pages: torch.Tensor, cval: int = 2) -> torch.Tensor:
     x, n, h, w, c = _pages(pages)
     out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
@@ -376,6 +404,46 @@ def deskew(pages: torch.Tensor, max_lines: int = 4096):
     keep = int(nl.max(initial=0))
     lh = lines[:, :max(keep, 1)].cpu().numpy()
     angles, mats, apply = deskew_decide(lh, nl, h, w)
+    if not apply.any():
+        return pages, angles
+    out = warp_affine_cubic(x, mats, apply)
+    return (out.squeeze(-1) if pages.dim() == 3 else out), angles
+
+
+@_on_tensor_device
+def estimate_skew_fast(edges: torch.Tensor) -> torch.Tensor:
+    """Projection-profile estimate of the reference's deskew angle from Canny edge maps [N,H,W] (degrees, f64, on the
+    device).  NOT the reference's algorithm (Hough segments + median): a tolerance-certified alternative, flag-gated."""
+    if not edges.is_cuda or edges.dtype != torch.uint8 or edges.dim() != 3:
+        raise TypeError("estimate_skew_fast expects a CUDA uint8 [N,H,W] edge map")
+    e = edges.contiguous()
+    n, h, w = e.shape
+    angles = torch.empty(n, dtype=torch.float64, device=e.device)
+    wsb = int(_L().lumina_skew_workspace_bytes(n))
+    ws = _ws(wsb, e.device)
+    _chk(_L().lumina_skew_estimate_fast(_ptr(e), n, h, w, _ptr(angles), _ptr(ws), wsb, _stream()))
+    return angles
+
+
+def deskew_fast(pages: torch.Tensor):
+    """The reference's deskew (image_preprocessing.py:372-460) with the angle taken from ``estimate_skew_fast``
+    instead of HoughLinesP + median; gates (:433-439), rotation matrix and bicubic warp are the reference's.
+    Flag-gated: rasters differ from the reference's wherever the two angles differ."""
+    x, n, h, w, c = _pages(pages)
+    est = estimate_skew_fast(canny(x, 50, 150)).cpu().numpy()
+    angles = np.zeros(n, np.float64)
+    mats = np.zeros((n, 6), np.float64)
+    apply = np.zeros(n, np.uint8)
+    for i in range(n):
+        a = float(est[i])
+        if abs(a) < 0.5:          # :433-435 (angle reported, image untouched)
+            angles[i] = a
+        elif abs(a) > 45:         # :437-439
+            angles[i] = 0.0
+        else:
+            angles[i] = a
+            mats[i] = rotation_matrix(w // 2, h // 2, a, 1.0).reshape(-1)
+            apply[i] = 1
     if not apply.any():
         return pages, angles
     out = warp_affine_cubic(x, mats, apply)

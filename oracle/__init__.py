@@ -313,3 +313,59 @@ def jpeg_decode(data: bytes):
     if rc:
         raise ValueError("malformed JPEG")
     return out[:, :, 0] if c.value == 1 else out
+
+
+# --- north_star extras: Otsu / Sauvola (not called by the reference) ---------
+def otsu_threshold(gray) -> int:
+    """getThreshVal_Otsu_8u (OpenCV modules/imgproc/src/thresh.cpp) restated in float64, same operation order.
+    Pinned against cv2.threshold(..., THRESH_OTSU) in tests/test_oracle_pins.py."""
+    gray = _u8(gray)
+    h = np.bincount(gray.ravel(), minlength=256).astype(np.float64)
+    scale = 1.0 / gray.size
+    mu = 0.0
+    for i in range(256):
+        mu += i * h[i]
+    mu *= scale
+    mu1 = q1 = max_sigma = 0.0
+    max_val = 0
+    eps = float(np.finfo(np.float32).eps)
+    for i in range(256):
+        p_i = h[i] * scale
+        mu1 *= q1
+        q1 += p_i
+        q2 = 1.0 - q1
+        if min(q1, q2) < eps or max(q1, q2) > 1.0 - eps:
+            continue
+        mu1 = (mu1 + i * p_i) / q1
+        mu2 = (mu - q1 * mu1) / q2
+        sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2)
+        if sigma > max_sigma:
+            max_sigma, max_val = sigma, i
+    return int(max_val)
+
+
+def sauvola(gray, window: int = 25, k: float = 0.2, r: float = 128.0):
+    """Sauvola threshold with the window clipped to the page: exact integer sums (int64 integral images), then
+    T = m * (1 + k * (s / r - 1)) in float64 with separate operations.  PARITY UNPINNED by the reference (it has no
+    such operator) and by any library in this image (skimage is absent): this restatement defines the operator."""
+    g = _u8(gray).astype(np.int64)
+    hh, ww = g.shape
+    rad = window // 2
+    i1 = np.zeros((hh + 1, ww + 1), np.int64)
+    i2 = np.zeros((hh + 1, ww + 1), np.int64)
+    i1[1:, 1:] = g.cumsum(0).cumsum(1)
+    i2[1:, 1:] = (g * g).cumsum(0).cumsum(1)
+    ys, xs = np.arange(hh), np.arange(ww)
+    y0, y1 = np.maximum(ys - rad, 0), np.minimum(ys + rad, hh - 1) + 1
+    x0, x1 = np.maximum(xs - rad, 0), np.minimum(xs + rad, ww - 1) + 1
+
+    def box(ii):
+        return ii[y1[:, None], x1[None, :]] - ii[y0[:, None], x1[None, :]] - ii[y1[:, None], x0[None, :]] + ii[y0[:, None], x0[None, :]]
+
+    cnt = ((y1 - y0)[:, None] * (x1 - x0)[None, :]).astype(np.float64)
+    m = box(i1).astype(np.float64) / cnt
+    var = box(i2).astype(np.float64) / cnt - m * m
+    var = np.where(var < 0.0, 0.0, var)
+    s = np.sqrt(var)
+    t = m * (1.0 + k * (s / r - 1.0))
+    return np.where(g.astype(np.float64) > t, 255, 0).astype(np.uint8)

@@ -283,3 +283,30 @@ def test_ingest_zero_copy_and_fallback_agree(cuda):
         got = ip._upload(imgs).cpu().numpy()
         want = np.stack([np.asarray(im).reshape(im.size[1], im.size[0], -1) for im in imgs])
         assert np.array_equal(got, want)
+
+
+def test_otsu_equals_cv2_and_sauvola_equals_the_float64_restatement(oracle, cuda):
+    """north_star extras (not reference call sites): Otsu is pinned by cv2 (threshold and mask bit-equal); Sauvola by
+    the NumPy float64 restatement with exact integer window sums (windows clipped to the page)."""
+    import cv2
+    import torch
+
+    from ocr_system_b200 import ops
+
+    rng = np.random.default_rng(5)
+    pages = np.stack([oracle.gray_pil(oracle.synth_page(700, 500, s)) for s in range(3)] +
+                     [rng.integers(0, 256, (700, 500), dtype=np.uint8)])
+    x = torch.from_numpy(pages).to(cuda)
+    mask, thr = ops.otsu_binarize(x)
+    for i in range(len(pages)):
+        t, ref = cv2.threshold(pages[i], 0, 255, cv2.THRESH_BINARY | cv2.THRESH_OTSU)
+        assert int(thr[i]) == int(t) == oracle.otsu_threshold(pages[i])
+        assert np.array_equal(mask[i].cpu().numpy(), ref)
+    for window, k in ((25, 0.2), (15, 0.34), (49, 0.1), (3, 0.5)):
+        got = ops.sauvola_binarize(x, window, k, 128.0).cpu().numpy()
+        for i in range(len(pages)):
+            assert np.array_equal(got[i], oracle.sauvola(pages[i], window, k, 128.0)), (window, k, i)
+    odd = torch.from_numpy(np.ascontiguousarray(pages[0][:133, :77])).to(cuda)[None]     # ragged tiles, odd pitch
+    assert np.array_equal(ops.sauvola_binarize(odd, 25, 0.2).cpu().numpy()[0], oracle.sauvola(pages[0][:133, :77], 25, 0.2))
+    m2, t2 = ops.otsu_binarize(odd)
+    assert int(t2[0]) == oracle.otsu_threshold(pages[0][:133, :77])

@@ -102,3 +102,15 @@ def test_oracle_composition_reproduces_reference_optimize_for_ocr_flags(oracle, 
     if kw["apply_sharpness"]:
         x = oracle.sharpness(x, 1.1)
     assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == case["want"]["sha"]
+
+
+def test_otsu_restatement_equals_cv2(oracle):
+    import cv2
+
+    rng = np.random.default_rng(4)
+    imgs = [oracle.gray_pil(oracle.synth_page(300, 220, s)) for s in range(3)]
+    imgs += [rng.integers(0, 256, (64, 80), dtype=np.uint8), np.full((20, 20), 77, np.uint8),
+             (rng.random((90, 70)) < 0.3).astype(np.uint8) * 200 + 20]
+    for g in imgs:
+        t, mask = cv2.threshold(g, 0, 255, cv2.THRESH_BINARY | cv2.THRESH_OTSU)
+        assert oracle.otsu_threshold(g) == int(t)

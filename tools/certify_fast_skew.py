@@ -1,0 +1,49 @@
+"""Certification run of the flag-gated fast skew estimator against the exact (reference) deskew angle.
+python tools/certify_fast_skew.py [n_pages] [max_dimension]  ->  one JSON line (profiles/r2_fast_skew_certification.json)"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ocr_system_b200 import ops  # noqa: E402
+
+n_pages = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+md = int(sys.argv[2]) if len(sys.argv) > 2 else 960
+torch.cuda.set_device(0)
+exact, fast, t_fast, t_exact = [], [], 0.0, 0.0
+for s0 in range(0, n_pages, 64):
+    pages = ops.synth_pages(64, 3508, 2480, seed0=s0)
+    x = ops.resize_if_needed(pages, md)
+    del pages
+    edges = ops.canny(x, 50, 150)
+    torch.cuda.synchronize()
+    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    a.record()
+    est = ops.estimate_skew_fast(edges)
+    b.record()
+    lines, nlines = ops.hough_lines_p(edges)
+    c.record()
+    torch.cuda.synchronize()
+    t_fast += a.elapsed_time(b)
+    t_exact += b.elapsed_time(c)
+    nl = nlines.cpu().numpy()
+    ang, _m, _ap = ops.deskew_decide(lines[:, :max(int(nl.max()), 1)].cpu().numpy(), nl, x.shape[1], x.shape[2])
+    exact += ang.tolist()
+    fast += est.cpu().numpy().tolist()
+exact, fast = np.array(exact), np.array(fast)
+d = np.abs(fast - exact)
+gate_e, gate_f = np.abs(exact) >= 0.5, np.abs(fast) >= 0.5
+near_gate = np.abs(np.abs(exact) - 0.5) < 0.1
+print(json.dumps({
+    "pages": int(len(exact)), "max_dimension": md,
+    "abs_delta_deg": {"max": float(d.max()), "p50": float(np.percentile(d, 50)), "p95": float(np.percentile(d, 95)),
+                      "p99": float(np.percentile(d, 99)), "mean": float(d.mean())},
+    "within_0.1_deg": float((d <= 0.1).mean()), "within_0.05_deg": float((d <= 0.05).mean()),
+    "same_side_of_0.5_gate": float((gate_e == gate_f).mean()),
+    "gate_disagreements_all_within_0.1_of_gate": bool(np.all(near_gate[gate_e != gate_f])) if (gate_e != gate_f).any() else True,
+    "ms_per_64_pages": {"fast_estimator": round(t_fast / (n_pages / 64), 3), "exact_houghlinesp": round(t_exact / (n_pages / 64), 3)},
+    "worst": [{"exact": float(exact[i]), "fast": float(fast[i])} for i in np.argsort(-d)[:5]],
+}))
