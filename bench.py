@@ -470,6 +470,21 @@ def bench_chain(cx: Ctx):
     launches = ops.launch_count() - launches0
     clocks = sampler.stop()
 
+    # ---- (b') the same steps with the flag-gated fast skew estimator instead of the exact HoughLinesP replica
+    # (NOT the reference's angle: reported beside `value`, never as it) ----------------------------------------
+    fpipe = PagePipeline(max_dimension=args.max_dim, device=dev, deskew_mode="fast")
+    for r in fpipe.run_device_stream([pool[i % P] for i in range(W)]):
+        del r
+    torch.cuda.synchronize()
+
+    def round_fast():
+        s = state["i"]
+        for r in fpipe.run_device_stream([pool[(s + i) % P] for i in range(K)]):
+            del r
+        state["i"] += K
+
+    fast_ms, R_fast = cx.timed_rounds(round_fast, K, pip_ms / (R_pip * K) / 2)
+
     # ---- (c) e2e: pinned host rasters -> HBM -> chain -> host results --------------------------------------
     host_pool = []
     for p in range(P):
@@ -568,6 +583,9 @@ def bench_chain(cx: Ctx):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "rounds": R_pip, "timed_steps": steps_timed, "timed_region_s": pip_ms / 1e3, "distinct_batches": P,
         "value_unpipelined": world * B * R_unp * K / (unp_ms / 1e3), "ms_per_step_unpipelined": unp_ms / (R_unp * K),
+        "value_fast_deskew": {"value": world * B * R_fast * K / (fast_ms / 1e3), "unit": UNIT, "ms_per_step": fast_ms / (R_fast * K),
+                              "note": "deskew_mode='fast' (projection-profile angle, flag-gated, NOT the reference's "
+                                      "HoughLinesP angle: rasters differ; profiles/r2_fast_skew_certification.json)"},
         "dtype": "u8", "data": "synthetic", "config": _workload2(args),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / Ke, "timed_steps": Ke, "pinned_h2d_GBps": round(h2d_gbps, 1),

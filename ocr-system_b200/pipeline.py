@@ -111,7 +111,13 @@ class PageBatchResult:
 
 class PagePipeline:
     def __init__(self, max_dimension: int = 960, deskew: bool = True, enhance: bool = False,
-                 det_limit_side_len: int = 960, device: Optional[torch.device] = None):
+                 det_limit_side_len: int = 960, device: Optional[torch.device] = None, deskew_mode: str = "exact"):
+        """``deskew_mode``: "exact" (default) reproduces the reference's angle bit for bit (Canny + HoughLinesP +
+        median); "fast" takes it from the projection-profile estimator (``ops.estimate_skew_fast``): a different,
+        tolerance-certified estimate -- rasters then differ from the reference's (tests/test_gpu_fast_skew.py)."""
+        if deskew_mode not in ("exact", "fast"):
+            raise ValueError("deskew_mode must be 'exact' or 'fast'")
+        self.deskew_mode = deskew_mode
         self.max_dimension = int(max_dimension)
         self.deskew = deskew
         self.enhance = enhance
@@ -139,13 +145,18 @@ class PagePipeline:
         lines = nlines = None
         if self.deskew:
             edges = t.run("canny", lambda: ops.canny(x, 50, 150))
-            lines, nlines = t.run("ppht", lambda: ops.hough_lines_p(edges))
+            if self.deskew_mode == "fast":
+                lines = t.run("skew_fast", lambda: ops.estimate_skew_fast(edges))   # [N] f64 angles instead of line lists
+            else:
+                lines, nlines = t.run("ppht", lambda: ops.hough_lines_p(edges))
         return x, lines, nlines
 
     def _back(self, x, lines, nlines, t: "_StageTimer") -> PageBatchResult:
         """Host median / gating (the chain's one synchronisation) and everything after it."""
         angles = np.zeros(x.shape[0], np.float64)
-        if self.deskew:
+        if self.deskew and self.deskew_mode == "fast":
+            x, angles = t.run("angle+warp", lambda: self._rotate_fast(x, lines))
+        elif self.deskew:
             x, angles = t.run("angle+warp", lambda: self._rotate(x, lines, nlines))
         if self.enhance:
             x = t.run("contrast+sharpness", lambda: ops.contrast_sharpness(x, 1.2, 1.1))
@@ -179,11 +190,14 @@ class PagePipeline:
             with torch.cuda.stream(hi):
                 x = t.run("resize_lanczos", lambda: ops.resize_if_needed(pages, self.max_dimension))
                 job = None
+                lines = nlines = None
                 if self.deskew:
                     edges = t.run("canny", lambda: ops.canny(x, 50, 150))
-                    job = t.run("ppht_prepare", lambda: ops.HoughJob(edges).prepare())
-            lines = nlines = None
-            if self.deskew:
+                    if self.deskew_mode == "fast":
+                        lines = t.run("skew_fast", lambda: ops.estimate_skew_fast(edges))
+                    else:
+                        job = t.run("ppht_prepare", lambda: ops.HoughJob(edges).prepare())
+            if job is not None:
                 lo.wait_stream(hi)
                 with torch.cuda.stream(lo):
                     lines, nlines = t.run("ppht", job.lines)
@@ -210,6 +224,19 @@ class PagePipeline:
                 yield finish(pending.pop(0))
         while pending:
             yield finish(pending.pop(0))
+
+    def _rotate_fast(self, x: torch.Tensor, est: torch.Tensor):
+        """deskew_mode="fast": the reference's gates (image_preprocessing.py:433-439) and warp on the estimated angles."""
+        n, h, w = x.shape[0], x.shape[1], x.shape[2]
+        a = est.cpu().numpy()     # n doubles; synchronises like the exact path's line lists
+        angles = np.where(np.abs(a) > 45, 0.0, a)
+        apply = ((np.abs(a) >= 0.5) & (np.abs(a) <= 45)).astype(np.uint8)
+        mats = np.zeros((n, 6), np.float64)
+        for i in np.nonzero(apply)[0]:
+            mats[i] = ops.rotation_matrix(w // 2, h // 2, float(a[i]), 1.0).reshape(-1)
+        if apply.any():
+            x = ops.warp_affine_cubic(x, mats, apply)
+        return x, angles
 
     def _rotate(self, x: torch.Tensor, lines: torch.Tensor, nlines: torch.Tensor):
         """Host median / gating (image_preprocessing.py:414-439) + one warp launch.  The only

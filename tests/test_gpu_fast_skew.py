@@ -53,3 +53,21 @@ def test_deskew_fast_applies_the_reference_gates_and_warp(oracle, cuda):
             assert angles[i] == a
             M = oracle.rotation_matrix(x.shape[2] // 2, x.shape[1] // 2, a, 1.0)
             assert np.array_equal(out[i].cpu().numpy(), oracle.warp_affine_cubic(xs[i], M))
+
+
+def test_page_pipeline_fast_mode_is_flag_gated_and_consistent(oracle, cuda):
+    import torch
+    from ocr_system_b200 import ops
+    from ocr_system_b200.pipeline import PagePipeline
+
+    assert PagePipeline().deskew_mode == "exact"
+    with pytest.raises(ValueError):
+        PagePipeline(deskew_mode="approximate")
+    batches = [ops.synth_pages(4, 1200, 860, seed0=10 * b, device=cuda) for b in range(3)]
+    pipe = PagePipeline(max_dimension=600, deskew_mode="fast", device=cuda)
+    seq = [pipe.run_device(b) for b in batches]
+    for i, res in enumerate(pipe.run_device_stream(batches)):
+        assert np.array_equal(res.angles, seq[i].angles)
+        assert torch.equal(res.pages, seq[i].pages) and torch.equal(res.binary, seq[i].binary)
+        want, wangles = ops.deskew_fast(ops.resize_if_needed(batches[i], 600))
+        assert np.array_equal(res.angles, wangles) and torch.equal(res.pages, want)
