@@ -247,6 +247,19 @@ def cpu_ctc_rate(repeats: int = 10, crops_per_task: int = 32):
                              f"{crops_per_task} crops per task, NumPy argmax/max + Python collapse (upstream CTCLabelDecode)")
 
 
+def _chain_kind():
+    from oracle import reference_port as RP
+
+    return RP.kind()
+
+
+def _chain_kind_note():
+    if _chain_kind() == "reference":
+        return ("oracle/_ref/image_preprocessing.py = the reference's own module (unmodified copy placed by "
+                "oracle/make_ref.py), its ImagePreprocessor methods called in the bench chain's order")
+    return "oracle/reference_port.py = the reference's Pillow/OpenCV call sequence"
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -264,10 +277,9 @@ def main_reference(args):
                                   "note": f"same page-tasks starting from the page's JPEG file (quality {JPEG_Q}): the "
                                           "reference's load_image_bytes (Pillow decode) + the chain"}
         return dict(base, metric=METRIC, value=rate, unit=UNIT, ms_per_step=dt * 1e3, dtype="u8", config=_workload2(args),
-                    cpu_baseline={"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    cpu_baseline={"value": rate, "unit": UNIT, "cores": cores, "kind": _chain_kind(),
                                   "sample": f"{sample} synthetic A4 pages per step, one page per task, "
-                                            f"multiprocessing.Pool({cores}), cv2.setNumThreads(1); "
-                                            "oracle/reference_port.py = the reference's Pillow/OpenCV call sequence"},
+                                            f"multiprocessing.Pool({cores}), cv2.setNumThreads(1); " + _chain_kind_note()},
                     e2e={"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
 
     def db_line():
@@ -294,7 +306,7 @@ def main_reference(args):
         return dict(base, metric=METRIC, value=rate, unit=UNIT, ms_per_step=64e3 / rate, dtype="u8",
                     config=_workload5(args, args.stream_pages),
                     cpu_baseline={"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                  "sample": f"extrapolated from bounded samples: chain {r2:.1f} pages/s on {sample} pages; "
+                                  "sample": f"(chain leg: kind {_chain_kind()}) extrapolated from bounded samples: chain {r2:.1f} pages/s on {sample} pages; "
                                             f"DB {r3:.1f} maps/s ({s3}); CTC {r4:.0f} crops/s ({s4}); {cpp} crops per page"},
                     e2e={"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
 
@@ -622,10 +634,9 @@ def bench_chain(cx: Ctx):
         sample = args.cpu_sample or 8 * (os.cpu_count() or 1)
         rate, dt, cores = cpu_reference_rate(sample, args.max_dim, steps=3, warmup=1)
         line["cpu_baseline"] = {
-            "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "value": rate, "unit": UNIT, "cores": cores, "kind": _chain_kind(),
             "sample": f"{sample} synthetic A4 page-tasks x 3 runs ({dt:.1f} s each, ~{dt * cores:.0f} core-s), one page per task on "
-                      f"multiprocessing.Pool({cores}), cv2.setNumThreads(1); oracle/reference_port.py = "
-                      "the reference's own Pillow/OpenCV call sequence",
+                      f"multiprocessing.Pool({cores}), cv2.setNumThreads(1); " + _chain_kind_note(),
         }
     return line
 

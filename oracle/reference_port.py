@@ -24,6 +24,49 @@ except ImportError:  # pragma: no cover
 from PIL import Image, ImageEnhance, ImageFilter, ImageOps
 
 
+_REAL = None
+
+
+def real_preprocessor():
+    """The reference's own ImagePreprocessor from oracle/_ref/ (placed there by oracle/make_ref.py when the reference
+    tree is present), or None.  When it exists the timed page chain below calls ITS methods (kind "reference")."""
+    global _REAL
+    if _REAL is None:
+        import importlib.util
+        import logging
+        import os
+        import sys
+
+        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+        path = os.path.join(here, "image_preprocessing.py")
+        if not os.path.exists(path):
+            _REAL = False
+        else:
+            saved = sys.modules.get("config")
+            spec_c = importlib.util.spec_from_file_location("config", os.path.join(here, "config.py"))
+            cfg = importlib.util.module_from_spec(spec_c)
+            spec_c.loader.exec_module(cfg)
+            sys.modules["config"] = cfg
+            try:
+                spec = importlib.util.spec_from_file_location("_lumina_reference_image_preprocessing", path)
+                mod = importlib.util.module_from_spec(spec)
+                sys.dont_write_bytecode = True
+                spec.loader.exec_module(mod)
+                logging.getLogger(mod.__name__).setLevel(logging.WARNING)   # the module logs every call at INFO
+                mod.logger.setLevel(logging.WARNING)
+                _REAL = mod
+            finally:
+                if saved is not None:
+                    sys.modules["config"] = saved
+                else:
+                    sys.modules.pop("config", None)
+    return _REAL or None
+
+
+def kind() -> str:
+    return "reference" if real_preprocessor() is not None else "port"
+
+
 def resize_if_needed(image: Image.Image, max_dim: int) -> Image.Image:
     """:81-110"""
     width, height = image.size
@@ -134,6 +177,19 @@ def page_chain(page, max_dim: int = 960, enhance: bool = False):
     [load_image_bytes when `page` is an encoded file] -> resize -> deskew -> [contrast 1.2, sharpness 1.1] ->
     gray -> adaptive binarize -> det normalize.
     Returns (deskewed RGB u8, angle, gray u8, binary u8, normalized CHW f32)."""
+    real = real_preprocessor()
+    if real is not None:   # the reference's own code (oracle/_ref), same call sequence
+        ip = real.ImagePreprocessor(max_dimension=max_dim)
+        img = ip.load_image_bytes(page) if isinstance(page, (bytes, bytearray)) else Image.fromarray(page)
+        img = ip.resize_if_needed(img)
+        img, angle = ip.deskew(img)
+        if enhance:
+            img = ip.enhance_sharpness(ip.enhance_contrast(img, 1.2), 1.1)
+        gray = ip.convert_to_grayscale(img)
+        binary = ip.adaptive_binarize(img)
+        rgb = np.asarray(img)
+        norm, _ = det_resize_normalize(rgb, 960)   # upstream PaddleOCR op: not in the reference
+        return rgb, angle, np.asarray(gray), np.asarray(binary), norm
     img = load_image_bytes(page) if isinstance(page, (bytes, bytearray)) else Image.fromarray(page)
     img = resize_if_needed(img, max_dim)
     img, angle = deskew(img)
