@@ -589,6 +589,49 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_cand_score_kernel(const DbPa
 
 // ---- 5d. unclip + second min-area quad (one THREAD per candidate, offset polygon in shared memory) ------------
 constexpr int DB_UNCLIP_THREADS = 32;
+constexpr int DB_OFFS_SMALL = 64;   // offset polygons of ordinary text boxes have 12-40 vertices
+
+// unclip of one candidate with the offset polygon in `offs` (room for max_pts) and its hull in `offs_hull`.
+// Returns 1 accepted (box written), 0 rejected, -1 the polygon does not fit max_pts.
+__device__ __forceinline__ int db_unclip_one(const DbParams &p, int page, int *tb, DbgPt *offs, DbgPt *offs_hull, int max_pts) {
+    const float *qf = reinterpret_cast<const float *>(tb);
+    DbgPtF b4[4];
+    for (int i = 0; i < 4; i++) { b4[i].x = qf[i * 2]; b4[i].y = qf[i * 2 + 1]; }
+    const double dist = dbg_unclip_distance(b4, p.unclip_ratio);
+    if (!(dist >= 0)) return 0;
+    const int m = dbg_clipper_offset(b4, dist, offs, max_pts);
+    if (m < 0) return -1;
+    if (m < 3) return 0;
+    dbg_sort(offs, m);
+    const int hn = dbg_hull_sorted(offs, m, offs_hull);
+    const DbgRect r2 = dbg_min_area_rect(offs_hull, hn);
+    DbgPtF o2[4];
+    const float ss2 = dbg_mini_box(r2, o2);
+    if (ss2 < (float)(p.min_size + 2)) return 0;
+    const double dw = (double)p.src_hw[page * 2 + 1], dh = (double)p.src_hw[page * 2];
+    int outq[8];
+    for (int i = 0; i < 4; i++) {
+        outq[i * 2] = dbg_scale_coord(o2[i].x, p.w, dw);
+        outq[i * 2 + 1] = dbg_scale_coord(o2[i].y, p.h, dh);
+    }
+    for (int i = 0; i < 8; i++) tb[i] = outq[i];
+    return 1;
+}
+
+// first pass: per-thread buffers for DB_OFFS_SMALL vertices in local memory (no shared memory: full occupancy);
+// a candidate whose polygon is larger keeps state 4 for the second pass
+__global__ void __launch_bounds__(128) db_cand_unclip_small_kernel(const DbParams p) {
+    const int page = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= p.ncand[page * 2 + 1]) return;
+    uint8_t *acc = p.accept + (size_t)page * p.maxc + slot;
+    if (*acc != 4) return;
+    DbgPt offs[DB_OFFS_SMALL + 2], offs_hull[DB_OFFS_SMALL + 2];
+    const int r = db_unclip_one(p, page, p.tmpbox + ((size_t)page * p.maxc + slot) * 8, offs, offs_hull, DB_OFFS_SMALL);
+    if (r >= 0) *acc = r ? 1 : 13;
+}
+
+// second pass (rare): polygons of up to DB_OFFS_MAX vertices, buffers in shared memory
 __global__ void __launch_bounds__(DB_UNCLIP_THREADS) db_cand_unclip_kernel(const DbParams p) {
     extern __shared__ __align__(16) unsigned char db_smem[];
     DbgPt *offs = reinterpret_cast<DbgPt *>(db_smem) + (size_t)threadIdx.x * 2 * (DB_OFFS_MAX + 2);
@@ -598,37 +641,8 @@ __global__ void __launch_bounds__(DB_UNCLIP_THREADS) db_cand_unclip_kernel(const
     if (slot >= p.ncand[page * 2 + 1]) return;
     uint8_t *acc = p.accept + (size_t)page * p.maxc + slot;
     if (*acc != 4) return;
-    int *tb = p.tmpbox + ((size_t)page * p.maxc + slot) * 8;
-    const float *qf = reinterpret_cast<const float *>(tb);
-    DbgPtF b4[4];
-    for (int i = 0; i < 4; i++) { b4[i].x = qf[i * 2]; b4[i].y = qf[i * 2 + 1]; }
-    int ok = 0;
-    int outq[8];
-    const double dist = dbg_unclip_distance(b4, p.unclip_ratio);
-    if (dist >= 0) {
-        const int m = dbg_clipper_offset(b4, dist, offs, DB_OFFS_MAX);
-        if (m >= 3) {
-            dbg_sort(offs, m);
-            const int hn = dbg_hull_sorted(offs, m, offs_hull);
-            const DbgRect r2 = dbg_min_area_rect(offs_hull, hn);
-            DbgPtF o2[4];
-            const float ss2 = dbg_mini_box(r2, o2);
-            if (!(ss2 < (float)(p.min_size + 2))) {
-                const double dw = (double)p.src_hw[page * 2 + 1], dh = (double)p.src_hw[page * 2];
-                for (int i = 0; i < 4; i++) {
-                    outq[i * 2] = dbg_scale_coord(o2[i].x, p.w, dw);
-                    outq[i * 2 + 1] = dbg_scale_coord(o2[i].y, p.h, dh);
-                }
-                ok = 1;
-            }
-        }
-    }
-    if (ok) {
-        for (int i = 0; i < 8; i++) tb[i] = outq[i];
-        *acc = 1;
-    } else {
-        *acc = 13;
-    }
+    const int r = db_unclip_one(p, page, p.tmpbox + ((size_t)page * p.maxc + slot) * 8, offs, offs_hull, DB_OFFS_MAX);
+    *acc = r == 1 ? 1 : 13;
 }
 
 // ---- 6. ordered compaction of the accepted candidates ------------------------------------
@@ -788,6 +802,8 @@ LUMINA_API int lumina_db_postprocess_ex(const float *d_pred, int n, int h, int w
     {
         const size_t smem = (size_t)DB_UNCLIP_THREADS * 2 * (DB_OFFS_MAX + 2) * sizeof(DbgPt);
         LUMINA_CUDA_TRY(cudaFuncSetAttribute(db_cand_unclip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        db_cand_unclip_small_kernel<<<dim3(div_up(max_candidates, 128), n), 128, 0, st>>>(p);
+        LUMINA_KERNEL_CHECK("db_cand_unclip_small_kernel");
         db_cand_unclip_kernel<<<dim3(div_up(max_candidates, DB_UNCLIP_THREADS), n), DB_UNCLIP_THREADS, smem, st>>>(p);
         LUMINA_KERNEL_CHECK("db_cand_unclip_kernel");
     }

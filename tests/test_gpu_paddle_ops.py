@@ -120,3 +120,22 @@ def test_ctc_label_decode_strings(cuda, oracle):
         conf = float(np.mean(mx[b][sel])) if sel.any() else 0.0
         assert out[b][0].encode("utf-8") == text.encode("utf-8")
         assert abs(out[b][1] - conf) <= 1e-4
+
+
+def test_db_postprocess_large_boxes_take_the_second_unclip_pass(cuda):
+    """A box whose Clipper offset polygon has more than 64 vertices (large unclip distance) is handled by the
+    shared-memory pass; ordinary boxes on the same map by the local-memory pass."""
+    from ocr_system_b200.paddle_ops import DBPostProcess
+    from oracle import db_post as D
+
+    h = w = 960
+    m = np.zeros((h, w), np.float32)
+    m[40:760, 30:930] = 0.9            # 900 x 720: distance ~300 px -> > 64 offset vertices
+    m[800:830, 100:400] = 0.85         # ordinary text line
+    m[860:900, 500:900] = 0.95
+    kw = dict(thresh=0.3, box_thresh=0.6, unclip_ratio=1.5)
+    ref = D.DBPostProcess(**kw)({"maps": m[None, None]}, [(h, w, 1.0, 1.0)], with_scores=True)
+    got = DBPostProcess(**kw)({"maps": m[None, None]}, [(h, w, 1.0, 1.0)], with_scores=True)
+    assert len(ref[0]["points"]) == 3
+    assert np.array_equal(got[0]["points"], ref[0]["points"])
+    assert np.abs(got[0]["scores"] - ref[0]["scores"]).max() <= 1e-4
