@@ -199,7 +199,6 @@ JD_HD JdSubResult jd_decode_sub(const JdPageHdr &pg, const JdHuff *tabs, const u
     for (uint32_t i = 0; i < bpm; i++) slotmap |= (unsigned long long)(pg.slot_dc[i] | (pg.slot_ac[i] << 4)) << (8 * i);
     uint32_t tsel = (uint32_t)(slotmap >> (8 * slot));
     const JdHuff *t_dc = tabs + (tsel & 15u), *t_ac = tabs + ((tsel >> 4) & 15u);
-    uint32_t mcu = WRITE ? (uint32_t)(blk0 - (int32_t)slot) / bpm : 0u; /* MCU of the current block */
     while (p < end_bit) {
         const uint32_t v = bits.peek32(p);
         const bool is_dc = k == 0;
@@ -220,7 +219,6 @@ JD_HD JdSubResult jd_decode_sub(const JdPageHdr &pg, const JdHuff *tabs, const u
             abs_base = ri * blocks_per_interval;
             nb = 0;
             blk = abs_base;
-            mcu = (uint32_t)ri * pg.restart_interval;
             tsel = (uint32_t)slotmap;
             t_dc = tabs + (tsel & 15u);
             t_ac = tabs + ((tsel >> 4) & 15u);
@@ -231,7 +229,12 @@ JD_HD JdSubResult jd_decode_sub(const JdPageHdr &pg, const JdHuff *tabs, const u
             const int val = s ? jd_extend((v << len) >> (32 - s), (int)s) : 0;
             k += r;
             if (WRITE && blk < nblk_total) {
-                if (is_dc) dcdiff[pg.slot_dcbase[slot] + mcu * pg.slot_cnt[slot]] = (int16_t)val;
+                if (is_dc) {
+                    /* index from the block number alone, so that a corrupt stream (block number and slot out of
+                     * step) can never write outside the page's DC array */
+                    const uint32_t m = (uint32_t)blk / bpm, sl = (uint32_t)blk - m * bpm;
+                    dcdiff[pg.slot_dcbase[sl] + m * pg.slot_cnt[sl]] = (int16_t)val;
+                }
                 else coef[(size_t)blk * 64 + (k < 64 ? zz[k] : 63)] = (int16_t)val;
             }
             k++;
@@ -242,7 +245,7 @@ JD_HD JdSubResult jd_decode_sub(const JdPageHdr &pg, const JdHuff *tabs, const u
             k = 0;
             nb++;
             blk++;
-            if (++slot == bpm) slot = 0, mcu++;
+            if (++slot == bpm) slot = 0;
             tsel = (uint32_t)(slotmap >> (8 * slot));
             t_dc = tabs + (tsel & 15u);
             t_ac = tabs + ((tsel >> 4) & 15u);
