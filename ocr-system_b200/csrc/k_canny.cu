@@ -117,6 +117,140 @@ __global__ void __launch_bounds__(256) canny_final_kernel(const uint8_t *__restr
     edges[g] = e;
 }
 
+// ---- 4 pixels per thread (any width; needs h*w % 4 == 0 so that pages start on a word) -------------------------
+// The batch is one flat pixel stream; a thread owns 4 consecutive pixels (one 32-bit map load, one 128-bit label
+// load / store).  Row runs are formed inside flat 32-pixel segments (8 lanes assemble the segment's bits with three
+// xor-shuffles); a row start breaks a run.  Only the ~14 % non-suppressed pixels touch labels at all.
+__device__ __forceinline__ uint32_t canny_fg4(uint32_t wv) {   // bit k = (byte k & 3) != 1
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r |= ((((wv >> (8 * k)) & 3u) != 1u) ? 1u : 0u) << k;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) canny_init4_kernel(const uint8_t *__restrict__ map, int *__restrict__ labels, int w,
+                                                          long long hw, long long total_groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = g < total_groups;
+    const long long gidx = g * 4;                       // flat pixel index over the batch
+    const int pidx0 = in ? (int)(gidx % hw) : 0;        // page-relative index of the first pixel
+    uint32_t fg = 0, brk = 0;
+    if (in) {
+        fg = canny_fg4(*reinterpret_cast<const uint32_t *>(map + gidx));
+        int x = pidx0 % w;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (x == 0) brk |= 1u << k;
+            if (++x == w) x = 0;
+        }
+    }
+    const int sub = (int)(g & 7);
+    uint32_t sfg = fg << (4 * sub), sbrk = brk << (4 * sub);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        sfg |= __shfl_xor_sync(0xffffffffu, sfg, o);
+        sbrk |= __shfl_xor_sync(0xffffffffu, sbrk, o);
+    }
+    if (!in) return;
+    // run starts: position 0, a row start, or the pixel behind a suppressed one
+    const uint32_t starts = (~sfg << 1) | 1u | sbrk;
+    int out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int pos = 4 * sub + k;
+        if ((sfg >> pos) & 1u) {
+            const uint32_t below = starts & ((2u << pos) - 1u);
+            const int start = 31 - __clz(below);
+            out[k] = pidx0 + k - (pos - start);
+        } else {
+            out[k] = -1;
+        }
+    }
+    *reinterpret_cast<int4 *>(labels + gidx) = make_int4(out[0], out[1], out[2], out[3]);
+}
+
+__global__ void __launch_bounds__(256) canny_merge4_kernel(const uint8_t *__restrict__ map, int *__restrict__ labels, int h,
+                                                           int w, long long hw, long long total_groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_groups) return;
+    const long long gidx = g * 4;
+    const uint32_t fg = canny_fg4(*reinterpret_cast<const uint32_t *>(map + gidx));
+    if (!fg) return;
+    const long long page = gidx / hw;
+    const int pidx0 = (int)(gidx - page * hw);
+    const uint8_t *M = map + page * hw;
+    int *L = labels + page * hw;
+    const bool seg_start = (g & 7) == 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (!((fg >> k) & 1u)) continue;
+        const int idx = pidx0 + k;
+        const int y = idx / w, x = idx - y * w;
+        const bool left_fg = x > 0 && (k > 0 ? ((fg >> (k - 1)) & 1u) != 0u : (M[idx - 1] & 3) != 1);
+        // runs are pre-linked inside a flat 32-pixel segment: the left link is due only at its first pixel
+        if (k == 0 && seg_start && left_fg) ccl_union(L, idx, idx - 1);
+        if (y > 0) {
+            const int up = idx - w;
+            if ((M[up] & 3) != 1) {
+                const bool upleft_fg = x > 0 && (M[up - 1] & 3) != 1;
+                if (!(left_fg && upleft_fg)) ccl_union(L, idx, up);
+            } else {
+                if (x > 0 && (M[up - 1] & 3) != 1) ccl_union(L, idx, up - 1);
+                if (x + 1 < w && (M[up + 1] & 3) != 1) ccl_union(L, idx, up + 1);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) canny_flatten4_kernel(uint8_t *__restrict__ map, int *__restrict__ labels, long long hw,
+                                                             long long total_groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_groups) return;
+    const long long gidx = g * 4;
+    const int4 lv = *reinterpret_cast<const int4 *>(labels + gidx);
+    if (lv.x < 0 && lv.y < 0 && lv.z < 0 && lv.w < 0) return;   // all suppressed
+    const long long page = gidx / hw;
+    const int pidx0 = (int)(gidx - page * hw);
+    uint8_t *mp = map + page * hw;
+    int *L = labels + page * hw;
+    const uint32_t mw = *reinterpret_cast<const uint32_t *>(map + gidx);
+    const int lab[4] = {lv.x, lv.y, lv.z, lv.w};
+    int out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        out[k] = lab[k];
+        if (lab[k] < 0) continue;
+        if (k > 0 && lab[k] == lab[k - 1]) out[k] = out[k - 1];
+        else {
+            int a = lab[k], p = a == pidx0 + k ? a : L[a];
+            while (p != a) { a = p; p = L[a]; }
+            out[k] = a;
+        }
+        if (((mw >> (8 * k)) & 3u) == 2u) {   // strong pixel: raise the flag on the root (same value from every writer)
+            const uint8_t rv = mp[out[k]];
+            if (!(rv & 4)) mp[out[k]] = (uint8_t)((rv & 3) | 4);
+        }
+    }
+    *reinterpret_cast<int4 *>(labels + gidx) = make_int4(out[0], out[1], out[2], out[3]);
+}
+
+__global__ void __launch_bounds__(256) canny_final4_kernel(const uint8_t *__restrict__ map, const int *__restrict__ labels,
+                                                           uint8_t *__restrict__ edges, long long hw, long long total_groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_groups) return;
+    const long long gidx = g * 4;
+    const int4 lv = *reinterpret_cast<const int4 *>(labels + gidx);
+    const int lab[4] = {lv.x, lv.y, lv.z, lv.w};
+    uint32_t e = 0;
+    if (lv.x >= 0 || lv.y >= 0 || lv.z >= 0 || lv.w >= 0) {
+        const uint8_t *mp = map + (gidx / hw) * hw;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (lab[k] >= 0 && (mp[lab[k]] & 4)) e |= 0xFFu << (8 * k);
+    }
+    *reinterpret_cast<uint32_t *>(edges + gidx) = e;
+}
+
 }  // namespace lumina
 
 using namespace lumina;
@@ -144,6 +278,20 @@ LUMINA_API int lumina_canny_u8(const uint8_t *d_src, uint8_t *d_edges, int n, in
     if (c == 3) canny_nms_kernel<3><<<grid, 256, 0, st>>>(d_src, map, h, w, low, high);
     else canny_nms_kernel<1><<<grid, 256, 0, st>>>(d_src, map, h, w, low, high);
     LUMINA_KERNEL_CHECK("canny_nms_kernel");
+    const long long hw = (long long)h * w;
+    if ((hw & 3) == 0 && (((uintptr_t)d_edges) & 3) == 0) {
+        const long long groups = (long long)px / 4;
+        const unsigned gg = (unsigned)((groups + 255) / 256);
+        canny_init4_kernel<<<gg, 256, 0, st>>>(map, labels, w, hw, groups);
+        LUMINA_KERNEL_CHECK("canny_init4_kernel");
+        canny_merge4_kernel<<<gg, 256, 0, st>>>(map, labels, h, w, hw, groups);
+        LUMINA_KERNEL_CHECK("canny_merge4_kernel");
+        canny_flatten4_kernel<<<gg, 256, 0, st>>>(map, labels, hw, groups);
+        LUMINA_KERNEL_CHECK("canny_flatten4_kernel");
+        canny_final4_kernel<<<gg, 256, 0, st>>>(map, labels, d_edges, hw, groups);
+        LUMINA_KERNEL_CHECK("canny_final4_kernel");
+        return LUMINA_OK;
+    }
     CannyFG fg{map};
     const long long nseg = (long long)n * h * ((w + 31) / 32);
     LUMINA_REQUIRE(nseg < (1LL << 31), "batch too large");
@@ -152,9 +300,9 @@ LUMINA_API int lumina_canny_u8(const uint8_t *d_src, uint8_t *d_edges, int n, in
     const unsigned gpx = (unsigned)((px + 255) / 256);
     ccl_merge_kernel<CannyFG><<<gpx, 256, 0, st>>>(fg, labels, h, w, (long long)px);
     LUMINA_KERNEL_CHECK("ccl_merge_kernel<canny>");
-    canny_flatten_kernel<<<gpx, 256, 0, st>>>(map, labels, (long long)h * w, (long long)px);
+    canny_flatten_kernel<<<gpx, 256, 0, st>>>(map, labels, hw, (long long)px);
     LUMINA_KERNEL_CHECK("canny_flatten_kernel");
-    canny_final_kernel<<<gpx, 256, 0, st>>>(map, labels, d_edges, (long long)h * w, (long long)px);
+    canny_final_kernel<<<gpx, 256, 0, st>>>(map, labels, d_edges, hw, (long long)px);
     LUMINA_KERNEL_CHECK("canny_final_kernel");
     return LUMINA_OK;
 }

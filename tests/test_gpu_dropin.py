@@ -356,3 +356,33 @@ def test_preprocess_pages_for_azure_decodes_jpeg_bytes_on_the_device(oracle, cud
     for i, f in enumerate(files):
         want = ip_.preprocess_for_azure(Image.open(io.BytesIO(f)), target_size_mb=0.2)
         assert got[i] == want, i
+
+
+def test_tiff_and_png_files_take_the_host_codec_and_match_the_reference_sequence(oracle, cuda, tmp_path):
+    """load_image (image_preprocessing.py:57-68) on TIFF / PNG paths -- the formats north_star's "PDF/TIFF page rasters"
+    arrive in (uncompressed, LZW and Group-4 TIFF; PNG is what pdf_to_images asks poppler for): decoded by the host
+    codec exactly as in the reference, then the device chain; result == the reference call sequence on the same file."""
+    import io
+
+    from PIL import Image
+
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+    from oracle import reference_port as RP
+
+    ip_ = ImagePreprocessor(max_dimension=600)
+    page = oracle.synth_page(1000, 720, 77)
+    cases = [("a.tif", dict()), ("b.tif", dict(compression="tiff_lzw")), ("c.png", dict()),
+             ("d.tif", dict(compression="group4"))]
+    for name, kw in cases:
+        im = Image.fromarray(page)
+        if kw.get("compression") == "group4":
+            im = im.convert("1")                      # bilevel fax page: load_image converts it to RGB
+        path = tmp_path / name
+        im.save(path, **kw)
+        loaded = ip_.load_image(path)
+        assert loaded.mode in ("RGB", "L")
+        ref_in = Image.open(path)
+        ref_in = ref_in if ref_in.mode in ("RGB", "L") else ref_in.convert("RGB")
+        want = RP.preprocess_for_azure(np.asarray(ref_in), max_dim=600, target_size_mb=0.2)
+        assert ip_.preprocess_for_azure(path, target_size_mb=0.2) == want, name
+        assert ip_.preprocess_pages_for_azure([path, path.read_bytes()], target_size_mb=0.2) == [want, want], name
