@@ -152,7 +152,7 @@ int lumina_warp_affine_cubic_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int
 /* NOT what the reference computes (:402-428 HoughLinesP + median): a tolerance-certified estimate of the same
  * angle (degrees, sign as the reference: positive = text descends to the right) from the Canny edge maps
  * [n][h][w]; the caller applies the reference's gates (:433-439) and rotation.  d_angles [n] f64. */
-size_t lumina_skew_workspace_bytes(int n);
+size_t lumina_skew_workspace_bytes_for(int n, int h, int w);
 int lumina_skew_estimate_fast(const uint8_t *d_edges, int n, int h, int w, double *d_angles, void *d_workspace,
                               size_t workspace_bytes, void *stream);
 

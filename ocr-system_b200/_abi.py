@@ -57,7 +57,7 @@ PROTOTYPES = {
     "lumina_rotation_matrix_host": (None, [_D, _D, _D, _D, _P]),
     "lumina_warp_affine_cubic_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "lumina_det_target_size": (None, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
-    "lumina_skew_workspace_bytes": (_Z, [_I]),
+    "lumina_skew_workspace_bytes_for": (_Z, [_I, _I, _I]),
     "lumina_skew_estimate_fast": (_I, [_P, _I, _I, _I, _P, _P, _Z, _P]),
     "lumina_otsu_u8": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "lumina_sauvola_u8": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _P]),

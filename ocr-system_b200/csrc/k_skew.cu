@@ -32,8 +32,24 @@ __device__ int sk_argmax(const unsigned long long *s, int n) {
     return b;
 }
 
-// fine == 0: coarse angles; fine == 1: angles around the coarse maximum of `coarse_scores`
-__global__ void __launch_bounds__(256) skew_profile_kernel(const uint8_t *__restrict__ edges, int h, int w, int fine,
+// edge map -> one bit per pixel, rows padded to whole 32-bit words (one warp per word)
+__global__ void __launch_bounds__(256) skew_bitmask_kernel(const uint8_t *__restrict__ edges, uint32_t *__restrict__ bits, int w,
+                                                           int wpr, long long total_words) {
+    const long long word = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (word >= total_words) return;
+    const int lane = threadIdx.x & 31;
+    const long long row = word / wpr;                 // global row over the batch
+    const int x = (int)(word - row * wpr) * 32 + lane;
+    const bool e = x < w && edges[row * w + x] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, e);
+    if (lane == 0) bits[word] = m;
+}
+
+// fine == 0: coarse angles; fine == 1: angles around the coarse maximum of `coarse_scores`.
+// A warp walks tiles of 32 rows x 32 columns, one row per lane (one 32-bit word of the bitmask): the lanes of a
+// warp then hit different profile bins (bin ~ row for small angles), so the shared-memory atomics do not collide,
+// and the pixels of a lane's segment that fall into the same bin are counted in registers first.
+__global__ void __launch_bounds__(256) skew_profile_kernel(const uint32_t *__restrict__ bits, int h, int w, int wpr, int fine,
                                                            const unsigned long long *__restrict__ coarse_scores,
                                                            unsigned long long *__restrict__ scores) {
     extern __shared__ unsigned int sk_prof[];     // [4][nbins]
@@ -55,32 +71,40 @@ __global__ void __launch_bounds__(256) skew_profile_kernel(const uint8_t *__rest
         sn[k] = (float)sin(rad);
     }
     __syncthreads();
-    const uint8_t *E = edges + (size_t)page * h * w;
-    const int px = h * w;
-    const bool vec = (((uintptr_t)E) & 15) == 0;
-    const int nvec = vec ? px / 16 : 0;
-    for (int v = threadIdx.x; v < nvec; v += 256) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(E) + v);
-        if ((q.x | q.y | q.z | q.w) == 0u) continue;
-        const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-        const int base = v * 16;
+    const uint32_t *B = bits + (size_t)page * h * wpr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles_y = (h + 31) >> 5, ntiles = tiles_y * wpr;
+    // the coarse pass only has to find the right half-degree cell: it looks at every fourth 32-pixel COLUMN band
+    // (whole rows of bins stay populated; cutting row bands instead would favour 0 degrees, where the cut is a bin edge)
+    const int tx_step = fine ? 1 : 4;
+    for (int t = warp; t < ntiles; t += 8) {
+        const int ty = t / wpr, tx = t - ty * wpr;
+        if (tx % tx_step) continue;
+        const int y = ty * 32 + lane;
+        uint32_t m = y < h ? __ldg(B + (size_t)y * wpr + tx) : 0u;
+        if (!m) continue;
+        const float fy = (float)y;
+        int cur[SK_ANGLES_PER_CTA], cnt[SK_ANGLES_PER_CTA];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if (!((wv[j >> 2] >> (8 * (j & 3))) & 255u)) continue;
-            const int idx = base + j;
-            const int y = idx / w, x = idx - y * w;
-            const float fx = (float)x, fy = (float)y;
+        for (int k = 0; k < SK_ANGLES_PER_CTA; k++) { cur[k] = -1; cnt[k] = 0; }
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float fx = (float)(tx * 32 + j);
 #pragma unroll
-            for (int k = 0; k < SK_ANGLES_PER_CTA; k++)
-                atomicAdd(&sk_prof[k * nbins + __float2int_rn(fy * cs[k] - fx * sn[k]) + off], 1u);
+            for (int k = 0; k < SK_ANGLES_PER_CTA; k++) {
+                const int b = __float2int_rn(fy * cs[k] - fx * sn[k]) + off;
+                if (b != cur[k]) {
+                    if (cnt[k]) atomicAdd(&sk_prof[k * nbins + cur[k]], (unsigned int)cnt[k]);
+                    cur[k] = b;
+                    cnt[k] = 0;
+                }
+                cnt[k]++;
+            }
         }
-    }
-    for (int idx = nvec * 16 + threadIdx.x; idx < px; idx += 256) {
-        if (!E[idx]) continue;
-        const int y = idx / w, x = idx - y * w;
 #pragma unroll
         for (int k = 0; k < SK_ANGLES_PER_CTA; k++)
-            atomicAdd(&sk_prof[k * nbins + __float2int_rn((float)y * cs[k] - (float)x * sn[k]) + off], 1u);
+            if (cnt[k]) atomicAdd(&sk_prof[k * nbins + cur[k]], (unsigned int)cnt[k]);
     }
     __syncthreads();
     __shared__ unsigned long long s_part[8];
@@ -95,9 +119,9 @@ __global__ void __launch_bounds__(256) skew_profile_kernel(const uint8_t *__rest
         if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
         __syncthreads();
         if (threadIdx.x == 0 && a0 + k < nang) {
-            unsigned long long t = 0;
-            for (int i = 0; i < 8; i++) t += s_part[i];
-            scores[(size_t)page * nang + a0 + k] = t;
+            unsigned long long tt = 0;
+            for (int i = 0; i < 8; i++) tt += s_part[i];
+            scores[(size_t)page * nang + a0 + k] = tt;
         }
         __syncthreads();
     }
@@ -123,22 +147,31 @@ __global__ void skew_angle_kernel(const unsigned long long *__restrict__ coarse,
 
 using namespace lumina;
 
-LUMINA_API size_t lumina_skew_workspace_bytes(int n) { return n > 0 ? (size_t)n * (SK_COARSE + SK_FINE) * 8 + 256 : 0; }
+static size_t sk_scores_bytes(int n) { return ((size_t)n * (SK_COARSE + SK_FINE) * 8 + 255) & ~(size_t)255; }
+
+LUMINA_API size_t lumina_skew_workspace_bytes_for(int n, int h, int w) {
+    return n > 0 && h > 0 && w > 0 ? sk_scores_bytes(n) + (size_t)n * h * ((w + 31) / 32) * 4 + 256 : 0;
+}
 
 LUMINA_API int lumina_skew_estimate_fast(const uint8_t *d_edges, int n, int h, int w, double *d_angles, void *d_workspace,
                                          size_t workspace_bytes, void *stream) {
     LUMINA_REQUIRE(d_edges && d_angles && d_workspace, "null pointer");
     LUMINA_REQUIRE(n > 0 && h > 0 && w > 0 && n <= 65535, "bad batch");
-    LUMINA_REQUIRE(workspace_bytes >= lumina_skew_workspace_bytes(n), "skew workspace too small");
+    LUMINA_REQUIRE(workspace_bytes >= lumina_skew_workspace_bytes_for(n, h, w), "skew workspace too small");
     const size_t smem = (size_t)SK_ANGLES_PER_CTA * (h + 2 * w + 3) * 4;
     LUMINA_REQUIRE(smem <= 200 * 1024, "page too large for the shared-memory profiles");
     cudaStream_t st = as_stream(stream);
     unsigned long long *coarse = reinterpret_cast<unsigned long long *>(d_workspace);
     unsigned long long *fine = coarse + (size_t)n * SK_COARSE;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_workspace) + sk_scores_bytes(n));
+    const int wpr = (w + 31) / 32;
+    const long long words = (long long)n * h * wpr;
+    skew_bitmask_kernel<<<(unsigned)((words * 32 + 255) / 256), 256, 0, st>>>(d_edges, bits, w, wpr, words);
+    LUMINA_KERNEL_CHECK("skew_bitmask_kernel");
     LUMINA_CUDA_TRY(cudaFuncSetAttribute(skew_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    skew_profile_kernel<<<dim3(div_up(SK_COARSE, SK_ANGLES_PER_CTA), n), 256, smem, st>>>(d_edges, h, w, 0, nullptr, coarse);
+    skew_profile_kernel<<<dim3(div_up(SK_COARSE, SK_ANGLES_PER_CTA), n), 256, smem, st>>>(bits, h, w, wpr, 0, nullptr, coarse);
     LUMINA_KERNEL_CHECK("skew_profile_kernel");
-    skew_profile_kernel<<<dim3(div_up(SK_FINE, SK_ANGLES_PER_CTA), n), 256, smem, st>>>(d_edges, h, w, 1, coarse, fine);
+    skew_profile_kernel<<<dim3(div_up(SK_FINE, SK_ANGLES_PER_CTA), n), 256, smem, st>>>(bits, h, w, wpr, 1, coarse, fine);
     LUMINA_KERNEL_CHECK("skew_profile_kernel");
     skew_angle_kernel<<<(n + 63) / 64, 64, 0, st>>>(coarse, fine, n, d_angles);
     LUMINA_KERNEL_CHECK("skew_angle_kernel");

@@ -419,7 +419,7 @@ def estimate_skew_fast(edges: torch.Tensor) -> torch.Tensor:
     e = edges.contiguous()
     n, h, w = e.shape
     angles = torch.empty(n, dtype=torch.float64, device=e.device)
-    wsb = int(_L().lumina_skew_workspace_bytes(n))
+    wsb = int(_L().lumina_skew_workspace_bytes_for(n, h, w))
     ws = _ws(wsb, e.device)
     _chk(_L().lumina_skew_estimate_fast(_ptr(e), n, h, w, _ptr(angles), _ptr(ws), wsb, _stream()))
     return angles
