@@ -32,8 +32,22 @@ __global__ void __launch_bounds__(256) ctc_argmax_kernel(const float *__restrict
     if (lane < head) { bv = p[lane]; bi = lane; }
     const int nvec = (c - head) >> 2;
     const float4 *pv = reinterpret_cast<const float4 *>(p + head);
-#pragma unroll 4
-    for (int i = lane; i < nvec; i += 32) {
+    // 8 independent 128-bit loads in flight per lane before the (dependent) compare chain runs
+    int i = lane;
+    for (; i + 7 * 32 < nvec; i += 8 * 32) {
+        uint4 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) u[q] = ldg_stream_u4(pv + i + q * 32);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const float f[4] = {__uint_as_float(u[q].x), __uint_as_float(u[q].y), __uint_as_float(u[q].z), __uint_as_float(u[q].w)};
+            const int base = head + (i + q * 32) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (ctc_better(f[k], base + k, bv, bi)) { bv = f[k]; bi = base + k; }
+        }
+    }
+    for (; i < nvec; i += 32) {
         const uint4 u = ldg_stream_u4(pv + i);
         const float f[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
         const int base = head + i * 4;
