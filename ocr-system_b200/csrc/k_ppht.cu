@@ -597,6 +597,13 @@ __global__ void __launch_bounds__(NW * 32) ppht_main_kernel(const PphtParams p) 
 
 using namespace lumina;
 
+#ifdef LUMINA_PPHT_PROFILE
+// diagnostics build only (tools/ppht_pipe_stats.py): where the per-page statistics live in the workspace
+LUMINA_API size_t lumina_ppht_stats_offset(int n, int h, int w, double rho, double theta) {
+    return ppht_layout(n, h, w, rho, theta).stats_off;
+}
+#endif
+
 LUMINA_API size_t lumina_ppht_workspace_bytes(int n, int h, int w, double rho, double theta) {
     if (n <= 0 || h <= 0 || w <= 0 || !(rho > 0) || !(theta > 0)) return 0;
     return ppht_layout(n, h, w, rho, theta).total;

@@ -108,6 +108,11 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
 
     int buf_lo = 0, buf_hi = 0;
     int nl = 0, n_events = 0, n_batches = 0, n_exch = 0, n_flush = 0;
+#ifdef LUMINA_PPHT_PROFILE
+    long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // control warp: 0 exchange wait, 1 events, 2 snapshot, 3 barrier wait, 4 flush, 9 total
+    long long tc0 = clock64();
+    const long long t_begin = tc0;
+#endif
     __syncthreads();
     cl.sync();
 
@@ -161,7 +166,9 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
                 if (lane == 0) pcl_mbar_expect_tx(bar, (uint32_t)(CS * PCL_B * 4));
                 const uint32_t slot = pcl_smem_u32(&keys[xp][rank][lane]);
                 for (int c = 0; c < CS; c++) pcl_st_async(pcl_mapa(slot, c), key, pcl_mapa(bar, c));
+                PCL_TICK(5);
                 pcl_mbar_wait(bar, (uint32_t)((n_exch >> 1) & 1));
+                PCL_TICK(0);
                 // ---- line events of `cur` (same code path as ppht_cluster_lm_kernel) ----
                 const int nb = nb_cur;
                 const uint32_t mypt = lane < nb ? ordbuf[pos_cur + lane - buf_lo] : 0u;
@@ -290,6 +297,7 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
                     if ((livebits ^ nowlive) & later) { status = 1; break; }
                 }
                 n_exch++;
+                PCL_TICK(1);
             }
             int nxt_ok = 1;
             if (status == 0) {
@@ -301,6 +309,7 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
                 if (nxt_ok) prepare(pos_nxt + nb_nxt, qn ^ 1);   // the batch after `nxt` (parity of `cur`, now free)
             }
             if (lane == 0) { s_status = status; s_ks = ks; s_maxn = max_n; s_nxt_ok = nxt_ok; }
+            PCL_TICK(2);
         } else if (is_row_warp && nb_nxt > 0) {
             // ---- speculative votes of `nxt` from its snapshot ----
             const unsigned livebits = s_live[qn];
@@ -328,6 +337,7 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
             }
         }
         __syncthreads();
+        if (warp == 0) { PCL_TICK(3); }
         const int status = s_status, nxt_ok = s_nxt_ok;
         if (status == 0 && nxt_ok) {
             // commit: `nxt` becomes the batch to judge, the prepared batch becomes `nxt`
@@ -437,12 +447,17 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
         refill(pos_nxt);
         if (warp == 0) prepare(pos_nxt, qn);
         __syncthreads();
+        if (warp == 0) { PCL_TICK(4); }
     }
     cl.sync();
     if (rank == 0 && tid == 0) {
         p.nlines[page] = nl;
         int32_t *st = p.stats + page * 8;
         st[0] = N; st[1] = n_flush; st[2] = n_events; st[3] = nl; st[4] = 2; st[5] = n_batches; st[6] = CS; st[7] = n_exch;
+#ifdef LUMINA_PPHT_PROFILE
+        tph[9] = clock64() - t_begin;
+        for (int i = 0; i < 10; i++) p.stats_ll[page * 10 + i] = tph[i];
+#endif
     }
 }
 
