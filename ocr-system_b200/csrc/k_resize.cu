@@ -33,6 +33,11 @@ struct lumina_resize_plan {
     uint32_t *d_cyp;            // [out_h][3 planes][kyw]            tap t -> byte (ymin & 3) + t  (row-group phase)
     int kxw, kyw;
     int max_seg_px;             // widest input column span of any TOW-column strip
+    // tensor-core path (int8 mma.sync): per 8-column tile the B fragments of the three coefficient byte planes
+    uint32_t *d_bfrag;          // [tiles][ksteps][3 planes][2][32 lanes]
+    int32_t *d_kb;              // [tiles] first staged byte (multiple of 4, relative to the strip's xs16) of the tile's K window
+    int ksteps;                 // K window of a tile in units of 32 input pixels (0: path not available)
+    int imma_span;              // bytes of a staged plane row the A fragments may touch
     int device;
 };
 
@@ -254,6 +259,8 @@ struct ResizeDp4aParams {
     uint8_t *dst;
     const int32_t *bx, *by;
     const uint32_t *cxp, *cyp;
+    const uint32_t *bfrag;
+    const int32_t *kb;
     int in_h, in_w, out_h, out_w, kxw, kyw;
     int rows_per_seg;
     int segpx;         // staged pixels per row and plane (multiple of 16, + slack)
@@ -417,6 +424,189 @@ __global__ void __launch_bounds__(256, 4) resize_strip_dp4a_kernel(const ResizeD
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant of the horizontal pass.  PIL's horizontal resample IS a banded matrix product: 16 staged
+// rows x the K input pixels under an 8-column tile (A, u8, straight from the de-interleaved plane rows in shared
+// memory) times the tile's coefficients (B, the same three byte planes as the dp4a form: two unsigned, one signed),
+// accumulated in int32 -- exact, so the result is the same bytes.  One warp owns one 8-column tile of the strip and
+// issues mma.sync.m16n8k32 (u8 x u8 / u8 x s8 -> s32): KSTEPS x 3 MMAs + 4 x KSTEPS shared-memory loads per channel
+// replace 16 x 8 x (18 dp4a + 6 funnel shifts + 7 loads).  Staging and the vertical pass are the dp4a kernel's.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_u8u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KSTEPS>
+__global__ void __launch_bounds__(256, 4) resize_strip_imma_kernel(const ResizeDp4aParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int ROWB = TOW * 3;
+    uint8_t *inbuf = smem;                                             // [RB][3][segpx]
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + (size_t)RB * 3 * p.segpx);  // [RINGG][ROWB] words of 4 rows
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ox0 = blockIdx.x * TOW;
+    const int oy0 = blockIdx.y * p.rows_per_seg;
+    const int oy1 = min(oy0 + p.rows_per_seg, p.out_h);
+    const int page = blockIdx.z;
+    const size_t pitch = (size_t)p.in_w * 3;
+    const uint8_t *src = p.src + (size_t)page * p.in_h * pitch;
+    uint8_t *dst = p.dst + (size_t)page * p.out_h * p.out_w * 3;
+
+    const int ox_last = min(ox0 + TOW, p.out_w) - 1;
+    const int xs = p.bx[ox0 * 2];
+    const int xe = p.bx[ox_last * 2] + p.bx[ox_last * 2 + 1];
+    const int xs16 = xs & ~15;
+    const int ngroups = (xe - xs16 + 15) >> 4;  // 16-pixel groups staged per row
+    const int ys = p.by[oy0 * 2];
+    const int ye = p.by[(oy1 - 1) * 2] + p.by[(oy1 - 1) * 2 + 1];
+
+    // this warp's 8-column tile: B fragments (3 byte planes x KSTEPS x 2 registers) and the start of its K window
+    const int tile = blockIdx.x * (TOW / 8) + warp;
+    const bool tile_ok = tile * 8 < p.out_w;
+    uint32_t bf[KSTEPS][3][2];
+    int kb = 0;
+    if (tile_ok) {
+        kb = p.kb[tile];
+#pragma unroll
+        for (int st = 0; st < KSTEPS; st++)
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++)
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) bf[st][pl][hf] = p.bfrag[((((size_t)tile * KSTEPS + st) * 3 + pl) * 2 + hf) * 32 + lane];
+    }
+    const int grp = lane >> 2, tq = lane & 3;
+    const uint8_t *src_end = p.src + p.src_total;
+    int next_oy = oy0;
+    __shared__ int s_oy_end;
+
+    for (int r0 = ys; r0 < ye; r0 += RB) {
+        const int nrows = min(RB, ye - r0);
+        // ---- stage + de-interleave: a thread moves 16 pixels (48 B in, 3 x 16 B out) ----
+        for (int t = tid; t < nrows * ngroups; t += 256) {
+            const int r = t / ngroups, g = t - r * ngroups;
+            const uint8_t *gp = src + (size_t)(r0 + r) * pitch + (size_t)(xs16 + g * 16) * 3;
+            uint32_t w[12];
+            if (gp + 48 <= src_end) {
+                const uint4 a = ldg_stream_u4(gp), b = ldg_stream_u4(gp + 16), c = ldg_stream_u4(gp + 32);
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+                w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    uint32_t v = 0;
+                    for (int b = 0; b < 4; b++)
+                        if (gp + i * 4 + b < src_end) v |= (uint32_t)gp[i * 4 + b] << (8 * b);
+                    w[i] = v;
+                }
+            }
+            uint32_t R[4], G[4], B[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+                R[q] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+                G[q] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+                B[q] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+            }
+            uint8_t *sr = inbuf + (size_t)r * 3 * p.segpx + g * 16;
+            *reinterpret_cast<uint4 *>(sr) = make_uint4(R[0], R[1], R[2], R[3]);
+            *reinterpret_cast<uint4 *>(sr + p.segpx) = make_uint4(G[0], G[1], G[2], G[3]);
+            *reinterpret_cast<uint4 *>(sr + 2 * p.segpx) = make_uint4(B[0], B[1], B[2], B[3]);
+        }
+        __syncthreads();
+        // ---- horizontal pass: 16 rows x 8 columns x K per warp on the tensor cores ----
+        if (tile_ok) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                int acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0}, acc2[4] = {0, 0, 0, 0};
+                const uint8_t *r_lo = inbuf + ((size_t)grp * 3 + ch) * p.segpx + kb + tq * 4;
+                const uint8_t *r_hi = inbuf + ((size_t)(grp + 8) * 3 + ch) * p.segpx + kb + tq * 4;
+#pragma unroll
+                for (int st = 0; st < KSTEPS; st++) {
+                    uint32_t af[4];
+                    af[0] = *reinterpret_cast<const uint32_t *>(r_lo + st * 32);
+                    af[1] = *reinterpret_cast<const uint32_t *>(r_hi + st * 32);
+                    af[2] = *reinterpret_cast<const uint32_t *>(r_lo + st * 32 + 16);
+                    af[3] = *reinterpret_cast<const uint32_t *>(r_hi + st * 32 + 16);
+                    mma_u8u8(acc0, af, bf[st][0][0], bf[st][0][1]);
+                    mma_u8u8(acc1, af, bf[st][1][0], bf[st][1][1]);
+                    mma_u8s8(acc2, af, bf[st][2][0], bf[st][2][1]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int row = grp + (i >> 1) * 8;            // row of the chunk
+                    const int col = warp * 8 + tq * 2 + (i & 1);   // column of the strip
+                    if (row < nrows && ox0 + col < p.out_w) {
+                        const int arow = r0 + row;
+                        // exact modulo 2^32; the true sum fits int32
+                        const int acc = (int)((1u << (PREC_BITS - 1)) + (uint32_t)acc0[i] + ((uint32_t)acc1[i] << 8) + ((uint32_t)acc2[i] << 16));
+                        uint32_t *rg = ring + (size_t)((arow >> 2) & (RINGG - 1)) * ROWB + col * 3;
+                        reinterpret_cast<uint8_t *>(rg + ch)[arow & 3] = clip8(acc);
+                    }
+                }
+            }
+        }
+        if (tid == 255) {  // which output rows have their whole tap window in the ring after this chunk
+            const int rows_done = r0 + nrows;
+            int oe = next_oy;
+            while (oe < oy1 && p.by[oe * 2] + p.by[oe * 2 + 1] <= rows_done) oe++;
+            s_oy_end = oe;
+        }
+        __syncthreads();
+        // ---- vertical pass: a thread owns 4 adjacent byte columns of one output row (one 128-bit ring
+        // load per 4 taps x 4 columns, the row's coefficient words shared by the 4 columns) ----
+        const int oy_end = s_oy_end;
+        constexpr int COL4 = ROWB / 4;
+        const int ntask = (oy_end - next_oy) * COL4;
+        const int row_bytes = p.out_w * 3;
+        for (int task = tid; task < ntask; task += 256) {
+            const int orow = task / COL4, c4 = task - orow * COL4;
+            const int oy = next_oy + orow;
+            const int bcol = ox0 * 3 + c4 * 4;
+            if (bcol >= row_bytes) continue;
+            const int ymin = p.by[oy * 2];
+            const uint32_t *k = p.cyp + (size_t)oy * 3 * p.kyw;
+            int s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+            int rgrp = (ymin >> 2) & (RINGG - 1);
+            for (int j = 0; j < p.kyw; j++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(ring + (size_t)rgrp * ROWB + c4 * 4);
+                const uint32_t k0 = __ldg(k + j), k1 = __ldg(k + p.kyw + j), k2 = __ldg(k + 2 * p.kyw + j);
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    s0[q] = (int)__dp4a(vv[q], k0, (uint32_t)s0[q]);
+                    s1[q] = (int)__dp4a(vv[q], k1, (uint32_t)s1[q]);
+                    s2[q] = dp4a_u8s8(vv[q], k2, s2[q]);
+                }
+                rgrp = (rgrp + 1) & (RINGG - 1);
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                o[q] = clip8((int)((1u << (PREC_BITS - 1)) + (uint32_t)s0[q] + ((uint32_t)s1[q] << 8) + ((uint32_t)s2[q] << 16)));
+            uint8_t *dp = dst + (size_t)oy * row_bytes + bcol;
+            if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 3) == 0) {
+                *reinterpret_cast<uint32_t *>(dp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+            } else if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 1) == 0) {
+                *reinterpret_cast<uint16_t *>(dp) = (uint16_t)(o[0] | (o[1] << 8));
+                *reinterpret_cast<uint16_t *>(dp + 2) = (uint16_t)(o[2] | (o[3] << 8));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (bcol + q < row_bytes) dp[q] = (uint8_t)o[q];
+            }
+        }
+        next_oy = oy_end;
+        __syncthreads();
+    }
+}
+
 // one axis only (the other is identity) or tap counts beyond the unrolled
 // variants: plain two-pass kernels through an HBM intermediate.
 template <int C>
@@ -488,6 +678,53 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
         if (span > msp) msp = span;
     }
     pl->max_seg_px = msp;
+    // tensor-core path: per 8-column tile the K window [kb, kb + 32 * ksteps) of staged plane bytes and the B
+    // fragments of mma.m16n8k32 (lane l holds column l >> 2, rows (l & 3) * 4 .. + 3 and the same + 16)
+    pl->d_bfrag = nullptr; pl->d_kb = nullptr; pl->ksteps = 0; pl->imma_span = 0;
+    std::vector<uint32_t> bfrag;
+    std::vector<int32_t> kbv;
+    {
+        const int tiles = (out_w + 7) / 8;
+        kbv.assign(tiles, 0);
+        int maxk = 0, span = 0;
+        for (int t = 0; t < tiles; t++) {
+            const int strip0 = (t * 8 / TOW) * TOW;
+            const int xs16 = bx[strip0 * 2] & ~15;
+            const int kb = (bx[t * 8 * 2] - xs16) & ~3;
+            kbv[t] = kb;
+            for (int n = 0; n < 8 && t * 8 + n < out_w; n++) {
+                const int ox = t * 8 + n;
+                const int need = bx[ox * 2] - xs16 - kb + bx[ox * 2 + 1];
+                maxk = need > maxk ? need : maxk;
+            }
+        }
+        const int ks = (maxk + 31) / 32;
+        if (ks >= 1 && ks <= 3) {
+            pl->ksteps = ks;
+            bfrag.assign((size_t)tiles * ks * 3 * 2 * 32, 0u);
+            for (int t = 0; t < tiles; t++) {
+                const int strip0 = (t * 8 / TOW) * TOW;
+                const int xs16 = bx[strip0 * 2] & ~15;
+                if (kbv[t] + ks * 32 > span) span = kbv[t] + ks * 32;
+                for (int lane = 0; lane < 32; lane++) {
+                    const int ox = t * 8 + (lane >> 2);
+                    if (ox >= out_w) continue;
+                    const int off = bx[ox * 2] - xs16 - kbv[t], ntap = bx[ox * 2 + 1];
+                    for (int st = 0; st < ks; st++)
+                        for (int hf = 0; hf < 2; hf++)
+                            for (int e = 0; e < 4; e++) {
+                                const int kk = st * 32 + hf * 16 + (lane & 3) * 4 + e, tap = kk - off;
+                                if (tap < 0 || tap >= ntap) continue;
+                                const int32_t c = cx[(size_t)ox * pl->kx + tap];
+                                const uint32_t bb[3] = {(uint32_t)c & 0xffu, ((uint32_t)c >> 8) & 0xffu, (uint32_t)(c >> 16) & 0xffu};
+                                for (int plane = 0; plane < 3; plane++)
+                                    bfrag[((((size_t)t * ks + st) * 3 + plane) * 2 + hf) * 32 + lane] |= bb[plane] << (8 * e);
+                            }
+                }
+            }
+            pl->imma_span = span;
+        }
+    }
     cudaGetDevice(&pl->device);
     auto up = [](int32_t **d, const std::vector<int32_t> &h) -> cudaError_t {
         cudaError_t e = cudaMalloc((void **)d, h.size() * sizeof(int32_t));
@@ -502,7 +739,8 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
     cudaError_t e;
     if ((e = up(&pl->d_bx, bx)) != cudaSuccess || (e = up(&pl->d_cx, cx)) != cudaSuccess ||
         (e = up(&pl->d_by, by)) != cudaSuccess || (e = up(&pl->d_cy, cy)) != cudaSuccess ||
-        (e = upu(&pl->d_cxp, cxp)) != cudaSuccess || (e = upu(&pl->d_cyp, cyp)) != cudaSuccess) {
+        (e = upu(&pl->d_cxp, cxp)) != cudaSuccess || (e = upu(&pl->d_cyp, cyp)) != cudaSuccess ||
+        (pl->ksteps && ((e = upu(&pl->d_bfrag, bfrag)) != cudaSuccess || (e = up(&pl->d_kb, kbv)) != cudaSuccess))) {
         lumina_resize_plan_destroy(pl);
         return set_error(LUMINA_E_CUDA, "resize plan upload failed: %s", cudaGetErrorString(e));
     }
@@ -514,6 +752,7 @@ LUMINA_API void lumina_resize_plan_destroy(lumina_resize_plan *pl) {
     if (!pl) return;
     cudaFree(pl->d_bx); cudaFree(pl->d_cx); cudaFree(pl->d_by); cudaFree(pl->d_cy);
     cudaFree(pl->d_cxp); cudaFree(pl->d_cyp);
+    cudaFree(pl->d_bfrag); cudaFree(pl->d_kb);
     delete pl;
 }
 
@@ -574,6 +813,32 @@ static int launch_strip_dp4a(const lumina_resize_plan *pl, const uint8_t *src, u
     return LUMINA_OK;
 }
 
+template <int KSTEPS>
+static int launch_strip_imma(const lumina_resize_plan *pl, const uint8_t *src, uint8_t *dst, int n, cudaStream_t st) {
+    ResizeDp4aParams p;
+    p.src = src; p.dst = dst; p.bx = pl->d_bx; p.by = pl->d_by; p.cxp = pl->d_cxp; p.cyp = pl->d_cyp;
+    p.bfrag = pl->d_bfrag; p.kb = pl->d_kb;
+    p.in_h = pl->in_h; p.in_w = pl->in_w; p.out_h = pl->out_h; p.out_w = pl->out_w; p.kxw = pl->kxw; p.kyw = pl->kyw;
+    p.src_total = (size_t)n * pl->in_h * pl->in_w * 3;
+    // staged pixels per plane row: the strip's span rounded out to 16-pixel groups, and every byte an A fragment reads
+    int seg = pl->max_seg_px + 15 + 16 + 8;
+    if (pl->imma_span + 16 > seg) seg = pl->imma_span + 16;
+    p.segpx = (seg + 15) & ~15;
+    if ((p.segpx / 4) % 8 == 0) p.segpx += 16;   // plane rows 3 * segpx apart: keep the 8 fragment rows on distinct banks
+    const int strips = div_up(pl->out_w, TOW);
+    int segs = 1;
+    while ((long long)strips * segs * n < 4LL * kNumSMs * 4 && pl->out_h / (segs * 2) >= 64) segs *= 2;
+    p.rows_per_seg = div_up(pl->out_h, segs);
+    segs = div_up(pl->out_h, p.rows_per_seg);
+    const size_t smem = (size_t)RB * 3 * p.segpx + (size_t)RINGG * TOW * 3 * 4;
+    auto kern = resize_strip_imma_kernel<KSTEPS>;
+    if (smem > 48 * 1024) LUMINA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LUMINA_REQUIRE(n <= 65535 && segs <= 65535, "batch too large for grid");
+    kern<<<dim3(strips, segs, n), 256, smem, st>>>(p);
+    LUMINA_KERNEL_CHECK("resize_strip_imma_kernel");
+    return LUMINA_OK;
+}
+
 static bool dp4a_ok(const lumina_resize_plan *pl, const uint8_t *src, int c) {
     // measured on B200 (64 A4 pages): dp4a 1.66 ms vs IMAD 2.45 ms at 23 taps (-> 960), 3.16 vs 4.27 ms at 13 taps (-> 2000)
     return c == 3 && (pl->in_w % 16) == 0 && (((uintptr_t)src) & 15) == 0 && pl->kxw <= 8 && pl->kx >= 9 &&
@@ -589,6 +854,12 @@ LUMINA_API int lumina_resize_lanczos_u8(const lumina_resize_plan *pl, const uint
     if (pl->in_w == pl->out_w && pl->in_h == pl->out_h) {
         LUMINA_CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, (size_t)n * pl->in_h * pl->in_w * c, cudaMemcpyDeviceToDevice, st));
         return LUMINA_OK;
+    }
+    if (fused_ok(pl) && dp4a_ok(pl, d_src, c) && pl->ksteps && !getenv("LUMINA_RESIZE_DP4A")) {
+        // measured on B200 (64 A4 pages -> 678x960): tensor-core horizontal pass vs dp4a, see DESIGN.md
+        if (pl->ksteps == 1) return launch_strip_imma<1>(pl, d_src, d_dst, n, st);
+        if (pl->ksteps == 2) return launch_strip_imma<2>(pl, d_src, d_dst, n, st);
+        return launch_strip_imma<3>(pl, d_src, d_dst, n, st);
     }
     if (fused_ok(pl) && dp4a_ok(pl, d_src, c)) {
         if (pl->kxw <= 2) return launch_strip_dp4a<2>(pl, d_src, d_dst, n, st);
