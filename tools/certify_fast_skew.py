@@ -43,6 +43,11 @@ print(json.dumps({
                       "p99": float(np.percentile(d, 99)), "mean": float(d.mean())},
     "within_0.1_deg": float((d <= 0.1).mean()), "within_0.05_deg": float((d <= 0.05).mean()),
     "same_side_of_0.5_gate": float((gate_e == gate_f).mean()),
+    # the reference's estimate sits on HoughLinesP's 1-degree theta grid: rounding the (accurate) fast estimate to whole
+    # degrees reproduces it far better than the estimate itself does -- evidence of the reference's bias, not a mode
+    "within_0.1_deg_if_fast_is_rounded_to_whole_degrees": float((np.abs(np.round(fast) - exact) <= 0.1).mean()),
+    "within_0.15_deg_if_fast_is_rounded_to_whole_degrees": float((np.abs(np.round(fast) - exact) <= 0.15).mean()),
+    "exact_angle_histogram_of_fractional_parts": np.histogram(np.abs(exact) - np.floor(np.abs(exact)), bins=10, range=(0, 1))[0].tolist(),
     "gate_disagreements_all_within_0.1_of_gate": bool(np.all(near_gate[gate_e != gate_f])) if (gate_e != gate_f).any() else True,
     "ms_per_64_pages": {"fast_estimator": round(t_fast / (n_pages / 64), 3), "exact_houghlinesp": round(t_exact / (n_pages / 64), 3)},
     "worst": [{"exact": float(exact[i]), "fast": float(fast[i])} for i in np.argsort(-d)[:5]],
