@@ -532,6 +532,7 @@ class ImagePreprocessor:
         # tagged images, other formats and JPEG flavours outside the device subset take the host codec below.
         imgs: List[Optional[Image.Image]] = [None] * len(images)
         enc_groups = {}
+        host_idx: List[int] = []
         for i, src in enumerate(images):
             data = None
             if isinstance(src, bytes):
@@ -542,7 +543,23 @@ class ImagePreprocessor:
             if info is not None and Image.open(io.BytesIO(data)).getexif().get(0x0112) not in (2, 3, 4, 5, 6, 7, 8):
                 enc_groups.setdefault((info.width, info.height, info.channels, info.hs, info.vs), []).append((i, data, info))
             else:
-                imgs[i] = self._open(src)
+                host_idx.append(i)
+        # everything else (PNG -- what pdf_to_images asks poppler for --, TIFF, progressive / CMYK JPEG, PIL objects):
+        # the host codec, as in the reference; encoded inputs are decoded on a thread pool (Pillow's decoders release
+        # the GIL), not one page after the other
+        def _decode(i):
+            im = self._open(images[i])
+            im.load()
+            return im
+
+        enc_host = [i for i in host_idx if not isinstance(images[i], Image.Image)]
+        if len(enc_host) > 1:
+            with ThreadPoolExecutor(max_workers=min(8, len(enc_host))) as ex:
+                for i, im in zip(enc_host, ex.map(_decode, enc_host)):
+                    imgs[i] = im
+        for i in host_idx:
+            if imgs[i] is None:
+                imgs[i] = self._open(images[i])
         for key, members in enc_groups.items():
             dec = self._jpeg_decoder()
             blob, offs = dec.pack([d for _, d, _ in members])
