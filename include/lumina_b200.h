@@ -184,7 +184,10 @@ int lumina_db_postprocess(const float *d_pred, int n, int h, int w, float thresh
                           int32_t *d_boxes, float *d_scores, int32_t *d_counts, void *d_workspace,
                           size_t workspace_bytes, void *stream);
 /* flags bit 0: use_dilation=True (the mask is dilated by upstream's 2x2 kernel before the contours are taken;
- * scores still come from the undilated probabilities). */
+ * scores still come from the undilated probabilities).
+ * flags bit 1: score_mode="slow" (upstream box_score_slow: the mean of the probabilities over
+ * cv2.fillPoly(contour), i.e. over the component, its holes and everything nested in them, instead of over the
+ * first min-area quad). */
 int lumina_db_postprocess_ex(const float *d_pred, int n, int h, int w, float thresh, double box_thresh,
                              double unclip_ratio, int max_candidates, int min_size, int flags,
                              const int32_t *h_src_hw, int32_t *d_boxes, float *d_scores, int32_t *d_counts,

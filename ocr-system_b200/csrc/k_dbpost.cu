@@ -587,6 +587,84 @@ __global__ void __launch_bounds__(DB_WARPS * 32) db_cand_score_kernel(const DbPa
     }
 }
 
+// ---- 5c'. box_score_slow: mean of pred over cv2.fillPoly(contour) (one warp per candidate) ---------------------------
+// The traced contour never exists here, and is not needed: the polygon through a border's pixels covers exactly
+//   outer border of component C :  every pixel that cannot leave C's outline over non-C pixels (4-moves) = C, its holes
+//                                  and whatever is nested in them;
+//   hole border of hole H       :  the border's own pixels (foreground 4-adjacent to H), H, and whatever is nested in H
+// (checked against cv2.findContours + cv2.fillPoly on 7 400 random contours with nesting, tests/test_db_geom.py).
+// "Nested in" is read off the labels without any flood fill: the raster-first pixel of a component is its root; the
+// pixel left of a foreground root belongs to the background component around that component, the pixel left of a
+// hole's root to the foreground component the hole is a hole of -- the same walk findContours' hierarchy is built by.
+__device__ __forceinline__ int db_root_pos(const int *L, int p) {
+    const int lab = L[p];
+    return lab < 0 ? p : lab;
+}
+
+// does the component of pixel p lie inside `target` (a root position; hole or outer as `target_hole` says)?
+__device__ __forceinline__ bool db_enclosed_by(const uint8_t *M, const int *L, int w, int p, int target, bool target_hole) {
+    bool fg = M[p] & 1;
+    int X = db_root_pos(L, p);
+    for (;;) {
+        if (fg) {
+            if (!target_hole && X == target) return true;
+            if (X % w == 0) return false;       // the component's first pixel sits in column 0: nothing around it
+            X = db_root_pos(L, X - 1);
+            fg = false;
+        } else {
+            if (target_hole && X == target) return true;
+            if (M[X] == 2) return false;        // background joined to the image border
+            X = db_root_pos(L, X - 1);          // a hole does not touch the border: its first pixel has a left neighbour
+            fg = true;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DB_WARPS * 32) db_cand_score_slow_kernel(const DbParams p) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int page = blockIdx.y;
+    const int slot = blockIdx.x * DB_WARPS + wib;
+    if (slot >= p.ncand[page * 2 + 1]) return;
+    uint8_t *acc = p.accept + (size_t)page * p.maxc + slot;
+    if (*acc != 3) return;
+    const int px = p.h * p.w;
+    const float *P = p.pred + (size_t)page * px;
+    const uint8_t *M = p.mask + (size_t)page * px;
+    const int *L = p.labels + (size_t)page * px;
+    const int centry = p.cand[(size_t)page * p.maxc + slot];
+    const bool hole = centry < 0;
+    const int root = hole ? -1 - centry : centry;
+    const int *B = p.bbox + ((size_t)page * p.maxc + slot) * 4;   // bounding box of the contour's points
+    const int bx0 = B[0], by0 = B[1], bx1 = B[2], by1 = B[3];
+    double sum = 0.0;
+    int cnt = 0;
+    for (int y = by0; y <= by1; y++) {
+        for (int x = bx0 + lane; x <= bx1; x += 32) {
+            const int q = y * p.w + x;
+            bool member = false;
+            if (hole && (M[q] & 1)) {
+                // a pixel of the hole's border
+                if (x > 0 && !(M[q - 1] & 1) && db_root_pos(L, q - 1) == root) member = true;
+                else if (x + 1 < p.w && !(M[q + 1] & 1) && db_root_pos(L, q + 1) == root) member = true;
+                else if (y > 0 && !(M[q - p.w] & 1) && db_root_pos(L, q - p.w) == root) member = true;
+                else if (y + 1 < p.h && !(M[q + p.w] & 1) && db_root_pos(L, q + p.w) == root) member = true;
+            }
+            if (!member) member = db_enclosed_by(M, L, p.w, q, root, hole);
+            if (member) { sum += (double)__ldg(P + q); cnt++; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const double score = cnt > 0 ? sum / (double)cnt : 0.0;
+    if (lane == 0) {
+        p.tmpscore[(size_t)page * p.maxc + slot] = (float)score;
+        *acc = p.box_thresh > score ? 12 : 4;
+    }
+}
+
 // ---- 5d. unclip + second min-area quad (one THREAD per candidate, offset polygon in shared memory) ------------
 constexpr int DB_UNCLIP_THREADS = 32;
 constexpr int DB_OFFS_SMALL = 64;   // offset polygons of ordinary text boxes have 12-40 vertices
@@ -760,7 +838,7 @@ LUMINA_API int lumina_db_postprocess_ex(const float *d_pred, int n, int h, int w
                                         double unclip_ratio, int max_candidates, int min_size, int flags,
                                         const int32_t *h_src_hw, int32_t *d_boxes, float *d_scores, int32_t *d_counts,
                                         void *d_workspace, size_t workspace_bytes, void *stream) {
-    LUMINA_REQUIRE((flags & ~1) == 0, "unknown flag");
+    LUMINA_REQUIRE((flags & ~3) == 0, "unknown flag");
     LUMINA_REQUIRE(d_pred && h_src_hw && d_boxes && d_scores && d_counts && d_workspace, "null pointer");
     LUMINA_REQUIRE(n > 0 && h > 0 && w > 0 && max_candidates > 0, "empty batch");
     LUMINA_REQUIRE((long long)h * w < (1LL << 30), "map too large");
@@ -797,8 +875,13 @@ LUMINA_API int lumina_db_postprocess_ex(const float *d_pred, int n, int h, int w
     LUMINA_KERNEL_CHECK("db_cand_rows_kernel");
     db_cand_rect_kernel<<<dim3(div_up(max_candidates, 128), n), 128, 0, st>>>(p);
     LUMINA_KERNEL_CHECK("db_cand_rect_kernel");
-    db_cand_score_kernel<<<dim3(div_up(max_candidates, DB_WARPS), n), DB_WARPS * 32, 0, st>>>(p);
-    LUMINA_KERNEL_CHECK("db_cand_score_kernel");
+    if (flags & 2) {
+        db_cand_score_slow_kernel<<<dim3(div_up(max_candidates, DB_WARPS), n), DB_WARPS * 32, 0, st>>>(p);
+        LUMINA_KERNEL_CHECK("db_cand_score_slow_kernel");
+    } else {
+        db_cand_score_kernel<<<dim3(div_up(max_candidates, DB_WARPS), n), DB_WARPS * 32, 0, st>>>(p);
+        LUMINA_KERNEL_CHECK("db_cand_score_kernel");
+    }
     {
         const size_t smem = (size_t)DB_UNCLIP_THREADS * 2 * (DB_OFFS_MAX + 2) * sizeof(DbgPt);
         LUMINA_CUDA_TRY(cudaFuncSetAttribute(db_cand_unclip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

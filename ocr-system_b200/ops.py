@@ -544,10 +544,14 @@ def db_mask_ccl(pred: torch.Tensor, thresh: float = 0.3):
 
 @_on_tensor_device
 def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: float = 0.7,
-                   unclip_ratio: float = 2.0, max_candidates: int = 1000, min_size: int = 3, use_dilation: bool = False):
+                   unclip_ratio: float = 2.0, max_candidates: int = 1000, min_size: int = 3, use_dilation: bool = False,
+                   score_mode: str = "fast"):
     """DBPostProcess core on [N,H,W] float32 maps -> (boxes [N,max_candidates,4,2] int32,
     scores [N,max_candidates] f32, counts [N] int32), all on the device.  ``use_dilation``: upstream's 2x2 mask
-    dilation before the contours are taken."""
+    dilation before the contours are taken.  ``score_mode``: "fast" (mean over the first quad) or "slow" (mean over
+    the filled contour)."""
+    if score_mode not in ("fast", "slow"):
+        raise ValueError("score_mode must be 'fast' or 'slow'")
     if not pred.is_cuda or pred.dtype != torch.float32 or pred.dim() != 3:
         raise TypeError("db_postprocess expects a CUDA float32 [N,H,W] tensor")
     p = pred.contiguous()
@@ -559,7 +563,7 @@ def db_postprocess(pred: torch.Tensor, src_hw, thresh: float = 0.3, box_thresh: 
     wsb = int(_L().lumina_db_workspace_bytes(n, h, w, int(max_candidates)))
     ws = _ws(wsb, p.device)
     _chk(_L().lumina_db_postprocess_ex(_ptr(p), n, h, w, float(np.float32(thresh)), float(box_thresh), float(unclip_ratio),
-                                       int(max_candidates), int(min_size), 1 if use_dilation else 0,
+                                       int(max_candidates), int(min_size), (1 if use_dilation else 0) | (2 if score_mode == "slow" else 0),
                                        hw.ctypes.data_as(C.c_void_p), _ptr(boxes), _ptr(scores), _ptr(counts), _ptr(ws), wsb,
                                        _stream()))
     return boxes, scores, counts

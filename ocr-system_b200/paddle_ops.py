@@ -44,15 +44,18 @@ class DBPostProcess:
     DBPostProcess(thresh, box_thresh, max_candidates, unclip_ratio, use_dilation, score_mode, box_type)
     (outs_dict{"maps": [N,1,H,W]}, shape_list[N x (src_h, src_w, ratio_h, ratio_w)]) -> [{"points": int32[K,4,2]}]
 
-    Supported: score_mode="fast", box_type="quad" (the defaults upstream ships in its det configs), with or without
-    ``use_dilation`` (RapidOCR's default).  score_mode="slow" and box_type="poly" need the traced contour polygon
-    (cv2.findContours point lists / approxPolyDP) that the label-based device pipeline never builds; they raise
-    instead of silently doing something different."""
+    Supported: box_type="quad" (what upstream ships in its det configs) with score_mode "fast" or "slow", with or
+    without ``use_dilation`` (RapidOCR's default).  box_type="poly" needs the ordered contour (approxPolyDP) and a
+    general polygon offset (Clipper union of a non-convex path) that the label-based device pipeline never builds;
+    it raises instead of silently doing something different."""
 
     def __init__(self, thresh=0.3, box_thresh=0.7, max_candidates=1000, unclip_ratio=2.0, use_dilation=False,
                  score_mode="fast", box_type="quad", **kwargs):
-        if score_mode != "fast" or box_type != "quad":
-            raise NotImplementedError("only score_mode='fast' and box_type='quad' are implemented")
+        if score_mode not in ("fast", "slow"):
+            raise ValueError("score_mode must be 'fast' or 'slow'")
+        if box_type != "quad":
+            raise NotImplementedError("box_type='poly' is not implemented (only 'quad')")
+        self.score_mode = score_mode
         self.use_dilation = bool(use_dilation)
         self.thresh, self.box_thresh = thresh, box_thresh
         self.max_candidates, self.unclip_ratio = max_candidates, unclip_ratio
@@ -67,7 +70,7 @@ class DBPostProcess:
         sl = np.asarray(shape_list, dtype=np.float64)
         src_hw = sl[:, :2].astype(np.int32)
         boxes, scores, counts = ops.db_postprocess(pred, src_hw, self.thresh, self.box_thresh, self.unclip_ratio,
-                                                   self.max_candidates, self.min_size, self.use_dilation)
+                                                   self.max_candidates, self.min_size, self.use_dilation, self.score_mode)
         counts_h = counts.cpu().numpy()
         kmax = int(counts_h.max(initial=0))
         boxes_h = boxes[:, : max(kmax, 1)].cpu().numpy()

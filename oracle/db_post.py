@@ -138,6 +138,21 @@ def box_score_fast(bitmap, _box):
     return cv2.mean(bitmap[ymin : ymax + 1, xmin : xmax + 1], mask)[0]
 
 
+def box_score_slow(bitmap, contour):
+    """upstream box_score_slow: mean of the probabilities over cv2.fillPoly(contour)."""
+    h, w = bitmap.shape[:2]
+    contour = np.reshape(contour.copy(), (-1, 2))
+    xmin = np.clip(np.min(contour[:, 0]), 0, w - 1)
+    xmax = np.clip(np.max(contour[:, 0]), 0, w - 1)
+    ymin = np.clip(np.min(contour[:, 1]), 0, h - 1)
+    ymax = np.clip(np.max(contour[:, 1]), 0, h - 1)
+    mask = np.zeros((ymax - ymin + 1, xmax - xmin + 1), dtype=np.uint8)
+    contour[:, 0] = contour[:, 0] - xmin
+    contour[:, 1] = contour[:, 1] - ymin
+    cv2.fillPoly(mask, contour.reshape(1, -1, 2).astype("int32"), 1)
+    return cv2.mean(bitmap[ymin : ymax + 1, xmin : xmax + 1], mask)[0]
+
+
 def unclip(box, unclip_ratio):
     """shapely area/length + pyclipper offset, restated.  Returns int array [K,2] or None."""
     b = np.asarray(box, np.float64)
@@ -154,7 +169,7 @@ def unclip(box, unclip_ratio):
 
 
 def boxes_from_bitmap(pred, bitmap, dest_width, dest_height, box_thresh=0.6, unclip_ratio=1.5, max_candidates=1000,
-                      min_size=3):
+                      min_size=3, score_mode="fast"):
     height, width = bitmap.shape
     contours, _ = cv2.findContours((bitmap * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
     num = min(len(contours), max_candidates)
@@ -165,7 +180,7 @@ def boxes_from_bitmap(pred, bitmap, dest_width, dest_height, box_thresh=0.6, unc
         if sside < min_size:
             continue
         points = np.array(points)
-        score = box_score_fast(pred, points.reshape(-1, 2))
+        score = box_score_fast(pred, points.reshape(-1, 2)) if score_mode == "fast" else box_score_slow(pred, contour)
         if box_thresh > score:
             continue
         ex = unclip(points, unclip_ratio)
@@ -188,7 +203,8 @@ class DBPostProcess:
 
     def __init__(self, thresh=0.3, box_thresh=0.7, max_candidates=1000, unclip_ratio=2.0, use_dilation=False,
                  score_mode="fast", box_type="quad", **kwargs):
-        assert score_mode == "fast" and box_type == "quad"
+        assert score_mode in ("fast", "slow") and box_type == "quad"
+        self.score_mode = score_mode
         self.thresh, self.box_thresh = thresh, box_thresh
         self.max_candidates, self.unclip_ratio = max_candidates, unclip_ratio
         self.min_size = 3
@@ -205,7 +221,7 @@ class DBPostProcess:
             if self.dilation_kernel is not None:
                 mask = cv2.dilate(np.array(mask).astype(np.uint8), self.dilation_kernel)
             boxes, scores = boxes_from_bitmap(pred[b], mask, src_w, src_h, self.box_thresh, self.unclip_ratio,
-                                              self.max_candidates, self.min_size)
+                                              self.max_candidates, self.min_size, self.score_mode)
             d = {"points": boxes}
             if with_scores:
                 d["scores"] = np.asarray(scores, np.float64)

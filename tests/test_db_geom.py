@@ -233,3 +233,47 @@ def _candidate_chain(G, D, pred):
             # same four vertices in the same order (get_mini_boxes' tl, tr, br, bl)
             assert np.array_equal(boxes[0].reshape(-1, 2), out8.reshape(-1, 2)), (ci, boxes[0].tolist(), out8.tolist())
     assert tot > 100
+
+
+def test_fillpoly_of_a_contour_is_the_enclosed_region():
+    """What score_mode='slow' rests on (k_dbpost.cu db_cand_score_slow_kernel): cv2.fillPoly of a findContours border
+    covers, for an outer border, everything that cannot leave the component's outline over non-component pixels, and
+    for a hole border, the border pixels plus the 4-connected non-component region that holds the hole."""
+    import cv2
+    from scipy import ndimage as ndi
+
+    rng = np.random.default_rng(1)
+    s8, s4 = np.ones((3, 3), int), np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    total = holes = 0
+    for _ in range(120):
+        h, w = rng.integers(20, 80, 2)
+        mask = (ndi.gaussian_filter(rng.random((h, w)), rng.uniform(0.6, 2.5)) > rng.uniform(0.45, 0.55)).astype(np.uint8)
+        cs, hier = cv2.findContours(mask, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_SIMPLE)
+        if hier is None:
+            continue
+        fg, _ = ndi.label(mask, s8)
+        bg, _ = ndi.label(1 - mask, s4)
+        for c, hh in zip(cs, hier[0]):
+            pts = c.reshape(-1, 2)
+            fill = np.zeros((h, w), np.uint8)
+            cv2.fillPoly(fill, [pts.astype(np.int32)], 1)
+            comp = fg[pts[0, 1], pts[0, 0]]
+            not_c = fg != comp
+            if hh[3] < 0:                                   # outer border
+                lab, _ = ndi.label(np.pad(not_c, 1, constant_values=True), s4)
+                region = ~(lab == lab[0, 0])[1:-1, 1:-1]
+                assert np.array_equal(region, fill > 0)
+            else:                                           # hole border: find the hole among the bg neighbours
+                lab, _ = ndi.label(not_c, s4)
+                ok = False
+                x, y = pts[0]
+                for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+                    xx, yy = x + dx, y + dy
+                    if 0 <= xx < w and 0 <= yy < h and not mask[yy, xx]:
+                        hm = bg == bg[yy, xx]
+                        region = (ndi.binary_dilation(hm, s4) & (mask > 0)) | (lab == lab[yy, xx])
+                        ok |= np.array_equal(region, fill > 0)
+                assert ok
+                holes += 1
+            total += 1
+    assert total > 2000 and holes > 200

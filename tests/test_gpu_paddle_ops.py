@@ -139,3 +139,75 @@ def test_db_postprocess_large_boxes_take_the_second_unclip_pass(cuda):
     assert len(ref[0]["points"]) == 3
     assert np.array_equal(got[0]["points"], ref[0]["points"])
     assert np.abs(got[0]["scores"] - ref[0]["scores"]).max() <= 1e-4
+
+
+def _nested_map(h=160, w=200):
+    """ring > blob > hole > blob (nesting depth 3), a ring leaning on the image border, a thin diagonal chain."""
+    m = np.full((h, w), 0.05, np.float32)
+    m[10:130, 10:150] = 0.9; m[20:120, 20:140] = 0.1              # outer ring and its hole
+    m[30:110, 30:130] = 0.8; m[45:95, 50:110] = 0.2               # blob in the hole, with its own hole
+    m[55:85, 60:100] = 0.95                                        # blob in that hole
+    m[0:40, 160:200] = 0.85; m[6:30, 168:192] = 0.15              # ring touching the top/right border
+    for k in range(25):                                            # 8-connected diagonal chain (1 px wide)
+        m[135 + k // 2, 20 + k] = 0.9
+    m[140:156, 100:190] = 0.7; m[144:152, 110:120] = 0.0; m[144:152, 150:180] = 0.25   # box with two holes
+    m[60:128, 156:196] = 0.9; m[70:118, 166:196] = 0.1; m[85:100, 176:190] = 0.8      # C shape (open to the right) around an island
+    return m
+
+
+@pytest.mark.parametrize("dil", [False, True])
+def test_db_postprocess_score_mode_slow_nested(cuda, dil):
+    """score_mode='slow' = mean over cv2.fillPoly(contour): holes and nested components count, which is what tells
+    it from the quad score."""
+    from ocr_system_b200.paddle_ops import DBPostProcess
+    from oracle import db_post as D
+
+    maps = [_nested_map()]
+    rng = np.random.default_rng(11)
+    from scipy import ndimage as ndi
+    for k in range(5):                                             # random blob fields: many holes, islands in holes
+        f = ndi.gaussian_filter(rng.random((160, 200)), rng.uniform(1.0, 2.5))
+        f = (f - f.min()) / (f.max() - f.min())
+        maps.append(f.astype(np.float32))
+    preds = np.stack(maps)
+    sl = [(160, 200, 1.0, 1.0)] * len(preds)
+    kw = dict(thresh=0.5, box_thresh=0.3, unclip_ratio=1.5, use_dilation=dil, score_mode="slow")
+    ref = D.DBPostProcess(**kw)({"maps": preds[:, None]}, sl, with_scores=True)
+    got = DBPostProcess(**kw)({"maps": preds[:, None]}, sl, with_scores=True)
+    fast = D.DBPostProcess(**{**kw, "score_mode": "fast"})({"maps": preds[:, None]}, sl, with_scores=True)
+    total = 0
+    for b in range(len(preds)):
+        assert np.array_equal(got[b]["points"], ref[b]["points"]), b
+        assert np.abs(got[b]["scores"] - ref[b]["scores"]).max(initial=0) <= 1e-4, b
+        total += len(ref[b]["points"])
+    assert total > 40
+    assert len(ref[0]["points"]) >= 6
+    # the two modes really differ on this input (else the test proves nothing)
+    assert any(len(fast[b]["points"]) != len(ref[b]["points"]) or
+               np.abs(np.asarray(fast[b]["scores"]) - np.asarray(ref[b]["scores"])).max(initial=0) > 1e-2
+               for b in range(len(preds)))
+
+
+@pytest.mark.parametrize("seed,h,w", [(7, 960, 960), (8, 640, 800)])
+def test_db_postprocess_score_mode_slow_text_maps(cuda, seed, h, w):
+    from ocr_system_b200.paddle_ops import DBPostProcess
+    from oracle import db_post as D
+
+    preds = np.stack([D.synth_prob_map(h, w, seed * 10 + k, n_boxes=300, hole_frac=0.3) for k in range(2)])
+    sl = [(h, w, 1.0, 1.0)] * 2
+    kw = dict(thresh=0.3, box_thresh=0.6, unclip_ratio=1.5, score_mode="slow")
+    ref = D.DBPostProcess(**kw)({"maps": preds[:, None]}, sl, with_scores=True)
+    got = DBPostProcess(**kw)({"maps": preds[:, None]}, sl, with_scores=True)
+    for b in range(2):
+        assert len(ref[b]["points"]) > 100
+        assert np.array_equal(got[b]["points"], ref[b]["points"])
+        assert np.abs(got[b]["scores"] - ref[b]["scores"]).max() <= 1e-4
+
+
+def test_db_postprocess_rejects_unknown_modes(cuda):
+    from ocr_system_b200.paddle_ops import DBPostProcess
+
+    with pytest.raises(NotImplementedError):
+        DBPostProcess(box_type="poly")
+    with pytest.raises(ValueError):
+        DBPostProcess(score_mode="median")
