@@ -264,6 +264,8 @@ struct ResizeDp4aParams {
     int in_h, in_w, out_h, out_w, kxw, kyw;
     int rows_per_seg;
     int segpx;         // staged pixels per row and plane (multiple of 16, + slack)
+    int rawpitch;      // bulk-staged variant: bytes between staged interleaved rows (== 48 mod 128: conflict-free fragments)
+    int copy_bytes;    // bulk-staged variant: bytes fetched per row (multiple of 16)
     size_t src_total;
 };
 
@@ -607,6 +609,205 @@ __global__ void __launch_bounds__(256, 4) resize_strip_imma_kernel(const ResizeD
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-staged variant (the shipped one).  What limited the kernel above was not arithmetic but the serial phases of a
+// chunk: every CTA waited for its own staging loads (23 % of the stall samples), de-interleaved them through shared
+// memory, and only then started the MMAs.  Here one thread fetches the INTERLEAVED rows of chunk i+2 with
+// cp.async.bulk (global -> shared, completion on an mbarrier) while chunks i and i+1 are computed, and nobody
+// de-interleaves into shared memory at all: a lane reads the three words that hold its four pixels and PRMTs them
+// into the R, G and B fragment words directly (row pitch == 48 mod 128 bytes keeps the 32 lanes on 32 banks).  The
+// three coefficient byte planes share one accumulator: c = ((c2 << 8) + c1 << 8) + c0 modulo 2^32, the MMAs of plane
+// p accumulating on top of the shifted sum of the planes above -- the true sum fits int32, so this is exact.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RS_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RS_DONE;\n"
+        "bra RS_WAIT;\n"
+        "RS_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <int KSTEPS>
+__global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeDp4aParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int ROWB = TOW * 3;
+    constexpr int STAGES = 2;
+    uint8_t *raw = smem;                                                                  // [STAGES][RB][rawpitch]
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + (size_t)STAGES * RB * p.rawpitch);  // [RINGG][ROWB] words of 4 rows
+    __shared__ __align__(8) unsigned long long s_full[STAGES];
+    __shared__ int s_oy_end;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ox0 = blockIdx.x * TOW;
+    const int oy0 = blockIdx.y * p.rows_per_seg;
+    const int oy1 = min(oy0 + p.rows_per_seg, p.out_h);
+    const int page = blockIdx.z;
+    const size_t pitch = (size_t)p.in_w * 3;
+    const uint8_t *src = p.src + (size_t)page * p.in_h * pitch;
+    uint8_t *dst = p.dst + (size_t)page * p.out_h * p.out_w * 3;
+    const int xs16 = p.bx[ox0 * 2] & ~15;
+    const int ys = p.by[oy0 * 2];
+    const int ye = p.by[(oy1 - 1) * 2] + p.by[(oy1 - 1) * 2 + 1];
+    const int nchunks = (ye - ys + RB - 1) / RB;
+    const uint8_t *src_end = p.src + p.src_total;
+
+    // one thread issues the bulk copies of a chunk: a row is one copy (the last rows of the batch are cut at its end;
+    // what stays stale in shared memory only meets zero coefficients)
+    auto issue = [&](int c) {
+        const int buf = c % STAGES;
+        const int r0 = ys + c * RB, nrows = min(RB, ye - r0);
+        const uint32_t bar = rs_smem_u32(&s_full[buf]);
+        uint32_t total = 0;
+        for (int r = 0; r < nrows; r++) {
+            const uint8_t *gp = src + (size_t)(r0 + r) * pitch + (size_t)xs16 * 3;
+            const long long left = src_end - gp;
+            total += (uint32_t)(left < p.copy_bytes ? left : p.copy_bytes);
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+        for (int r = 0; r < nrows; r++) {
+            const uint8_t *gp = src + (size_t)(r0 + r) * pitch + (size_t)xs16 * 3;
+            const long long left = src_end - gp;
+            const uint32_t bytes = (uint32_t)(left < p.copy_bytes ? left : p.copy_bytes);
+            const uint32_t d = rs_smem_u32(raw + ((size_t)buf * RB + r) * p.rawpitch);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(d), "l"(gp), "r"(bytes), "r"(bar) : "memory");
+        }
+    };
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; i++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(&s_full[i])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < STAGES && c < nchunks; c++) issue(c);
+
+    // this warp's 8-column tile: B fragments (3 byte planes x KSTEPS x 2 registers) and the start of its K window
+    const int tile = blockIdx.x * (TOW / 8) + warp;
+    const bool tile_ok = tile * 8 < p.out_w;
+    uint32_t bf[KSTEPS][3][2];
+    int kb = 0;
+    if (tile_ok) {
+        kb = p.kb[tile];
+#pragma unroll
+        for (int st = 0; st < KSTEPS; st++)
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++)
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) bf[st][pl][hf] = p.bfrag[((((size_t)tile * KSTEPS + st) * 3 + pl) * 2 + hf) * 32 + lane];
+    }
+    const int grp = lane >> 2, tq = lane & 3;
+    const int rawpitch_w = p.rawpitch >> 2;
+    int next_oy = oy0;
+
+    for (int c = 0; c < nchunks; c++) {
+        const int r0 = ys + c * RB;
+        const int nrows = min(RB, ye - r0);
+        const int buf = c % STAGES;
+        rs_mbar_wait(rs_smem_u32(&s_full[buf]), (uint32_t)((c / STAGES) & 1));
+        // ---- horizontal pass: 16 rows x 8 columns x K per warp on the tensor cores, A straight from the interleaved rows ----
+        if (tile_ok) {
+            const uint32_t *lo = reinterpret_cast<const uint32_t *>(raw + ((size_t)buf * RB + grp) * p.rawpitch) + 3 * ((kb >> 2) + tq);
+            const uint32_t *hi = lo + 8 * rawpitch_w;
+            uint32_t af[3][KSTEPS][4];
+#pragma unroll
+            for (int st = 0; st < KSTEPS; st++)
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                    for (int up = 0; up < 2; up++) {
+                        const uint32_t *q = (up ? hi : lo) + 3 * (st * 8 + hf * 4);
+                        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                        af[0][st][hf * 2 + up] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+                        af[1][st][hf * 2 + up] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+                        af[2][st][hf * 2 + up] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+                    }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int st = 0; st < KSTEPS; st++) mma_u8s8(acc, af[ch][st], bf[st][2][0], bf[st][2][1]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
+#pragma unroll
+                for (int st = 0; st < KSTEPS; st++) mma_u8u8(acc, af[ch][st], bf[st][1][0], bf[st][1][1]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
+#pragma unroll
+                for (int st = 0; st < KSTEPS; st++) mma_u8u8(acc, af[ch][st], bf[st][0][0], bf[st][0][1]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int row = grp + (i >> 1) * 8;            // row of the chunk
+                    const int col = warp * 8 + tq * 2 + (i & 1);   // column of the strip
+                    if (row < nrows && ox0 + col < p.out_w) {
+                        const int arow = r0 + row;
+                        const int v = (int)((1u << (PREC_BITS - 1)) + (uint32_t)acc[i]);   // exact modulo 2^32; the true sum fits int32
+                        uint32_t *rg = ring + (size_t)((arow >> 2) & (RINGG - 1)) * ROWB + col * 3;
+                        reinterpret_cast<uint8_t *>(rg + ch)[arow & 3] = clip8(v);
+                    }
+                }
+            }
+        }
+        if (tid == 255) {  // which output rows have their whole tap window in the ring after this chunk
+            const int rows_done = r0 + nrows;
+            int oe = next_oy;
+            while (oe < oy1 && p.by[oe * 2] + p.by[oe * 2 + 1] <= rows_done) oe++;
+            s_oy_end = oe;
+        }
+        __syncthreads();   // the ring is complete, and nobody reads this chunk's staged rows any more
+        if (tid == 0 && c + STAGES < nchunks) issue(c + STAGES);
+        // ---- vertical pass: a thread owns 4 adjacent byte columns of one output row ----
+        const int oy_end = s_oy_end;
+        constexpr int COL4 = ROWB / 4;
+        const int ntask = (oy_end - next_oy) * COL4;
+        const int row_bytes = p.out_w * 3;
+        for (int task = tid; task < ntask; task += 256) {
+            const int orow = task / COL4, c4 = task - orow * COL4;
+            const int oy = next_oy + orow;
+            const int bcol = ox0 * 3 + c4 * 4;
+            if (bcol >= row_bytes) continue;
+            const int ymin = p.by[oy * 2];
+            const uint32_t *k = p.cyp + (size_t)oy * 3 * p.kyw;
+            int s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+            int rgrp = (ymin >> 2) & (RINGG - 1);
+            for (int j = 0; j < p.kyw; j++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(ring + (size_t)rgrp * ROWB + c4 * 4);
+                const uint32_t k0 = __ldg(k + j), k1 = __ldg(k + p.kyw + j), k2 = __ldg(k + 2 * p.kyw + j);
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    s0[q] = (int)__dp4a(vv[q], k0, (uint32_t)s0[q]);
+                    s1[q] = (int)__dp4a(vv[q], k1, (uint32_t)s1[q]);
+                    s2[q] = dp4a_u8s8(vv[q], k2, s2[q]);
+                }
+                rgrp = (rgrp + 1) & (RINGG - 1);
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                o[q] = clip8((int)((1u << (PREC_BITS - 1)) + (uint32_t)s0[q] + ((uint32_t)s1[q] << 8) + ((uint32_t)s2[q] << 16)));
+            uint8_t *dp = dst + (size_t)oy * row_bytes + bcol;
+            if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 3) == 0) {
+                *reinterpret_cast<uint32_t *>(dp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+            } else if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 1) == 0) {
+                *reinterpret_cast<uint16_t *>(dp) = (uint16_t)(o[0] | (o[1] << 8));
+                *reinterpret_cast<uint16_t *>(dp + 2) = (uint16_t)(o[2] | (o[3] << 8));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (bcol + q < row_bytes) dp[q] = (uint8_t)o[q];
+            }
+        }
+        next_oy = oy_end;
+        __syncthreads();
+    }
+}
+
 // one axis only (the other is identity) or tap counts beyond the unrolled
 // variants: plain two-pass kernels through an HBM intermediate.
 template <int C>
@@ -814,6 +1015,32 @@ static int launch_strip_dp4a(const lumina_resize_plan *pl, const uint8_t *src, u
 }
 
 template <int KSTEPS>
+static int launch_strip_bulk(const lumina_resize_plan *pl, const uint8_t *src, uint8_t *dst, int n, cudaStream_t st) {
+    ResizeDp4aParams p;
+    p.src = src; p.dst = dst; p.bx = pl->d_bx; p.by = pl->d_by; p.cxp = pl->d_cxp; p.cyp = pl->d_cyp;
+    p.bfrag = pl->d_bfrag; p.kb = pl->d_kb;
+    p.in_h = pl->in_h; p.in_w = pl->in_w; p.out_h = pl->out_h; p.out_w = pl->out_w; p.kxw = pl->kxw; p.kyw = pl->kyw;
+    p.src_total = (size_t)n * pl->in_h * pl->in_w * 3;
+    p.segpx = 0;
+    // a staged row holds every byte an A fragment reads: imma_span pixels from the strip's xs16
+    p.copy_bytes = (pl->imma_span * 3 + 15) & ~15;
+    p.rawpitch = p.copy_bytes;
+    while (p.rawpitch % 128 != 48) p.rawpitch += 16;
+    const int strips = div_up(pl->out_w, TOW);
+    int segs = 1;
+    while ((long long)strips * segs * n < 4LL * kNumSMs * 4 && pl->out_h / (segs * 2) >= 64) segs *= 2;
+    p.rows_per_seg = div_up(pl->out_h, segs);
+    segs = div_up(pl->out_h, p.rows_per_seg);
+    const size_t smem = (size_t)2 * RB * p.rawpitch + (size_t)RINGG * TOW * 3 * 4;
+    auto kern = resize_strip_bulk_kernel<KSTEPS>;
+    if (smem > 48 * 1024) LUMINA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LUMINA_REQUIRE(n <= 65535 && segs <= 65535, "batch too large for grid");
+    kern<<<dim3(strips, segs, n), 256, smem, st>>>(p);
+    LUMINA_KERNEL_CHECK("resize_strip_bulk_kernel");
+    return LUMINA_OK;
+}
+
+template <int KSTEPS>
 static int launch_strip_imma(const lumina_resize_plan *pl, const uint8_t *src, uint8_t *dst, int n, cudaStream_t st) {
     ResizeDp4aParams p;
     p.src = src; p.dst = dst; p.bx = pl->d_bx; p.by = pl->d_by; p.cxp = pl->d_cxp; p.cyp = pl->d_cyp;
@@ -857,6 +1084,11 @@ LUMINA_API int lumina_resize_lanczos_u8(const lumina_resize_plan *pl, const uint
     }
     if (fused_ok(pl) && dp4a_ok(pl, d_src, c) && pl->ksteps && !getenv("LUMINA_RESIZE_DP4A")) {
         // measured on B200 (64 A4 pages -> 678x960): tensor-core horizontal pass vs dp4a, see DESIGN.md
+        if (pl->ksteps <= 2 && !getenv("LUMINA_RESIZE_STAGED")) {
+            // measured on B200: bulk-staged interleaved rows vs staged + de-interleaved planes, see DESIGN.md
+            if (pl->ksteps == 1) return launch_strip_bulk<1>(pl, d_src, d_dst, n, st);
+            return launch_strip_bulk<2>(pl, d_src, d_dst, n, st);
+        }
         if (pl->ksteps == 1) return launch_strip_imma<1>(pl, d_src, d_dst, n, st);
         if (pl->ksteps == 2) return launch_strip_imma<2>(pl, d_src, d_dst, n, st);
         return launch_strip_imma<3>(pl, d_src, d_dst, n, st);
