@@ -38,6 +38,10 @@ struct lumina_resize_plan {
     int32_t *d_kb;              // [tiles] first staged byte (multiple of 4, relative to the strip's xs16) of the tile's K window
     int ksteps;                 // K window of a tile in units of 32 input pixels (0: path not available)
     int imma_span;              // bytes of a staged plane row the A fragments may touch
+    // tensor-core vertical pass: per tile of 8 output rows the B fragments over a K window of 64 intermediate rows
+    uint32_t *d_vfrag;          // [out_h/8 tiles][2 k-steps][3 planes][2][32 lanes]
+    int32_t *d_vg0;             // [tiles] first ring row-group (input row / 4) of the tile's K window
+    int vtiles;                 // 0: path not available (a tile's taps do not fit 64 rows)
     int device;
 };
 
@@ -261,6 +265,8 @@ struct ResizeDp4aParams {
     const uint32_t *cxp, *cyp;
     const uint32_t *bfrag;
     const int32_t *kb;
+    const uint32_t *vfrag;
+    const int32_t *vg0;
     int in_h, in_w, out_h, out_w, kxw, kyw;
     int rows_per_seg;
     int segpx;         // staged pixels per row and plane (multiple of 16, + slack)
@@ -632,19 +638,22 @@ __device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+constexpr int RINGV = 32;    // ring row-groups of the bulk kernel: the 64-row K window of a tile + the chunk being written
+constexpr int ROWP = TOW * 3 + 8;  // ring pitch in words (== 8 mod 32: the vertical fragments' 4 groups x 8 columns hit 32 banks)
+
 template <int KSTEPS>
 __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeDp4aParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int ROWB = TOW * 3;
     constexpr int STAGES = 2;
     uint8_t *raw = smem;                                                                  // [STAGES][RB][rawpitch]
-    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + (size_t)STAGES * RB * p.rawpitch);  // [RINGG][ROWB] words of 4 rows
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + (size_t)STAGES * RB * p.rawpitch);  // [RINGV][ROWP] words of 4 rows
     __shared__ __align__(8) unsigned long long s_full[STAGES];
     __shared__ int s_oy_end;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ox0 = blockIdx.x * TOW;
-    const int oy0 = blockIdx.y * p.rows_per_seg;
+    const int oy0 = blockIdx.y * p.rows_per_seg;      // multiple of 8: vertical tiles are global
     const int oy1 = min(oy0 + p.rows_per_seg, p.out_h);
     const int page = blockIdx.z;
     const size_t pitch = (size_t)p.in_w * 3;
@@ -656,24 +665,22 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
     const int nchunks = (ye - ys + RB - 1) / RB;
     const uint8_t *src_end = p.src + p.src_total;
 
-    // one thread issues the bulk copies of a chunk: a row is one copy (the last rows of the batch are cut at its end;
-    // what stays stale in shared memory only meets zero coefficients)
+    // warp 0 issues the bulk copies of a chunk, one row per lane (the last rows of the batch are cut at its end; what
+    // stays stale in shared memory only meets zero coefficients)
     auto issue = [&](int c) {
         const int buf = c % STAGES;
         const int r0 = ys + c * RB, nrows = min(RB, ye - r0);
         const uint32_t bar = rs_smem_u32(&s_full[buf]);
-        uint32_t total = 0;
-        for (int r = 0; r < nrows; r++) {
-            const uint8_t *gp = src + (size_t)(r0 + r) * pitch + (size_t)xs16 * 3;
-            const long long left = src_end - gp;
-            total += (uint32_t)(left < p.copy_bytes ? left : p.copy_bytes);
-        }
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-        for (int r = 0; r < nrows; r++) {
-            const uint8_t *gp = src + (size_t)(r0 + r) * pitch + (size_t)xs16 * 3;
-            const long long left = src_end - gp;
-            const uint32_t bytes = (uint32_t)(left < p.copy_bytes ? left : p.copy_bytes);
-            const uint32_t d = rs_smem_u32(raw + ((size_t)buf * RB + r) * p.rawpitch);
+        const uint8_t *gp = src + (size_t)(r0 + lane) * pitch + (size_t)xs16 * 3;
+        const long long left = src_end - gp;
+        const uint32_t bytes = lane < nrows ? (uint32_t)(left < p.copy_bytes ? left : p.copy_bytes) : 0u;
+        uint32_t total = bytes;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+        __syncwarp();
+        if (bytes) {
+            const uint32_t d = rs_smem_u32(raw + ((size_t)buf * RB + lane) * p.rawpitch);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(d), "l"(gp), "r"(bytes), "r"(bar) : "memory");
         }
@@ -684,7 +691,7 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0)
+    if (warp == 0)
         for (int c = 0; c < STAGES && c < nchunks; c++) issue(c);
 
     // this warp's 8-column tile: B fragments (3 byte planes x KSTEPS x 2 registers) and the start of its K window
@@ -703,7 +710,8 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
     }
     const int grp = lane >> 2, tq = lane & 3;
     const int rawpitch_w = p.rawpitch >> 2;
-    int next_oy = oy0;
+    const int row_bytes = p.out_w * 3;
+    int next_oy = oy0;           // first output row not yet written (a multiple of 8 until the segment's last tile)
 
     for (int c = 0; c < nchunks; c++) {
         const int r0 = ys + c * RB;
@@ -727,6 +735,12 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                         af[1][st][hf * 2 + up] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
                         af[2][st][hf * 2 + up] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
                     }
+            // ring byte addresses of this lane's two rows (columns / channels are immediate offsets from them)
+            const int arow_lo = r0 + grp, arow_hi = arow_lo + 8;
+            uint8_t *ring_b = reinterpret_cast<uint8_t *>(ring);
+            uint8_t *rp_lo = ring_b + ((size_t)((arow_lo >> 2) & (RINGV - 1)) * ROWP + (warp * 8 + tq * 2) * 3) * 4 + (arow_lo & 3);
+            uint8_t *rp_hi = ring_b + ((size_t)((arow_hi >> 2) & (RINGV - 1)) * ROWP + (warp * 8 + tq * 2) * 3) * 4 + (arow_hi & 3);
+            const bool ok_lo = grp < nrows, ok_hi = grp + 8 < nrows;
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
                 int acc[4] = {0, 0, 0, 0};
@@ -740,16 +754,12 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
 #pragma unroll
                 for (int st = 0; st < KSTEPS; st++) mma_u8u8(acc, af[ch][st], bf[st][0][0], bf[st][0][1]);
+                // columns past out_w (last strip) land in ring columns nobody stores from
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int row = grp + (i >> 1) * 8;            // row of the chunk
-                    const int col = warp * 8 + tq * 2 + (i & 1);   // column of the strip
-                    if (row < nrows && ox0 + col < p.out_w) {
-                        const int arow = r0 + row;
-                        const int v = (int)((1u << (PREC_BITS - 1)) + (uint32_t)acc[i]);   // exact modulo 2^32; the true sum fits int32
-                        uint32_t *rg = ring + (size_t)((arow >> 2) & (RINGG - 1)) * ROWB + col * 3;
-                        reinterpret_cast<uint8_t *>(rg + ch)[arow & 3] = clip8(v);
-                    }
+                    const int v = (int)((1u << (PREC_BITS - 1)) + (uint32_t)acc[i]);   // exact modulo 2^32; the true sum fits int32
+                    uint8_t *rp = (i >> 1) ? rp_hi : rp_lo;
+                    if ((i >> 1) ? ok_hi : ok_lo) rp[((i & 1) * 3 + ch) * 4] = clip8(v);
                 }
             }
         }
@@ -760,50 +770,50 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
             s_oy_end = oe;
         }
         __syncthreads();   // the ring is complete, and nobody reads this chunk's staged rows any more
-        if (tid == 0 && c + STAGES < nchunks) issue(c + STAGES);
-        // ---- vertical pass: a thread owns 4 adjacent byte columns of one output row ----
+        if (warp == 0 && c + STAGES < nchunks) issue(c + STAGES);
+        // ---- vertical pass on the tensor cores: tiles of 8 output rows (N) x 16 byte columns (M) x 64 ring rows (K).
+        // A = the ring words themselves (4 consecutive rows of one byte column), B = the tile's coefficient fragments.
         const int oy_end = s_oy_end;
-        constexpr int COL4 = ROWB / 4;
-        const int ntask = (oy_end - next_oy) * COL4;
-        const int row_bytes = p.out_w * 3;
-        for (int task = tid; task < ntask; task += 256) {
-            const int orow = task / COL4, c4 = task - orow * COL4;
-            const int oy = next_oy + orow;
-            const int bcol = ox0 * 3 + c4 * 4;
-            if (bcol >= row_bytes) continue;
-            const int ymin = p.by[oy * 2];
-            const uint32_t *k = p.cyp + (size_t)oy * 3 * p.kyw;
-            int s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-            int rgrp = (ymin >> 2) & (RINGG - 1);
-            for (int j = 0; j < p.kyw; j++) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(ring + (size_t)rgrp * ROWB + c4 * 4);
-                const uint32_t k0 = __ldg(k + j), k1 = __ldg(k + p.kyw + j), k2 = __ldg(k + 2 * p.kyw + j);
-                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        while (next_oy < oy1 && (next_oy + 8 <= oy_end || oy_end == oy1)) {
+            const int vt = next_oy >> 3;
+            const int g0 = __ldg(p.vg0 + vt);
+            uint32_t vb[2][3][2];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    s0[q] = (int)__dp4a(vv[q], k0, (uint32_t)s0[q]);
-                    s1[q] = (int)__dp4a(vv[q], k1, (uint32_t)s1[q]);
-                    s2[q] = dp4a_u8s8(vv[q], k2, s2[q]);
+            for (int st = 0; st < 2; st++)
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++)
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) vb[st][pl][hf] = __ldg(p.vfrag + ((((size_t)vt * 2 + st) * 3 + pl) * 2 + hf) * 32 + lane);
+            for (int mt = warp; mt < ROWB / 16; mt += 8) {
+                const int mb = mt * 16;
+                uint32_t va[2][4];
+#pragma unroll
+                for (int st = 0; st < 2; st++) {
+                    const uint32_t *g_lo = ring + (size_t)((g0 + st * 8 + tq) & (RINGV - 1)) * ROWP + mb + grp;
+                    const uint32_t *g_hi = ring + (size_t)((g0 + st * 8 + 4 + tq) & (RINGV - 1)) * ROWP + mb + grp;
+                    va[st][0] = g_lo[0]; va[st][1] = g_lo[8]; va[st][2] = g_hi[0]; va[st][3] = g_hi[8];
                 }
-                rgrp = (rgrp + 1) & (RINGG - 1);
-            }
-            uint32_t o[4];
+                int acc[4] = {0, 0, 0, 0};
+                mma_u8s8(acc, va[0], vb[0][2][0], vb[0][2][1]);
+                mma_u8s8(acc, va[1], vb[1][2][0], vb[1][2][1]);
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                o[q] = clip8((int)((1u << (PREC_BITS - 1)) + (uint32_t)s0[q] + ((uint32_t)s1[q] << 8) + ((uint32_t)s2[q] << 16)));
-            uint8_t *dp = dst + (size_t)oy * row_bytes + bcol;
-            if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 3) == 0) {
-                *reinterpret_cast<uint32_t *>(dp) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-            } else if (bcol + 4 <= row_bytes && (((uintptr_t)dp) & 1) == 0) {
-                *reinterpret_cast<uint16_t *>(dp) = (uint16_t)(o[0] | (o[1] << 8));
-                *reinterpret_cast<uint16_t *>(dp + 2) = (uint16_t)(o[2] | (o[3] << 8));
-            } else {
+                for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
+                mma_u8u8(acc, va[0], vb[0][1][0], vb[0][1][1]);
+                mma_u8u8(acc, va[1], vb[1][1][0], vb[1][1][1]);
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (bcol + q < row_bytes) dp[q] = (uint8_t)o[q];
+                for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
+                mma_u8u8(acc, va[0], vb[0][0][0], vb[0][0][1]);
+                mma_u8u8(acc, va[1], vb[1][0][0], vb[1][0][1]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int bcol = ox0 * 3 + mb + grp + (i >> 1) * 8;      // byte column of the page row
+                    const int oy = next_oy + tq * 2 + (i & 1);
+                    if (bcol < row_bytes && oy < oy1)
+                        dst[(size_t)oy * row_bytes + bcol] = clip8((int)((1u << (PREC_BITS - 1)) + (uint32_t)acc[i]));
+                }
             }
+            next_oy = min(next_oy + 8, oy1);
         }
-        next_oy = oy_end;
         __syncthreads();
     }
 }
@@ -926,6 +936,44 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
             pl->imma_span = span;
         }
     }
+    // tensor-core vertical pass: tiles of 8 output rows; K = 64 intermediate rows from the 4-row group that holds the
+    // tile's first tap (B fragment of mma.m16n8k32: lane l holds output row l >> 2, K rows (l & 3) * 4 .. + 3 and + 16)
+    pl->d_vfrag = nullptr; pl->d_vg0 = nullptr; pl->vtiles = 0;
+    std::vector<uint32_t> vfrag;
+    std::vector<int32_t> vg0;
+    {
+        const int tiles = (out_h + 7) / 8;
+        vg0.assign(tiles, 0);
+        bool fits = true;
+        for (int t = 0; t < tiles; t++) {
+            const int g0 = by[t * 8 * 2] >> 2;
+            vg0[t] = g0;
+            for (int r = 0; r < 8 && t * 8 + r < out_h; r++) {
+                const int oy = t * 8 + r;
+                if (by[oy * 2] < 4 * g0 || by[oy * 2] + by[oy * 2 + 1] > 4 * g0 + 64) fits = false;
+            }
+        }
+        if (fits) {
+            pl->vtiles = tiles;
+            vfrag.assign((size_t)tiles * 2 * 3 * 2 * 32, 0u);
+            for (int t = 0; t < tiles; t++)
+                for (int lane = 0; lane < 32; lane++) {
+                    const int oy = t * 8 + (lane >> 2);
+                    if (oy >= out_h) continue;
+                    const int ymin = by[oy * 2], ntap = by[oy * 2 + 1];
+                    for (int st = 0; st < 2; st++)
+                        for (int hf = 0; hf < 2; hf++)
+                            for (int e = 0; e < 4; e++) {
+                                const int row = 4 * vg0[t] + st * 32 + hf * 16 + (lane & 3) * 4 + e, tap = row - ymin;
+                                if (tap < 0 || tap >= ntap) continue;
+                                const int32_t c = cy[(size_t)oy * pl->ky + tap];
+                                const uint32_t bb[3] = {(uint32_t)c & 0xffu, ((uint32_t)c >> 8) & 0xffu, (uint32_t)(c >> 16) & 0xffu};
+                                for (int plane = 0; plane < 3; plane++)
+                                    vfrag[((((size_t)t * 2 + st) * 3 + plane) * 2 + hf) * 32 + lane] |= bb[plane] << (8 * e);
+                            }
+                }
+        }
+    }
     cudaGetDevice(&pl->device);
     auto up = [](int32_t **d, const std::vector<int32_t> &h) -> cudaError_t {
         cudaError_t e = cudaMalloc((void **)d, h.size() * sizeof(int32_t));
@@ -941,7 +989,8 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
     if ((e = up(&pl->d_bx, bx)) != cudaSuccess || (e = up(&pl->d_cx, cx)) != cudaSuccess ||
         (e = up(&pl->d_by, by)) != cudaSuccess || (e = up(&pl->d_cy, cy)) != cudaSuccess ||
         (e = upu(&pl->d_cxp, cxp)) != cudaSuccess || (e = upu(&pl->d_cyp, cyp)) != cudaSuccess ||
-        (pl->ksteps && ((e = upu(&pl->d_bfrag, bfrag)) != cudaSuccess || (e = up(&pl->d_kb, kbv)) != cudaSuccess))) {
+        (pl->ksteps && ((e = upu(&pl->d_bfrag, bfrag)) != cudaSuccess || (e = up(&pl->d_kb, kbv)) != cudaSuccess)) ||
+        (pl->vtiles && ((e = upu(&pl->d_vfrag, vfrag)) != cudaSuccess || (e = up(&pl->d_vg0, vg0)) != cudaSuccess))) {
         lumina_resize_plan_destroy(pl);
         return set_error(LUMINA_E_CUDA, "resize plan upload failed: %s", cudaGetErrorString(e));
     }
@@ -954,6 +1003,7 @@ LUMINA_API void lumina_resize_plan_destroy(lumina_resize_plan *pl) {
     cudaFree(pl->d_bx); cudaFree(pl->d_cx); cudaFree(pl->d_by); cudaFree(pl->d_cy);
     cudaFree(pl->d_cxp); cudaFree(pl->d_cyp);
     cudaFree(pl->d_bfrag); cudaFree(pl->d_kb);
+    cudaFree(pl->d_vfrag); cudaFree(pl->d_vg0);
     delete pl;
 }
 
@@ -1022,6 +1072,7 @@ static int launch_strip_bulk(const lumina_resize_plan *pl, const uint8_t *src, u
     p.in_h = pl->in_h; p.in_w = pl->in_w; p.out_h = pl->out_h; p.out_w = pl->out_w; p.kxw = pl->kxw; p.kyw = pl->kyw;
     p.src_total = (size_t)n * pl->in_h * pl->in_w * 3;
     p.segpx = 0;
+    p.vfrag = pl->d_vfrag; p.vg0 = pl->d_vg0;
     // a staged row holds every byte an A fragment reads: imma_span pixels from the strip's xs16
     p.copy_bytes = (pl->imma_span * 3 + 15) & ~15;
     p.rawpitch = p.copy_bytes;
@@ -1029,9 +1080,9 @@ static int launch_strip_bulk(const lumina_resize_plan *pl, const uint8_t *src, u
     const int strips = div_up(pl->out_w, TOW);
     int segs = 1;
     while ((long long)strips * segs * n < 4LL * kNumSMs * 4 && pl->out_h / (segs * 2) >= 64) segs *= 2;
-    p.rows_per_seg = div_up(pl->out_h, segs);
+    p.rows_per_seg = (div_up(pl->out_h, segs) + 7) & ~7;   // vertical tiles of 8 output rows are global
     segs = div_up(pl->out_h, p.rows_per_seg);
-    const size_t smem = (size_t)2 * RB * p.rawpitch + (size_t)RINGG * TOW * 3 * 4;
+    const size_t smem = (size_t)2 * RB * p.rawpitch + (size_t)RINGV * ROWP * 4;
     auto kern = resize_strip_bulk_kernel<KSTEPS>;
     if (smem > 48 * 1024) LUMINA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LUMINA_REQUIRE(n <= 65535 && segs <= 65535, "batch too large for grid");
@@ -1084,7 +1135,7 @@ LUMINA_API int lumina_resize_lanczos_u8(const lumina_resize_plan *pl, const uint
     }
     if (fused_ok(pl) && dp4a_ok(pl, d_src, c) && pl->ksteps && !getenv("LUMINA_RESIZE_DP4A")) {
         // measured on B200 (64 A4 pages -> 678x960): tensor-core horizontal pass vs dp4a, see DESIGN.md
-        if (pl->ksteps <= 2 && !getenv("LUMINA_RESIZE_STAGED")) {
+        if (pl->ksteps <= 2 && pl->vtiles && !getenv("LUMINA_RESIZE_STAGED")) {
             // measured on B200: bulk-staged interleaved rows vs staged + de-interleaved planes, see DESIGN.md
             if (pl->ksteps == 1) return launch_strip_bulk<1>(pl, d_src, d_dst, n, st);
             return launch_strip_bulk<2>(pl, d_src, d_dst, n, st);
