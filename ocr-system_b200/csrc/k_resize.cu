@@ -40,7 +40,7 @@ struct lumina_resize_plan {
     int imma_span;              // bytes of a staged plane row the A fragments may touch
     // tensor-core vertical pass: per tile of 8 output rows the B fragments over a K window of 64 intermediate rows
     uint32_t *d_vfrag;          // [out_h/8 tiles][2 k-steps][3 planes][2][32 lanes]
-    int32_t *d_vg0;             // [tiles] first ring row-group (input row / 4) of the tile's K window
+    int32_t *d_vg0;             // [tiles][2] first ring row-group (input row / 4) of the tile's K window, last tap row + 1
     int vtiles;                 // 0: path not available (a tile's taps do not fit 64 rows)
     int device;
 };
@@ -639,6 +639,7 @@ __device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 constexpr int RINGV = 32;    // ring row-groups of the bulk kernel: the 64-row K window of a tile + the chunk being written
+constexpr int kRound16 = 1 << (PREC_BITS - 1 - 16);   // 0.5 in fixed point before the two byte shifts of the plane sum
 constexpr int ROWP = TOW * 3 + 8;  // ring pitch in words (== 8 mod 32: the vertical fragments' 4 groups x 8 columns hit 32 banks)
 
 template <int KSTEPS>
@@ -649,7 +650,6 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
     uint8_t *raw = smem;                                                                  // [STAGES][RB][rawpitch]
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem + (size_t)STAGES * RB * p.rawpitch);  // [RINGV][ROWP] words of 4 rows
     __shared__ __align__(8) unsigned long long s_full[STAGES];
-    __shared__ int s_oy_end;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ox0 = blockIdx.x * TOW;
@@ -712,6 +712,7 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
     const int rawpitch_w = p.rawpitch >> 2;
     const int row_bytes = p.out_w * 3;
     int next_oy = oy0;           // first output row not yet written (a multiple of 8 until the segment's last tile)
+    int2 vmeta = __ldg(reinterpret_cast<const int2 *>(p.vg0) + (oy0 >> 3));   // {first ring row-group, last tap row + 1} of the pending tile
 
     for (int c = 0; c < nchunks; c++) {
         const int r0 = ys + c * RB;
@@ -740,10 +741,11 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
             uint8_t *ring_b = reinterpret_cast<uint8_t *>(ring);
             uint8_t *rp_lo = ring_b + ((size_t)((arow_lo >> 2) & (RINGV - 1)) * ROWP + (warp * 8 + tq * 2) * 3) * 4 + (arow_lo & 3);
             uint8_t *rp_hi = ring_b + ((size_t)((arow_hi >> 2) & (RINGV - 1)) * ROWP + (warp * 8 + tq * 2) * 3) * 4 + (arow_hi & 3);
-            const bool ok_lo = grp < nrows, ok_hi = grp + 8 < nrows;
+            // rows past the last chunk's end are computed from stale staging and stored too: their ring slots belong to
+            // rows beyond this segment's last tap, which no tile reads with a non-zero coefficient
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-                int acc[4] = {0, 0, 0, 0};
+                int acc[4] = {kRound16, kRound16, kRound16, kRound16};   // the rounding term, two byte shifts early
 #pragma unroll
                 for (int st = 0; st < KSTEPS; st++) mma_u8s8(acc, af[ch][st], bf[st][2][0], bf[st][2][1]);
 #pragma unroll
@@ -756,27 +758,19 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 for (int st = 0; st < KSTEPS; st++) mma_u8u8(acc, af[ch][st], bf[st][0][0], bf[st][0][1]);
                 // columns past out_w (last strip) land in ring columns nobody stores from
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int v = (int)((1u << (PREC_BITS - 1)) + (uint32_t)acc[i]);   // exact modulo 2^32; the true sum fits int32
-                    uint8_t *rp = (i >> 1) ? rp_hi : rp_lo;
-                    if ((i >> 1) ? ok_hi : ok_lo) rp[((i & 1) * 3 + ch) * 4] = clip8(v);
-                }
+                for (int i = 0; i < 4; i++) ((i >> 1) ? rp_hi : rp_lo)[((i & 1) * 3 + ch) * 4] = clip8(acc[i]);   // exact modulo 2^32; the true sum fits int32
             }
-        }
-        if (tid == 255) {  // which output rows have their whole tap window in the ring after this chunk
-            const int rows_done = r0 + nrows;
-            int oe = next_oy;
-            while (oe < oy1 && p.by[oe * 2] + p.by[oe * 2 + 1] <= rows_done) oe++;
-            s_oy_end = oe;
         }
         __syncthreads();   // the ring is complete, and nobody reads this chunk's staged rows any more
         if (warp == 0 && c + STAGES < nchunks) issue(c + STAGES);
         // ---- vertical pass on the tensor cores: tiles of 8 output rows (N) x 16 byte columns (M) x 64 ring rows (K).
         // A = the ring words themselves (4 consecutive rows of one byte column), B = the tile's coefficient fragments.
-        const int oy_end = s_oy_end;
-        while (next_oy < oy1 && (next_oy + 8 <= oy_end || oy_end == oy1)) {
+        // No barrier after it: the next chunk's horizontal pass writes ring rows this pass reads only against zero
+        // coefficients (the ring holds 128 rows, a tile's taps lie within the last 80).
+        const int rows_done = r0 + nrows;
+        while (next_oy < oy1 && vmeta.y <= rows_done) {       // the tile's last tap row is in the ring
             const int vt = next_oy >> 3;
-            const int g0 = __ldg(p.vg0 + vt);
+            const int g0 = vmeta.x;
             uint32_t vb[2][3][2];
 #pragma unroll
             for (int st = 0; st < 2; st++)
@@ -784,7 +778,12 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 for (int pl = 0; pl < 3; pl++)
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) vb[st][pl][hf] = __ldg(p.vfrag + ((((size_t)vt * 2 + st) * 3 + pl) * 2 + hf) * 32 + lane);
-            for (int mt = warp; mt < ROWB / 16; mt += 8) {
+            // 12 column tiles over 8 warps: the four extra ones alternate between the warp halves from tile to tile
+            const int extra = (((warp >> 2) ^ vt) & 1) ? -1 : 8 + (warp & 3);
+#pragma unroll 1
+            for (int rep = 0; rep < 2; rep++) {
+                const int mt = rep ? extra : warp;
+                if (mt < 0) break;
                 const int mb = mt * 16;
                 uint32_t va[2][4];
 #pragma unroll
@@ -793,7 +792,7 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                     const uint32_t *g_hi = ring + (size_t)((g0 + st * 8 + 4 + tq) & (RINGV - 1)) * ROWP + mb + grp;
                     va[st][0] = g_lo[0]; va[st][1] = g_lo[8]; va[st][2] = g_hi[0]; va[st][3] = g_hi[8];
                 }
-                int acc[4] = {0, 0, 0, 0};
+                int acc[4] = {kRound16, kRound16, kRound16, kRound16};
                 mma_u8s8(acc, va[0], vb[0][2][0], vb[0][2][1]);
                 mma_u8s8(acc, va[1], vb[1][2][0], vb[1][2][1]);
 #pragma unroll
@@ -808,13 +807,16 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 for (int i = 0; i < 4; i++) {
                     const int bcol = ox0 * 3 + mb + grp + (i >> 1) * 8;      // byte column of the page row
                     const int oy = next_oy + tq * 2 + (i & 1);
-                    if (bcol < row_bytes && oy < oy1)
-                        dst[(size_t)oy * row_bytes + bcol] = clip8((int)((1u << (PREC_BITS - 1)) + (uint32_t)acc[i]));
+                    if (bcol < row_bytes && oy < oy1) dst[(size_t)oy * row_bytes + bcol] = clip8(acc[i]);
                 }
             }
             next_oy = min(next_oy + 8, oy1);
+            if (next_oy < oy1) {
+                vmeta = __ldg(reinterpret_cast<const int2 *>(p.vg0) + (next_oy >> 3));
+                // warm L1 with the next tile's fragments (12 lines of 128 bytes): they are needed a chunk or two from now
+                if (lane < 12) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.vfrag + ((size_t)(next_oy >> 3) * 12 + lane) * 32));
+            }
         }
-        __syncthreads();
     }
 }
 
@@ -943,11 +945,13 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
     std::vector<int32_t> vg0;
     {
         const int tiles = (out_h + 7) / 8;
-        vg0.assign(tiles, 0);
+        vg0.assign((size_t)tiles * 2, 0);
         bool fits = true;
         for (int t = 0; t < tiles; t++) {
             const int g0 = by[t * 8 * 2] >> 2;
-            vg0[t] = g0;
+            const int last = (t * 8 + 7 < out_h ? t * 8 + 7 : out_h - 1);
+            vg0[t * 2] = g0;
+            vg0[t * 2 + 1] = by[last * 2] + by[last * 2 + 1];   // the tile is complete once this many rows are in the ring
             for (int r = 0; r < 8 && t * 8 + r < out_h; r++) {
                 const int oy = t * 8 + r;
                 if (by[oy * 2] < 4 * g0 || by[oy * 2] + by[oy * 2 + 1] > 4 * g0 + 64) fits = false;
@@ -964,7 +968,7 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
                     for (int st = 0; st < 2; st++)
                         for (int hf = 0; hf < 2; hf++)
                             for (int e = 0; e < 4; e++) {
-                                const int row = 4 * vg0[t] + st * 32 + hf * 16 + (lane & 3) * 4 + e, tap = row - ymin;
+                                const int row = 4 * vg0[t * 2] + st * 32 + hf * 16 + (lane & 3) * 4 + e, tap = row - ymin;
                                 if (tap < 0 || tap >= ntap) continue;
                                 const int32_t c = cy[(size_t)oy * pl->ky + tap];
                                 const uint32_t bb[3] = {(uint32_t)c & 0xffu, ((uint32_t)c >> 8) & 0xffu, (uint32_t)(c >> 16) & 0xffu};

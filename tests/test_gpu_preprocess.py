@@ -46,6 +46,21 @@ def test_resize_lanczos_rgb(oracle, cuda, h, w, md):
     assert np.array_equal(got, oracle.resize_lanczos(img, tw, th))
 
 
+@pytest.mark.parametrize("n,h,w,tw,th", [(1, 1024, 1600, 600, 384), (1, 777, 1264, 333, 205), (1, 900, 640, 470, 661),
+                                         (3, 1200, 848, 300, 424), (1, 2150, 1600, 372, 500), (2, 2300, 1600, 347, 499),
+                                         (2, 640, 1008, 401, 255)])
+def test_resize_lanczos_tensor_core_shapes(oracle, cuda, n, h, w, tw, th):
+    """Widths that are multiples of 16 take the bulk-staged tensor-core kernel (k_resize.cu): scales 1.36-4.6 (one and
+    two K steps; the largest falls back to the staged kernel because a vertical tile's taps exceed 64 rows), output
+    sizes that are not multiples of 8 / 64, batches (the last rows of the batch are cut at the end of the buffer)."""
+    from ocr_system_b200 import ops
+
+    imgs = np.stack([_rand(h, w, 3, 11 + i) for i in range(n)])
+    got = ops.resize_lanczos(_t(imgs, cuda), tw, th).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], oracle.resize_lanczos(imgs[i], tw, th)), i
+
+
 def test_resize_lanczos_gray_batch_and_one_axis(oracle, cuda):
     from ocr_system_b200 import ops
 
