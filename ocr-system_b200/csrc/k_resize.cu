@@ -42,6 +42,7 @@ struct lumina_resize_plan {
     uint32_t *d_vfrag;          // [out_h/8 tiles][2 k-steps][3 planes][2][32 lanes]
     int32_t *d_vg0;             // [tiles][2] first ring row-group (input row / 4) of the tile's K window, last tap row + 1
     int vtiles;                 // 0: path not available (a tile's taps do not fit 64 rows)
+    int vsteps;                 // K steps of 32 ring rows a vertical tile needs (1: every tile's taps fit 32 rows; 2)
     int device;
 };
 
@@ -642,7 +643,7 @@ constexpr int RINGV = 32;    // ring row-groups of the bulk kernel: the 64-row K
 constexpr int kRound16 = 1 << (PREC_BITS - 1 - 16);   // 0.5 in fixed point before the two byte shifts of the plane sum
 constexpr int ROWP = TOW * 3 + 8;  // ring pitch in words (== 8 mod 32: the vertical fragments' 4 groups x 8 columns hit 32 banks)
 
-template <int KSTEPS>
+template <int KSTEPS, int VSTEPS>
 __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeDp4aParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int ROWB = TOW * 3;
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
         }
         __syncthreads();   // the ring is complete, and nobody reads this chunk's staged rows any more
         if (warp == 0 && c + STAGES < nchunks) issue(c + STAGES);
-        // ---- vertical pass on the tensor cores: tiles of 8 output rows (N) x 16 byte columns (M) x 64 ring rows (K).
+        // ---- vertical pass on the tensor cores: tiles of 8 output rows (N) x 16 byte columns (M) x 32 * VSTEPS ring rows (K).
         // A = the ring words themselves (4 consecutive rows of one byte column), B = the tile's coefficient fragments.
         // No barrier after it: the next chunk's horizontal pass writes ring rows this pass reads only against zero
         // coefficients (the ring holds 128 rows, a tile's taps lie within the last 80).
@@ -771,9 +772,9 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
         while (next_oy < oy1 && vmeta.y <= rows_done) {       // the tile's last tap row is in the ring
             const int vt = next_oy >> 3;
             const int g0 = vmeta.x;
-            uint32_t vb[2][3][2];
+            uint32_t vb[VSTEPS][3][2];
 #pragma unroll
-            for (int st = 0; st < 2; st++)
+            for (int st = 0; st < VSTEPS; st++)
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++)
 #pragma unroll
@@ -785,24 +786,24 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 const int mt = rep ? extra : warp;
                 if (mt < 0) break;
                 const int mb = mt * 16;
-                uint32_t va[2][4];
+                uint32_t va[VSTEPS][4];
 #pragma unroll
-                for (int st = 0; st < 2; st++) {
+                for (int st = 0; st < VSTEPS; st++) {
                     const uint32_t *g_lo = ring + (size_t)((g0 + st * 8 + tq) & (RINGV - 1)) * ROWP + mb + grp;
                     const uint32_t *g_hi = ring + (size_t)((g0 + st * 8 + 4 + tq) & (RINGV - 1)) * ROWP + mb + grp;
                     va[st][0] = g_lo[0]; va[st][1] = g_lo[8]; va[st][2] = g_hi[0]; va[st][3] = g_hi[8];
                 }
                 int acc[4] = {kRound16, kRound16, kRound16, kRound16};
-                mma_u8s8(acc, va[0], vb[0][2][0], vb[0][2][1]);
-                mma_u8s8(acc, va[1], vb[1][2][0], vb[1][2][1]);
+#pragma unroll
+                for (int st = 0; st < VSTEPS; st++) mma_u8s8(acc, va[st], vb[st][2][0], vb[st][2][1]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
-                mma_u8u8(acc, va[0], vb[0][1][0], vb[0][1][1]);
-                mma_u8u8(acc, va[1], vb[1][1][0], vb[1][1][1]);
+#pragma unroll
+                for (int st = 0; st < VSTEPS; st++) mma_u8u8(acc, va[st], vb[st][1][0], vb[st][1][1]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
-                mma_u8u8(acc, va[0], vb[0][0][0], vb[0][0][1]);
-                mma_u8u8(acc, va[1], vb[1][0][0], vb[1][0][1]);
+#pragma unroll
+                for (int st = 0; st < VSTEPS; st++) mma_u8u8(acc, va[st], vb[st][0][0], vb[st][0][1]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int bcol = ox0 * 3 + mb + grp + (i >> 1) * 8;      // byte column of the page row
@@ -940,13 +941,13 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
     }
     // tensor-core vertical pass: tiles of 8 output rows; K = 64 intermediate rows from the 4-row group that holds the
     // tile's first tap (B fragment of mma.m16n8k32: lane l holds output row l >> 2, K rows (l & 3) * 4 .. + 3 and + 16)
-    pl->d_vfrag = nullptr; pl->d_vg0 = nullptr; pl->vtiles = 0;
+    pl->d_vfrag = nullptr; pl->d_vg0 = nullptr; pl->vtiles = 0; pl->vsteps = 2;
     std::vector<uint32_t> vfrag;
     std::vector<int32_t> vg0;
     {
         const int tiles = (out_h + 7) / 8;
         vg0.assign((size_t)tiles * 2, 0);
-        bool fits = true;
+        bool fits = true, fits32 = true;
         for (int t = 0; t < tiles; t++) {
             const int g0 = by[t * 8 * 2] >> 2;
             const int last = (t * 8 + 7 < out_h ? t * 8 + 7 : out_h - 1);
@@ -955,10 +956,12 @@ LUMINA_API int lumina_resize_plan_create(int in_h, int in_w, int out_h, int out_
             for (int r = 0; r < 8 && t * 8 + r < out_h; r++) {
                 const int oy = t * 8 + r;
                 if (by[oy * 2] < 4 * g0 || by[oy * 2] + by[oy * 2 + 1] > 4 * g0 + 64) fits = false;
+                if (by[oy * 2] + by[oy * 2 + 1] > 4 * g0 + 32) fits32 = false;
             }
         }
         if (fits) {
             pl->vtiles = tiles;
+            pl->vsteps = fits32 ? 1 : 2;   // scales below ~2.2: the second K step would only meet zero coefficients
             vfrag.assign((size_t)tiles * 2 * 3 * 2 * 32, 0u);
             for (int t = 0; t < tiles; t++)
                 for (int lane = 0; lane < 32; lane++) {
@@ -1068,7 +1071,7 @@ static int launch_strip_dp4a(const lumina_resize_plan *pl, const uint8_t *src, u
     return LUMINA_OK;
 }
 
-template <int KSTEPS>
+template <int KSTEPS, int VSTEPS>
 static int launch_strip_bulk(const lumina_resize_plan *pl, const uint8_t *src, uint8_t *dst, int n, cudaStream_t st) {
     ResizeDp4aParams p;
     p.src = src; p.dst = dst; p.bx = pl->d_bx; p.by = pl->d_by; p.cxp = pl->d_cxp; p.cyp = pl->d_cyp;
@@ -1087,7 +1090,7 @@ static int launch_strip_bulk(const lumina_resize_plan *pl, const uint8_t *src, u
     p.rows_per_seg = (div_up(pl->out_h, segs) + 7) & ~7;   // vertical tiles of 8 output rows are global
     segs = div_up(pl->out_h, p.rows_per_seg);
     const size_t smem = (size_t)2 * RB * p.rawpitch + (size_t)RINGV * ROWP * 4;
-    auto kern = resize_strip_bulk_kernel<KSTEPS>;
+    auto kern = resize_strip_bulk_kernel<KSTEPS, VSTEPS>;
     if (smem > 48 * 1024) LUMINA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LUMINA_REQUIRE(n <= 65535 && segs <= 65535, "batch too large for grid");
     kern<<<dim3(strips, segs, n), 256, smem, st>>>(p);
@@ -1141,8 +1144,8 @@ LUMINA_API int lumina_resize_lanczos_u8(const lumina_resize_plan *pl, const uint
         // measured on B200 (64 A4 pages -> 678x960): tensor-core horizontal pass vs dp4a, see DESIGN.md
         if (pl->ksteps <= 2 && pl->vtiles && !getenv("LUMINA_RESIZE_STAGED")) {
             // measured on B200: bulk-staged interleaved rows vs staged + de-interleaved planes, see DESIGN.md
-            if (pl->ksteps == 1) return launch_strip_bulk<1>(pl, d_src, d_dst, n, st);
-            return launch_strip_bulk<2>(pl, d_src, d_dst, n, st);
+            if (pl->ksteps == 1) return pl->vsteps == 1 ? launch_strip_bulk<1, 1>(pl, d_src, d_dst, n, st) : launch_strip_bulk<1, 2>(pl, d_src, d_dst, n, st);
+            return pl->vsteps == 1 ? launch_strip_bulk<2, 1>(pl, d_src, d_dst, n, st) : launch_strip_bulk<2, 2>(pl, d_src, d_dst, n, st);
         }
         if (pl->ksteps == 1) return launch_strip_imma<1>(pl, d_src, d_dst, n, st);
         if (pl->ksteps == 2) return launch_strip_imma<2>(pl, d_src, d_dst, n, st);
