@@ -109,6 +109,8 @@ struct ResizeParams {
 };
 
 __device__ __forceinline__ uint8_t clip8(int v) { return (uint8_t)min(max(v >> PREC_BITS, 0), 255); }
+// same value, one VIMNMX.RELU: max(min(v >> 22, 255), 0)
+__device__ __forceinline__ int clip8r(int v) { return __vimin_s32_relu(v >> PREC_BITS, 255); }
 
 // C channels, KX = compile-time bound on horizontal taps (kx <= KX)
 template <int C, int KX>
@@ -759,7 +761,7 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 for (int st = 0; st < KSTEPS; st++) mma_u8u8(acc, af[ch][st], bf[st][0][0], bf[st][0][1]);
                 // columns past out_w (last strip) land in ring columns nobody stores from
 #pragma unroll
-                for (int i = 0; i < 4; i++) ((i >> 1) ? rp_hi : rp_lo)[((i & 1) * 3 + ch) * 4] = clip8(acc[i]);   // exact modulo 2^32; the true sum fits int32
+                for (int i = 0; i < 4; i++) ((i >> 1) ? rp_hi : rp_lo)[((i & 1) * 3 + ch) * 4] = (uint8_t)clip8r(acc[i]);   // exact modulo 2^32; the true sum fits int32
             }
         }
         __syncthreads();   // the ring is complete, and nobody reads this chunk's staged rows any more
@@ -779,6 +781,9 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 for (int pl = 0; pl < 3; pl++)
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) vb[st][pl][hf] = __ldg(p.vfrag + ((((size_t)vt * 2 + st) * 3 + pl) * 2 + hf) * 32 + lane);
+            const int col0 = ox0 * 3;
+            uint8_t *dtile = dst + (size_t)(next_oy + tq * 2) * row_bytes + col0 + grp;
+            const bool full_rows = next_oy + 8 <= oy1;
             // 12 column tiles over 8 warps: the four extra ones alternate between the warp halves from tile to tile
             const int extra = (((warp >> 2) ^ vt) & 1) ? -1 : 8 + (warp & 3);
 #pragma unroll 1
@@ -804,11 +809,18 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                 for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
 #pragma unroll
                 for (int st = 0; st < VSTEPS; st++) mma_u8u8(acc, va[st], vb[st][0][0], vb[st][0][1]);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int bcol = ox0 * 3 + mb + grp + (i >> 1) * 8;      // byte column of the page row
-                    const int oy = next_oy + tq * 2 + (i & 1);
-                    if (bcol < row_bytes && oy < oy1) dst[(size_t)oy * row_bytes + bcol] = clip8(acc[i]);
+                // lane (grp, tq) holds byte columns grp, grp + 8 of output rows 2 tq, 2 tq + 1: one address per column tile
+                uint8_t *o = dtile + mb;
+                if (full_rows && col0 + mb + 16 <= row_bytes) {
+                    o[0] = (uint8_t)clip8r(acc[0]); o[row_bytes] = (uint8_t)clip8r(acc[1]);
+                    o[8] = (uint8_t)clip8r(acc[2]); o[row_bytes + 8] = (uint8_t)clip8r(acc[3]);
+                } else {
+                    const bool c0 = col0 + mb + grp < row_bytes, c1 = col0 + mb + grp + 8 < row_bytes;
+                    const bool r0ok = next_oy + tq * 2 < oy1, r1ok = next_oy + tq * 2 + 1 < oy1;
+                    if (c0 && r0ok) o[0] = (uint8_t)clip8r(acc[0]);
+                    if (c0 && r1ok) o[row_bytes] = (uint8_t)clip8r(acc[1]);
+                    if (c1 && r0ok) o[8] = (uint8_t)clip8r(acc[2]);
+                    if (c1 && r1ok) o[row_bytes + 8] = (uint8_t)clip8r(acc[3]);
                 }
             }
             next_oy = min(next_oy + 8, oy1);
