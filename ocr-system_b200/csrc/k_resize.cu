@@ -21,6 +21,10 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>   // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no libcuda link)
+#include <cudaTypedefs.h>
+#include <string.h>
+
 #include "common.cuh"
 
 struct lumina_resize_plan {
@@ -645,8 +649,8 @@ constexpr int RINGV = 32;    // ring row-groups of the bulk kernel: the 64-row K
 constexpr int kRound16 = 1 << (PREC_BITS - 1 - 16);   // 0.5 in fixed point before the two byte shifts of the plane sum
 constexpr int ROWP = TOW * 3 + 8;  // ring pitch in words (== 8 mod 32: the vertical fragments' 4 groups x 8 columns hit 32 banks)
 
-template <int KSTEPS, int VSTEPS>
-__global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeDp4aParams p) {
+template <int KSTEPS, int VSTEPS, bool TMA>
+__global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeDp4aParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int ROWB = TOW * 3;
     constexpr int STAGES = 2;
@@ -668,34 +672,45 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
     const int nchunks = (ye - ys + RB - 1) / RB;
     const uint8_t *src_end = p.src + p.src_total;
 
-    // warp 0 issues the bulk copies of a chunk, one row per lane (the last rows of the batch are cut at its end; what
-    // stays stale in shared memory only meets zero coefficients)
+    // TMA == true: one thread fetches a whole chunk (16 rows x rawpitch bytes of the batch seen as a 2-D tensor of 32-bit
+    // words, row pitch = page row pitch) with a single cp.async.bulk.tensor; words past a row end or past the batch end
+    // are zero-filled by the copy engine.  TMA == false (rows wider than a 256-element box): every warp issues the bulk
+    // copies of two rows (a copy instruction is warp-uniform, so n rows issued by one warp are n serial iterations) and
+    // arrives on the chunk's barrier with its byte count; the last rows of the batch are cut at its end.  What stays
+    // stale, zero or foreign in shared memory only meets zero coefficients.
     auto issue = [&](int c) {
         const int buf = c % STAGES;
         const int r0 = ys + c * RB, nrows = min(RB, ye - r0);
         const uint32_t bar = rs_smem_u32(&s_full[buf]);
-        const uint8_t *gp = src + (size_t)(r0 + lane) * pitch + (size_t)xs16 * 3;
+        if (TMA) {
+            if (tid == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(RB * p.rawpitch)) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(rs_smem_u32(raw + (size_t)buf * RB * p.rawpitch)), "l"(&tmap), "r"((xs16 * 3) >> 2),
+                               "r"(page * p.in_h + r0), "r"(bar) : "memory");
+            }
+            return;
+        }
+        const int row = warp * 2 + (lane & 1);
+        const uint8_t *gp = src + (size_t)(r0 + row) * pitch + (size_t)xs16 * 3;
         const long long left = src_end - gp;
-        const uint32_t bytes = lane < nrows ? (uint32_t)(left < p.copy_bytes ? left : p.copy_bytes) : 0u;
-        uint32_t total = bytes;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        const uint32_t bytes = row < nrows ? (uint32_t)(left < p.copy_bytes ? left : p.copy_bytes) : 0u;
+        const uint32_t total = bytes + __shfl_xor_sync(0xffffffffu, bytes, 1);
         if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-        __syncwarp();
-        if (bytes) {
-            const uint32_t d = rs_smem_u32(raw + ((size_t)buf * RB + lane) * p.rawpitch);
+        if (lane < 2 && bytes) {
+            const uint32_t d = rs_smem_u32(raw + ((size_t)buf * RB + row) * p.rawpitch);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(d), "l"(gp), "r"(bytes), "r"(bar) : "memory");
         }
     };
     if (tid == 0) {
         for (int i = 0; i < STAGES; i++)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(&s_full[i])), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(&s_full[i])), "r"(TMA ? 1 : 8) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     __syncthreads();
-    if (warp == 0)
-        for (int c = 0; c < STAGES && c < nchunks; c++) issue(c);
+    for (int c = 0; c < STAGES && c < nchunks; c++) issue(c);
 
     // this warp's 8-column tile: B fragments (3 byte planes x KSTEPS x 2 registers) and the start of its K window
     const int tile = blockIdx.x * (TOW / 8) + warp;
@@ -765,7 +780,7 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
             }
         }
         __syncthreads();   // the ring is complete, and nobody reads this chunk's staged rows any more
-        if (warp == 0 && c + STAGES < nchunks) issue(c + STAGES);
+        if (c + STAGES < nchunks) issue(c + STAGES);
         // ---- vertical pass on the tensor cores: tiles of 8 output rows (N) x 16 byte columns (M) x 32 * VSTEPS ring rows (K).
         // A = the ring words themselves (4 consecutive rows of one byte column), B = the tile's coefficient fragments.
         // No barrier after it: the next chunk's horizontal pass writes ring rows this pass reads only against zero
@@ -1102,10 +1117,35 @@ static int launch_strip_bulk(const lumina_resize_plan *pl, const uint8_t *src, u
     p.rows_per_seg = (div_up(pl->out_h, segs) + 7) & ~7;   // vertical tiles of 8 output rows are global
     segs = div_up(pl->out_h, p.rows_per_seg);
     const size_t smem = (size_t)2 * RB * p.rawpitch + (size_t)RINGV * ROWP * 4;
-    auto kern = resize_strip_bulk_kernel<KSTEPS, VSTEPS>;
-    if (smem > 48 * 1024) LUMINA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LUMINA_REQUIRE(n <= 65535 && segs <= 65535, "batch too large for grid");
-    kern<<<dim3(strips, segs, n), 256, smem, st>>>(p);
+    // the batch as a 2-D tensor of 32-bit words [n * in_h rows][in_w * 3 / 4], box = one staged chunk (16 rows x rawpitch bytes)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    bool tma = p.rawpitch <= 1024 && (pl->in_w * 3) % 16 == 0 && !getenv("LUMINA_RESIZE_NO_TMA");
+    if (tma) {
+        static PFN_cuTensorMapEncodeTiled encode = [] {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
+            return (PFN_cuTensorMapEncodeTiled)fn;
+        }();
+        const cuuint64_t dims[2] = {(cuuint64_t)(pl->in_w * 3 / 4), (cuuint64_t)n * (cuuint64_t)pl->in_h};
+        const cuuint64_t strides[1] = {(cuuint64_t)pl->in_w * 3};
+        const cuuint32_t box[2] = {(cuuint32_t)(p.rawpitch / 4), (cuuint32_t)RB};
+        const cuuint32_t estr[2] = {1, 1};
+        tma = encode && encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(src), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (tma) {
+        auto kern = resize_strip_bulk_kernel<KSTEPS, VSTEPS, true>;
+        if (smem > 48 * 1024) LUMINA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3(strips, segs, n), 256, smem, st>>>(p, tmap);
+    } else {
+        auto kern = resize_strip_bulk_kernel<KSTEPS, VSTEPS, false>;
+        if (smem > 48 * 1024) LUMINA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3(strips, segs, n), 256, smem, st>>>(p, tmap);
+    }
     LUMINA_KERNEL_CHECK("resize_strip_bulk_kernel");
     return LUMINA_OK;
 }
