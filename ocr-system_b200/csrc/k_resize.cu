@@ -458,6 +458,13 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], ui
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// first MMA of a chain: C = 0 (the zero register, no accumulator initialisation)
+__device__ __forceinline__ void mma_u8s8_z(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0));
+}
+
 template <int KSTEPS>
 __global__ void __launch_bounds__(256, 4) resize_strip_imma_kernel(const ResizeDp4aParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -646,7 +653,7 @@ __device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 constexpr int RINGV = 32;    // ring row-groups of the bulk kernel: the 64-row K window of a tile + the chunk being written
-constexpr int kRound16 = 1 << (PREC_BITS - 1 - 16);   // 0.5 in fixed point before the two byte shifts of the plane sum
+constexpr uint32_t kRound = 1u << (PREC_BITS - 1);   // 0.5 in fixed point, added with the second byte shift of the plane sum
 constexpr int ROWP = TOW * 3 + 8;  // ring pitch in words (== 8 mod 32: the vertical fragments' 4 groups x 8 columns hit 32 banks)
 
 template <int KSTEPS, int VSTEPS, bool TMA>
@@ -763,15 +770,16 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
             // rows beyond this segment's last tap, which no tile reads with a non-zero coefficient
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-                int acc[4] = {kRound16, kRound16, kRound16, kRound16};   // the rounding term, two byte shifts early
+                int acc[4];
+                mma_u8s8_z(acc, af[ch][0], bf[0][2][0], bf[0][2][1]);
 #pragma unroll
-                for (int st = 0; st < KSTEPS; st++) mma_u8s8(acc, af[ch][st], bf[st][2][0], bf[st][2][1]);
+                for (int st = 1; st < KSTEPS; st++) mma_u8s8(acc, af[ch][st], bf[st][2][0], bf[st][2][1]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
 #pragma unroll
                 for (int st = 0; st < KSTEPS; st++) mma_u8u8(acc, af[ch][st], bf[st][1][0], bf[st][1][1]);
 #pragma unroll
-                for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
+                for (int i = 0; i < 4; i++) acc[i] = (int)(((uint32_t)acc[i] << 8) + kRound);   // the rounding term rides on the shift
 #pragma unroll
                 for (int st = 0; st < KSTEPS; st++) mma_u8u8(acc, af[ch][st], bf[st][0][0], bf[st][0][1]);
                 // columns past out_w (last strip) land in ring columns nobody stores from
@@ -813,15 +821,16 @@ __global__ void __launch_bounds__(256, 4) resize_strip_bulk_kernel(const ResizeD
                     const uint32_t *g_hi = ring + (size_t)((g0 + st * 8 + 4 + tq) & (RINGV - 1)) * ROWP + mb + grp;
                     va[st][0] = g_lo[0]; va[st][1] = g_lo[8]; va[st][2] = g_hi[0]; va[st][3] = g_hi[8];
                 }
-                int acc[4] = {kRound16, kRound16, kRound16, kRound16};
+                int acc[4];
+                mma_u8s8_z(acc, va[0], vb[0][2][0], vb[0][2][1]);
 #pragma unroll
-                for (int st = 0; st < VSTEPS; st++) mma_u8s8(acc, va[st], vb[st][2][0], vb[st][2][1]);
+                for (int st = 1; st < VSTEPS; st++) mma_u8s8(acc, va[st], vb[st][2][0], vb[st][2][1]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
 #pragma unroll
                 for (int st = 0; st < VSTEPS; st++) mma_u8u8(acc, va[st], vb[st][1][0], vb[st][1][1]);
 #pragma unroll
-                for (int i = 0; i < 4; i++) acc[i] = (int)((uint32_t)acc[i] << 8);
+                for (int i = 0; i < 4; i++) acc[i] = (int)(((uint32_t)acc[i] << 8) + kRound);
 #pragma unroll
                 for (int st = 0; st < VSTEPS; st++) mma_u8u8(acc, va[st], vb[st][0][0], vb[st][0][1]);
                 // lane (grp, tq) holds byte columns grp, grp + 8 of output rows 2 tq, 2 tq + 1: one address per column tile
