@@ -617,7 +617,7 @@ def bench_chain(cx: Ctx):
         "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_unp),
         "clocks": clocks,
         "roofline": {
-            "kernel": "resize kernel (fused PIL-Lanczos H+V, dominant HBM byte mover)",
+            "kernel": "resize_strip_bulk_kernel<2,2,true> (fused PIL-Lanczos H+V, TMA-staged, int8 mma.sync in both passes; the dominant HBM byte mover)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes,
