@@ -61,6 +61,24 @@ def test_resize_lanczos_tensor_core_shapes(oracle, cuda, n, h, w, tw, th):
         assert np.array_equal(got[i], oracle.resize_lanczos(imgs[i], tw, th)), i
 
 
+@pytest.mark.parametrize("env", ["", "LUMINA_RESIZE_NO_TMA", "LUMINA_RESIZE_STAGED", "LUMINA_RESIZE_DP4A"])
+def test_resize_lanczos_kernel_variants_and_batch_slices(oracle, cuda, env, monkeypatch):
+    """The shipped kernel stages chunks with one TMA tensor copy; the per-row bulk-copy form (spans wider than a TMA box),
+    the plane-staged tensor-core kernel and the dp4a kernel stay as fallbacks -- all four give the reference's bytes, also
+    on a batch that starts inside a larger allocation (the tensor map is built on the slice) and on the last page of the
+    allocation (copies / boxes that reach past the end)."""
+    from ocr_system_b200 import ops
+
+    if env:
+        monkeypatch.setenv(env, "1")
+    imgs = np.stack([_rand(700, 1008, 3, 31 + i) for i in range(3)])
+    x = _t(imgs, cuda)
+    for sl, (tw, th) in ((slice(1, 3), (275, 191)), (slice(0, 3), (575, 399)), (slice(2, 3), (230, 160))):
+        got = ops.resize_lanczos(x[sl], tw, th).cpu().numpy()
+        for k, i in enumerate(range(*sl.indices(3))):
+            assert np.array_equal(got[k], oracle.resize_lanczos(imgs[i], tw, th)), (env, sl, i)
+
+
 def test_resize_lanczos_gray_batch_and_one_axis(oracle, cuda):
     from ocr_system_b200 import ops
 
