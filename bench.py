@@ -894,18 +894,21 @@ def bench_stream(cx: Ctx, top: bool):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     e2e_ms = 0.0
-    if args.stream_e2e and sizes:
-        host_pool = [torch.empty(pool[k][0].shape, dtype=torch.uint8, pin_memory=True) for k in range(POOL)]
-        for k in range(POOL):
-            host_pool[k].copy_(pool[k][0])
-        pinned = [(torch.empty(B, dtype=torch.int32, pin_memory=True), torch.empty(B * cpp, dtype=torch.int32, pin_memory=True),
-                   torch.empty(B * cpp, dtype=torch.float32, pin_memory=True)) for _ in range(2)]
-        torch.cuda.synchronize()
-        sizes = full[:2]
-        run_from_host(host_pool, pinned)       # warm-up (pinned result slots, upload double buffer)
-        sizes = full
-        cx.barrier()
-        e2e_ms = run_from_host(host_pool, pinned)
+    if args.stream_e2e:
+        host_pool = pinned = None
+        if sizes:
+            host_pool = [torch.empty(pool[k][0].shape, dtype=torch.uint8, pin_memory=True) for k in range(POOL)]
+            for k in range(POOL):
+                host_pool[k].copy_(pool[k][0])
+            pinned = [(torch.empty(B, dtype=torch.int32, pin_memory=True), torch.empty(B * cpp, dtype=torch.int32, pin_memory=True),
+                       torch.empty(B * cpp, dtype=torch.float32, pin_memory=True)) for _ in range(2)]
+            torch.cuda.synchronize()
+            sizes = full[:2]
+            run_from_host(host_pool, pinned)       # warm-up (pinned result slots, upload double buffer)
+            sizes = full
+        cx.barrier()                               # every rank, also one whose shard is empty
+        if sizes:
+            e2e_ms = run_from_host(host_pool, pinned)
     cx.barrier()
     hot_max = cx.max_over_ranks(hot_ms)
     e2e_max = cx.max_over_ranks(e2e_ms)
