@@ -663,6 +663,7 @@ static int ppht_run(const uint8_t *d_edges, int n, int h, int w, double rho_d, d
         LUMINA_CUDA_TRY(cudaFuncGetAttributes(&fa, ppht_order_kernel));
         long long cap = ((long long)max_optin - (long long)fa.sharedSizeBytes - 256) / 4;
         if (cap > (long long)h * w) cap = (long long)h * w;
+        if (const char *e = getenv("LUMINA_PPHT_ORDER_CAP")) { const long long c = atoll(e); if (c > 0 && c < cap) cap = c; }   // experiment knob
         if (cap < 32) cap = 32;
         LUMINA_CUDA_TRY(cudaFuncSetAttribute(ppht_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cap * 4)));
         ppht_order_kernel<<<n, PORD_THREADS, (size_t)cap * 4, st>>>((uint32_t *)(ws + L.nz_off), (uint32_t *)(ws + L.order_off),
