@@ -341,8 +341,10 @@ __global__ void __launch_bounds__(PPI_THREADS) ppht_cluster_pipe_kernel(const Pp
         const int status = s_status, nxt_ok = s_nxt_ok;
         if (status == 0 && nxt_ok) {
             // commit: `nxt` becomes the batch to judge, the prepared batch becomes `nxt`
+            if (is_row_warp) {   // only the row warps keep rho tables; the control warp goes straight to the next exchange
 #pragma unroll
-            for (int j = 0; j < PCL_B; j++) rr_cur[j] = rr_nxt[j];
+                for (int j = 0; j < PCL_B; j++) rr_cur[j] = rr_nxt[j];
+            }
             pos_cur = pos_nxt; nb_cur = nb_nxt; qc = qn;
             have_cur = nb_nxt > 0;
             pos_nxt += nb_nxt; qn ^= 1;
