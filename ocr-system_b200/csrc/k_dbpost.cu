@@ -197,6 +197,166 @@ __global__ void __launch_bounds__(256) db_ccl_merge_kernel(const uint8_t *__rest
     }
 }
 
+// ---- tile-local labelling (w % 4 == 0): a CTA labels a 32-row x 128-column tile entirely in shared memory (row runs, unions
+// with shared-memory atomics, local flatten) and writes every pixel's label as the PAGE index of its tile-local root; the
+// links that cross a tile border are made afterwards on those labels (db_ccl_border_kernel), then the usual flatten.  Local
+// raster order equals page raster order inside a tile, so roots stay "minimum raster index" and the final labels are the
+// same as the global union-find's.
+constexpr int DBT_W = 128, DBT_H = 32;
+
+__device__ __forceinline__ int dbt_find(const int *L, int a) {
+    int p = L[a];
+    while (p != a) { a = p; p = L[a]; }
+    return a;
+}
+__device__ __forceinline__ void dbt_union(int *L, int a, int b) {
+    bool done;
+    do {
+        a = dbt_find(L, a);
+        b = dbt_find(L, b);
+        if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(256) db_ccl_tile_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h, int w,
+                                                          int tiles_x, int tiles_y) {
+    __shared__ __align__(16) int sl[DBT_H * DBT_W];
+    __shared__ uint32_t scls[DBT_H][DBT_W / 32], sval[DBT_H][DBT_W / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, page = blockIdx.x / (tiles_x * tiles_y);
+    const int x0t = tx * DBT_W, y0t = ty * DBT_H;
+    const size_t hw = (size_t)h * w;
+    const uint8_t *M = mask + (size_t)page * hw;
+    int *L = labels + (size_t)page * hw;
+    const int lx0 = lane * 4, sub = lane & 7;
+    // phase 1: class / validity bits of the tile, row runs inside 32-pixel segments
+#pragma unroll
+    for (int i = 0; i < DBT_H / 8; i++) {
+        const int ly = i * 8 + warp, y = y0t + ly, x = x0t + lx0;
+        uint32_t bits = 0, val = 0;
+        if (y < h) {
+            if (x + 4 <= w) { bits = db_class4(M + (size_t)y * w + x); val = 0xFu; }
+            else for (int k = 0; k < 4; k++) if (x + k < w) { bits |= (uint32_t)(M[(size_t)y * w + x + k] & 1) << k; val |= 1u << k; }
+        }
+        uint32_t seg = bits << (4 * sub), vseg = val << (4 * sub);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            seg |= __shfl_xor_sync(0xffffffffu, seg, o);
+            vseg |= __shfl_xor_sync(0xffffffffu, vseg, o);
+        }
+        int out[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pos = 4 * sub + k;
+            const uint32_t c = (seg >> pos) & 1u;
+            const uint32_t same = (c ? seg : ~seg) & vseg;
+            const uint32_t below = ~same & ((1u << pos) - 1u);
+            const int start = below ? 32 - __clz(below) : 0;
+            out[k] = ly * DBT_W + (lane >> 3) * 32 + start;
+        }
+        *reinterpret_cast<int4 *>(&sl[ly * DBT_W + lx0]) = make_int4(out[0], out[1], out[2], out[3]);
+        if (sub == 0) { scls[ly][lane >> 3] = seg; sval[ly][lane >> 3] = vseg; }
+    }
+    __syncthreads();
+    // phase 2: unions inside the tile (pixels outside the tile or the map count as absent)
+#pragma unroll 1
+    for (int i = 0; i < DBT_H / 8; i++) {
+        const int ly = i * 8 + warp;
+        const uint32_t cw = scls[ly][lane >> 3], vw = sval[ly][lane >> 3];
+        if (((vw >> (4 * sub)) & 0xFu) == 0u) continue;
+        const uint32_t uw = ly > 0 ? scls[ly - 1][lane >> 3] : 0u;
+        // classes of pixels lx0-1 .. lx0+4 of this row and the row above (bit k+1 = pixel lx0+k); neighbours in the next word
+        const int sh = 4 * sub;
+        uint32_t c = ((cw >> sh) & 0xFu) << 1, u = ((uw >> sh) & 0xFu) << 1;
+        uint32_t v = ((vw >> sh) & 0xFu) << 1;
+        if (sub > 0) { c |= (cw >> (sh - 1)) & 1u; u |= (uw >> (sh - 1)) & 1u; v |= 1u; }
+        else if (lane >= 8) { c |= scls[ly][(lane >> 3) - 1] >> 31; u |= (ly > 0 ? scls[ly - 1][(lane >> 3) - 1] >> 31 : 0u); v |= 1u; }
+        if (sub < 7) { u |= ((uw >> (sh + 4)) & 1u) << 5; v |= ((vw >> (sh + 4)) & 1u) << 5; }
+        else if (lane < 24) { u |= (ly > 0 ? (scls[ly - 1][(lane >> 3) + 1] & 1u) : 0u) << 5; v |= (sval[ly][(lane >> 3) + 1] & 1u) << 5; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!((v >> (k + 1)) & 1u)) continue;
+            const int lx = lx0 + k, idx = ly * DBT_W + lx;
+            const uint32_t cc = (c >> (k + 1)) & 1u;
+            const bool has_left = (v >> k) & 1u;                       // pixel lx-1 is inside the tile
+            const bool left_same = has_left && ((c >> k) & 1u) == cc;
+            if ((lx & 31) == 0 && left_same) dbt_union(sl, idx, idx - 1);
+            if (ly > 0) {
+                const int up = idx - DBT_W;
+                if (((u >> (k + 1)) & 1u) == cc) {
+                    const bool upleft_same = has_left && ((u >> k) & 1u) == cc;
+                    if (!(left_same && upleft_same)) dbt_union(sl, idx, up);
+                } else if (cc == 1u) {
+                    if (has_left && ((u >> k) & 1u)) dbt_union(sl, idx, up - 1);
+                    if (((v >> (k + 2)) & 1u) && ((u >> (k + 2)) & 1u)) dbt_union(sl, idx, up + 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // phase 3: local roots as page indices
+#pragma unroll 1
+    for (int i = 0; i < DBT_H / 8; i++) {
+        const int ly = i * 8 + warp, y = y0t + ly, x = x0t + lx0;
+        if (y >= h || x >= w) continue;
+        int out[4];
+        int prev_lab = -1, prev_root = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int lab = sl[ly * DBT_W + lx0 + k];
+            if (lab != prev_lab) { prev_lab = lab; prev_root = dbt_find(sl, lab); }
+            out[k] = (y0t + (prev_root >> 7)) * w + x0t + (prev_root & (DBT_W - 1));
+        }
+        int *dst = L + (size_t)y * w + x;
+        if (x + 4 <= w) *reinterpret_cast<int4 *>(dst) = make_int4(out[0], out[1], out[2], out[3]);
+        else for (int k = 0; k < 4; k++) if (x + k < w) dst[k] = out[k];
+    }
+}
+
+// links across tile borders: the first row of every tile row (N, or NW / NE for foreground under background) and the two
+// pixel columns either side of every vertical tile border (left link, NW of the right pixel, NE of the left pixel)
+__global__ void __launch_bounds__(256) db_ccl_border_kernel(const uint8_t *__restrict__ mask, int *__restrict__ labels, int h, int w,
+                                                            int tiles_x, int tiles_y, long long n_rows_part, long long total) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const size_t hw = (size_t)h * w;
+    if (g < n_rows_part) {
+        const int x = (int)(g % w);
+        const long long r = g / w;
+        const int ty = (int)(r % (tiles_y - 1)) + 1, page = (int)(r / (tiles_y - 1));
+        const int y = ty * DBT_H;
+        const uint8_t *M = mask + (size_t)page * hw;
+        int *L = labels + (size_t)page * hw;
+        const int idx = y * w + x, up = idx - w;
+        const uint32_t cc = M[idx] & 1u;
+        if ((M[up] & 1u) == cc) {
+            const bool left_same = x > 0 && (M[idx - 1] & 1u) == cc, upleft_same = x > 0 && (M[up - 1] & 1u) == cc;
+            if (!(left_same && upleft_same)) ccl_union(L, idx, up);
+        } else if (cc == 1u) {
+            if (x > 0 && (M[up - 1] & 1u)) ccl_union(L, idx, up - 1);
+            if (x + 1 < w && (M[up + 1] & 1u)) ccl_union(L, idx, up + 1);
+        }
+    } else {
+        const long long q = g - n_rows_part;
+        const int y = (int)(q % h);
+        const long long r = q / h;
+        const int tx = (int)(r % (tiles_x - 1)) + 1, page = (int)(r / (tiles_x - 1));
+        const int x = tx * DBT_W;
+        const uint8_t *M = mask + (size_t)page * hw;
+        int *L = labels + (size_t)page * hw;
+        const int idx = y * w + x;
+        const uint32_t cc = M[idx] & 1u, cl = M[idx - 1] & 1u;
+        if (cl == cc) ccl_union(L, idx, idx - 1);
+        if (y > 0) {
+            const uint32_t cu = M[idx - w] & 1u, cul = M[idx - w - 1] & 1u;
+            if (cc == 1u && cu == 0u && cul == 1u) ccl_union(L, idx, idx - w - 1);      // NW of the right pixel
+            if (cl == 1u && cul == 0u && cu == 1u) ccl_union(L, idx - 1, idx - w);      // NE of the left pixel
+        }
+    }
+}
+
 // flatten, 4 pixels per thread (128-bit label load / store; neighbours of a run share the root that was just found)
 __global__ void __launch_bounds__(256) db_ccl_flatten4_kernel(uint8_t *__restrict__ mask, int *__restrict__ labels, int h, int w,
                                                               long long total_groups) {
@@ -794,6 +954,23 @@ static int db_label(const float *d_pred, int n, int h, int w, float thresh, uint
         LUMINA_KERNEL_CHECK("db_mask_kernel");
     }
     const long long nseg = (long long)n * h * ((w + 31) / 32);
+    if ((w & 3) == 0 && getenv("LUMINA_DB_TILE_CCL")) {   // opt-in until verified on the GPU
+        const int tiles_x = (w + DBT_W - 1) / DBT_W, tiles_y = (h + DBT_H - 1) / DBT_H;
+        const long long ctas = (long long)n * tiles_x * tiles_y;
+        LUMINA_REQUIRE(ctas < (1LL << 31), "batch too large for grid");
+        db_ccl_tile_kernel<<<(unsigned)ctas, 256, 0, st>>>(mask, labels, h, w, tiles_x, tiles_y);
+        LUMINA_KERNEL_CHECK("db_ccl_tile_kernel");
+        const long long rows_part = (long long)n * (tiles_y - 1) * w, cols_part = (long long)n * (tiles_x - 1) * h;
+        if (rows_part + cols_part > 0) {
+            db_ccl_border_kernel<<<(unsigned)((rows_part + cols_part + 255) / 256), 256, 0, st>>>(mask, labels, h, w, tiles_x, tiles_y,
+                                                                                              rows_part, rows_part + cols_part);
+            LUMINA_KERNEL_CHECK("db_ccl_border_kernel");
+        }
+        const long long fgroups = (long long)n * h * (w >> 2);
+        db_ccl_flatten4_kernel<<<(unsigned)((fgroups + 255) / 256), 256, 0, st>>>(mask, labels, h, w, fgroups);
+        LUMINA_KERNEL_CHECK("db_ccl_flatten4_kernel");
+        return LUMINA_OK;
+    }
     if ((w & 3) == 0) {
         const long long igroups = (long long)n * h * (((w + 31) >> 5) << 3);
         db_ccl_init4_kernel<<<(unsigned)((igroups + 255) / 256), 256, 0, st>>>(mask, labels, h, w, igroups);
