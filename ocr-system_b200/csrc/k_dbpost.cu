@@ -260,39 +260,36 @@ __global__ void __launch_bounds__(256) db_ccl_tile_kernel(const uint8_t *__restr
         if (sub == 0) { scls[ly][lane >> 3] = seg; sval[ly][lane >> 3] = vseg; }
     }
     __syncthreads();
-    // phase 2: unions inside the tile (pixels outside the tile or the map count as absent)
-#pragma unroll 1
-    for (int i = 0; i < DBT_H / 8; i++) {
-        const int ly = i * 8 + warp;
-        const uint32_t cw = scls[ly][lane >> 3], vw = sval[ly][lane >> 3];
-        if (((vw >> (4 * sub)) & 0xFu) == 0u) continue;
-        const uint32_t uw = ly > 0 ? scls[ly - 1][lane >> 3] : 0u;
-        // classes of pixels lx0-1 .. lx0+4 of this row and the row above (bit k+1 = pixel lx0+k); neighbours in the next word
-        const int sh = 4 * sub;
-        uint32_t c = ((cw >> sh) & 0xFu) << 1, u = ((uw >> sh) & 0xFu) << 1;
-        uint32_t v = ((vw >> sh) & 0xFu) << 1;
-        if (sub > 0) { c |= (cw >> (sh - 1)) & 1u; u |= (uw >> (sh - 1)) & 1u; v |= 1u; }
-        else if (lane >= 8) { c |= scls[ly][(lane >> 3) - 1] >> 31; u |= (ly > 0 ? scls[ly - 1][(lane >> 3) - 1] >> 31 : 0u); v |= 1u; }
-        if (sub < 7) { u |= ((uw >> (sh + 4)) & 1u) << 5; v |= ((vw >> (sh + 4)) & 1u) << 5; }
-        else if (lane < 24) { u |= (ly > 0 ? (scls[ly - 1][(lane >> 3) + 1] & 1u) : 0u) << 5; v |= (sval[ly][(lane >> 3) + 1] & 1u) << 5; }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (!((v >> (k + 1)) & 1u)) continue;
-            const int lx = lx0 + k, idx = ly * DBT_W + lx;
-            const uint32_t cc = (c >> (k + 1)) & 1u;
-            const bool has_left = (v >> k) & 1u;                       // pixel lx-1 is inside the tile
-            const bool left_same = has_left && ((c >> k) & 1u) == cc;
-            if ((lx & 31) == 0 && left_same) dbt_union(sl, idx, idx - 1);
+    // phase 2: unions inside the tile (pixels outside the tile or the map count as absent).  Bit-parallel: a thread owns half a
+    // 32-pixel class word of one tile row, derives the pixels that need a link (run heads under a same-class pixel,
+    // foreground under background with a foreground diagonal, segment starts with a same-class left pixel) as bit masks and
+    // walks only their set bits.
+    {
+        const int t = threadIdx.x, ly = t >> 3, wi = (t >> 1) & 3;
+        const uint32_t half = (t & 1) ? 0xffff0000u : 0x0000ffffu;
+        const uint32_t C = scls[ly][wi], V = sval[ly][wi];
+        if (V & half) {
+            const uint32_t cl = wi > 0 ? scls[ly][wi - 1] >> 31 : 0u;
+            const uint32_t HL = (V << 1) | (wi > 0 ? 1u : 0u);              // the left neighbour is inside the tile
+            const uint32_t left_same = HL & ~(C ^ ((C << 1) | cl)) & V;
+            uint32_t mL = left_same & 1u & half, mN = 0, mNW = 0, mNE = 0;
             if (ly > 0) {
-                const int up = idx - DBT_W;
-                if (((u >> (k + 1)) & 1u) == cc) {
-                    const bool upleft_same = has_left && ((u >> k) & 1u) == cc;
-                    if (!(left_same && upleft_same)) dbt_union(sl, idx, up);
-                } else if (cc == 1u) {
-                    if (has_left && ((u >> k) & 1u)) dbt_union(sl, idx, up - 1);
-                    if (((v >> (k + 2)) & 1u) && ((u >> (k + 2)) & 1u)) dbt_union(sl, idx, up + 1);
-                }
+                const uint32_t U = scls[ly - 1][wi];
+                const uint32_t ul = wi > 0 ? scls[ly - 1][wi - 1] >> 31 : 0u;
+                const uint32_t ur = wi < 3 ? scls[ly - 1][wi + 1] & 1u : 0u, vr = wi < 3 ? sval[ly][wi + 1] & 1u : 0u;
+                const uint32_t Ul = (U << 1) | ul, Ur = (U >> 1) | (ur << 31), HR = (V >> 1) | (vr << 31);
+                const uint32_t up_same = ~(C ^ U) & V;
+                const uint32_t upleft_same = HL & ~(C ^ Ul);
+                mN = up_same & ~(left_same & upleft_same) & half;
+                const uint32_t fg_no_up = C & ~U & V & half;
+                mNW = fg_no_up & HL & Ul;
+                mNE = fg_no_up & HR & Ur;
             }
+            const int base = ly * DBT_W + wi * 32;
+            if (mL) dbt_union(sl, base, base - 1);
+            for (uint32_t m = mN; m; m &= m - 1) { const int idx = base + __ffs(m) - 1; dbt_union(sl, idx, idx - DBT_W); }
+            for (uint32_t m = mNW; m; m &= m - 1) { const int idx = base + __ffs(m) - 1; dbt_union(sl, idx, idx - DBT_W - 1); }
+            for (uint32_t m = mNE; m; m &= m - 1) { const int idx = base + __ffs(m) - 1; dbt_union(sl, idx, idx - DBT_W + 1); }
         }
     }
     __syncthreads();
@@ -954,7 +951,7 @@ static int db_label(const float *d_pred, int n, int h, int w, float thresh, uint
         LUMINA_KERNEL_CHECK("db_mask_kernel");
     }
     const long long nseg = (long long)n * h * ((w + 31) / 32);
-    if ((w & 3) == 0 && getenv("LUMINA_DB_TILE_CCL")) {   // opt-in until verified on the GPU
+    if ((w & 3) == 0 && !getenv("LUMINA_DB_GLOBAL_CCL")) {   // the global union-find stays as the A/B and fallback path
         const int tiles_x = (w + DBT_W - 1) / DBT_W, tiles_y = (h + DBT_H - 1) / DBT_H;
         const long long ctas = (long long)n * tiles_x * tiles_y;
         LUMINA_REQUIRE(ctas < (1LL << 31), "batch too large for grid");

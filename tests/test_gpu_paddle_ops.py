@@ -48,6 +48,32 @@ def test_db_mask_and_labels(cuda, seed, h, w):
     assert np.array_equal(labels, canon)
 
 
+@pytest.mark.parametrize("global_ccl", [False, True])
+@pytest.mark.parametrize("h,w,p", [(33, 128, 0.5), (100, 132, 0.45), (32, 260, 0.6), (700, 1000, 0.5), (65, 388, 0.3),
+                                   (31, 124, 0.55), (257, 512, 0.7)])
+def test_db_labels_tile_local_and_global_union_find_agree_with_cv2(cuda, h, w, p, global_ccl, monkeypatch):
+    """Widths that are multiples of 4 take the tile-local labelling (32 x 128 tiles in shared memory, then the links across
+    tile borders); LUMINA_DB_GLOBAL_CCL keeps the global union-find.  Salt-and-pepper maps make every tile border a link
+    site; sizes cover partial tiles at the right / bottom edge and maps smaller than one tile."""
+    import cv2
+
+    from ocr_system_b200 import ops
+
+    if global_ccl:
+        monkeypatch.setenv("LUMINA_DB_GLOBAL_CCL", "1")
+    rng = np.random.default_rng(h * 1000 + w)
+    pred = (rng.random((2, h, w)) < p).astype(np.float32)
+    mask, labels = ops.db_mask_ccl(_t(pred, cuda), 0.3)
+    mask, labels = mask.cpu().numpy(), labels.cpu().numpy()
+    for i in range(2):
+        ref_mask = (pred[i] > 0.3).astype(np.uint8)
+        assert np.array_equal(mask[i], ref_mask)
+        n, lab = cv2.connectedComponents(ref_mask, connectivity=8)
+        first = np.full(n, h * w, np.int64)
+        np.minimum.at(first, lab.ravel(), np.arange(h * w))
+        assert np.array_equal(labels[i], np.where(lab > 0, first[lab] + 1, 0)), (h, w, i)
+
+
 @pytest.mark.parametrize("seed,h,w,dst,dil", [(0, 960, 960, (960, 960), False), (3, 960, 960, (1280, 1707), False),
                                               (1, 640, 800, (640, 800), False), (2, 960, 960, (960, 960), True),
                                               (5, 640, 800, (1280, 1600), True)])
