@@ -147,48 +147,85 @@ __global__ void __launch_bounds__(256) stencil3_kernel(const uint8_t *__restrict
 // adaptive threshold: fp32 separable Gaussian (RowFilter left-to-right, then
 // SymmColumnFilter centre + symmetric pairs), rint, LUT compare.  One CTA per
 // 64x32 tile; gray tile (+5 halo) and the row-filtered floats live in shared memory.
+// Register blocking: a row-filter item is 4 consecutive outputs of one row (14 tile bytes = 4 aligned word
+// loads, each byte converted once instead of once per tap it meets; one 128-bit store), a column-filter item is
+// 4 consecutive rows of one column (14 floats for 4 outputs instead of 11 each).  The tile is filled row by
+// row (warp = row, lane = byte column), so no index division anywhere.  Every product and sum is a separate
+// fp32 operation in OpenCV's order -- the blocking only shares operands.
 // ---------------------------------------------------------------------------
 constexpr int AT_TW = 64, AT_TH = 32, AT_R = 5;
+constexpr int AT_ROWS = AT_TH + 2 * AT_R;          // 42 staged rows
+constexpr int AT_COLS = AT_TW + 2 * AT_R;          // 74 staged byte columns
+constexpr int AT_TP = 80;                          // tile pitch in bytes (word-aligned rows, >= 76: the last item reads 16 bytes from column 60)
+constexpr int AT_FP = AT_TW + 4;                   // float pitch (16-byte aligned rows)
 struct Gauss11 { float k[11]; };
 
 template <int C>
 __global__ void __launch_bounds__(256) adaptive_gauss11_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                                int h, int w, int cval, const Gauss11 g) {
-    __shared__ uint8_t tile[AT_TH + 2 * AT_R][AT_TW + 2 * AT_R + 2];
-    __shared__ float rowf[AT_TH + 2 * AT_R][AT_TW + 1];
+    __shared__ __align__(16) uint8_t tile[AT_ROWS][AT_TP];
+    __shared__ __align__(16) float rowf[AT_ROWS][AT_FP];
     const int page = blockIdx.z;
     const int x0 = blockIdx.x * AT_TW, y0 = blockIdx.y * AT_TH;
     const uint8_t *s = src + (size_t)page * h * w * C;
-    for (int i = threadIdx.x; i < (AT_TH + 2 * AT_R) * (AT_TW + 2 * AT_R); i += 256) {
-        const int ty = i / (AT_TW + 2 * AT_R), tx = i % (AT_TW + 2 * AT_R);
-        const int yy = min(max(y0 + ty - AT_R, 0), h - 1), xx = min(max(x0 + tx - AT_R, 0), w - 1);
-        const uint8_t *px = s + ((size_t)yy * w + xx) * C;
-        uint32_t v;
-        if (C == 3) v = (19595u * __ldg(px) + 38470u * __ldg(px + 1) + 7471u * __ldg(px + 2) + 0x8000u) >> 16;
-        else v = __ldg(px);
-        tile[ty][tx] = (uint8_t)v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int ty = warp; ty < AT_ROWS; ty += 8) {
+        const int yy = min(max(y0 + ty - AT_R, 0), h - 1);
+        const uint8_t *row = s + (size_t)yy * w * C;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int tx = lane + 32 * j;
+            if (tx < AT_COLS) {
+                const int xx = min(max(x0 + tx - AT_R, 0), w - 1);
+                const uint8_t *px = row + (size_t)xx * C;
+                uint32_t v;
+                if (C == 3) v = (19595u * __ldg(px) + 38470u * __ldg(px + 1) + 7471u * __ldg(px + 2) + 0x8000u) >> 16;
+                else v = __ldg(px);
+                tile[ty][tx] = (uint8_t)v;
+            }
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (AT_TH + 2 * AT_R) * AT_TW; i += 256) {
-        const int ty = i / AT_TW, tx = i % AT_TW;
-        float acc = __fmul_rn((float)tile[ty][tx], g.k[0]);
+    // row filter: item = (row, 4 output columns); 42 x 16 items
+    for (int i = threadIdx.x; i < AT_ROWS * (AT_TW / 4); i += 256) {
+        const int ty = i >> 4, q = i & 15;
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(&tile[ty][q * 4]);   // word-aligned (pitch 80), not 16-byte
+        const uint32_t wd[4] = {tw[0], tw[1], tw[2], tw[3]};
+        float xf[14];
 #pragma unroll
-        for (int k = 1; k < 11; k++) acc = __fadd_rn(acc, __fmul_rn((float)tile[ty][tx + k], g.k[k]));
-        rowf[ty][tx] = acc;
+        for (int b = 0; b < 14; b++) xf[b] = (float)((wd[b >> 2] >> (8 * (b & 3))) & 255u);
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            float acc = __fmul_rn(xf[e], g.k[0]);
+#pragma unroll
+            for (int k = 1; k < 11; k++) acc = __fadd_rn(acc, __fmul_rn(xf[e + k], g.k[k]));
+            o[e] = acc;
+        }
+        *reinterpret_cast<float4 *>(&rowf[ty][q * 4]) = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < AT_TH * AT_TW; i += 256) {
-        const int ty = i / AT_TW, tx = i % AT_TW;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x >= w || y >= h) continue;
-        float acc = __fmul_rn(g.k[5], rowf[ty + AT_R][tx]);
+    // column filter + compare: item = (column, 4 output rows); 64 x 8 items
+    for (int i = threadIdx.x; i < AT_TW * (AT_TH / 4); i += 256) {
+        const int tx = i & 63, ty0 = (i >> 6) * 4;
+        const int x = x0 + tx;
+        if (x >= w) continue;
+        float rf[14];
 #pragma unroll
-        for (int k = 1; k <= 5; k++)
-            acc = __fadd_rn(acc, __fmul_rn(g.k[5 + k], __fadd_rn(rowf[ty + AT_R + k][tx], rowf[ty + AT_R - k][tx])));
-        int m = __float2int_rn(acc);
-        m = min(max(m, 0), 255);
-        const int sv = tile[ty + AT_R][tx + AT_R];
-        dst[((size_t)page * h + y) * w + x] = (sv - m > -cval) ? 255 : 0;
+        for (int r = 0; r < 14; r++) rf[r] = rowf[ty0 + r][tx];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int y = y0 + ty0 + e;
+            if (y >= h) break;
+            float acc = __fmul_rn(g.k[5], rf[e + AT_R]);
+#pragma unroll
+            for (int k = 1; k <= 5; k++)
+                acc = __fadd_rn(acc, __fmul_rn(g.k[5 + k], __fadd_rn(rf[e + AT_R + k], rf[e + AT_R - k])));
+            int m = __float2int_rn(acc);
+            m = min(max(m, 0), 255);
+            const int sv = tile[ty0 + e + AT_R][tx + AT_R];
+            dst[((size_t)page * h + y) * w + x] = (sv - m > -cval) ? 255 : 0;
+        }
     }
 }
 

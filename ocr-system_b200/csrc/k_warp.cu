@@ -126,16 +126,16 @@ __global__ void __launch_bounds__(256) warp_affine_cubic_kernel(const uint8_t *_
             const uint32_t *wp32 = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
             const uint32_t a0 = __ldg(wp32), a1 = __ldg(wp32 + 1), a2 = __ldg(wp32 + 2), a3 = __ldg(wp32 + 3);
             const int sh = (int)(addr & 3) * 8;
-            const uint32_t v[3] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh)};
+            const uint32_t v0 = __funnelshift_r(a0, a1, sh), v1 = __funnelshift_r(a1, a2, sh), v2 = __funnelshift_r(a2, a3, sh);
+            // the row's 12 bytes R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3 -> one word of four taps per channel (2 PRMT each),
+            // then the four int16 weights of the row (two packed words) against it: dp2a.lo = taps 0,1, dp2a.hi = taps 2,3
+            const uint32_t cw[3] = {__byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210),
+                                    __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210),
+                                    __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410)};
 #pragma unroll
-            for (int k2 = 0; k2 < 4; k2++) {
-                const int q = k1 * 4 + k2;
-                const int wt = (int)(short)((wp[q >> 1] >> (16 * (q & 1))) & 0xffffu);
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    const int bi = k2 * 3 + ch;
-                    sum[ch] += (int)((v[bi >> 2] >> (8 * (bi & 3))) & 255u) * wt;
-                }
+            for (int ch = 0; ch < 3; ch++) {
+                asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(sum[ch]) : "r"(wp[k1 * 2]), "r"(cw[ch]));
+                asm("dp2a.hi.s32.u32 %0, %1, %2, %0;" : "+r"(sum[ch]) : "r"(wp[k1 * 2 + 1]), "r"(cw[ch]));
             }
         }
 #pragma unroll
