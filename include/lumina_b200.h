@@ -133,13 +133,22 @@ int lumina_ppht_prepare(const uint8_t *d_edges, int n, int h, int w, double rho,
 int lumina_ppht_lines(const uint8_t *d_edges, int n, int h, int w, double rho, double theta, int threshold,
                       int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
                       void *d_workspace, size_t workspace_bytes, void *stream);
-/* (iv)+(v) host: per-line degrees(arctan2) folded to +-45, np.median.  Host
- * code on purpose (glibc atan2 == the reference's libm). nlines==0 -> 0.0 */
+/* (iv)+(v) host: per-line degrees(arctan2) folded to +-45, np.median, with glibc's atan2.  nlines==0 -> 0.0.
+ * numpy's arctan2 is glibc's only where numpy does not dispatch to its bundled SIMD math (AVX-512 builds: the last
+ * place differs for ~0.3 % of (dy, dx) pairs); a host that has numpy computes the per-line angles with it and calls
+ * lumina_deskew_decide_angles_host (what the Python layer of this repo does). */
 double lumina_median_angle_host(const int32_t *h_lines, int nlines);
 /* (iv)-(vi) for a batch in one call: per page the reference's gating (:409-439) and, when the page
  * is to be rotated, getRotationMatrix2D((w//2, h//2), angle, 1).  h_lines [n][lines_stride][4]. */
 void lumina_deskew_decide_host(const int32_t *h_lines, const int32_t *h_nlines, int n, int lines_stride,
                                int h, int w, double *h_angles, double *h_m6, uint8_t *h_apply);
+/* (iv)-(vi) from per-line angles the caller computed with the reference's own expression
+ * np.degrees(np.arctan2(y2 - y1, x2 - x1)) and folded to +-45 (:421-426): median (:428), gating, rotation matrix.
+ * h_line_angles [n][angle_stride] f64, the first min(h_nlines[i], angle_stride) of a page are used. */
+void lumina_deskew_decide_angles_host(const double *h_line_angles, const int32_t *h_nlines, int n, int angle_stride,
+                                      int h, int w, double *h_angles, double *h_m6, uint8_t *h_apply);
+/* cv::invertAffineTransform's arithmetic as cv::warpAffine applies it to a forward 2x3 matrix (double) */
+void lumina_invert_affine_host(const double *h_m6, double *h_minv6);
 /* cv2.getRotationMatrix2D (double, 2x3 row-major) */
 void lumina_rotation_matrix_host(double cx, double cy, double angle_deg, double scale, double *h_m6);
 /* (vii) cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE), same size.

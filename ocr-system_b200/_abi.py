@@ -54,8 +54,10 @@ PROTOTYPES = {
     "lumina_ppht_lines": (_I, [_P, _I, _I, _I, _D, _D, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "lumina_median_angle_host": (_D, [_P, _I]),
     "lumina_deskew_decide_host": (None, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "lumina_deskew_decide_angles_host": (None, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "lumina_rotation_matrix_host": (None, [_D, _D, _D, _D, _P]),
     "lumina_warp_affine_cubic_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "lumina_invert_affine_host": (None, [_P, _P]),
     "lumina_det_target_size": (None, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "lumina_skew_workspace_bytes_for": (_Z, [_I, _I, _I]),
     "lumina_skew_estimate_fast": (_I, [_P, _I, _I, _I, _P, _P, _Z, _P]),

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(const uint8_t *__re
 
 using namespace lumina;
 
-LUMINA_API int lumina_abi_version(void) { return 3; }  // 3: round 2 (JPEG decode, db_postprocess_ex, Otsu / Sauvola, skew estimate)
+LUMINA_API int lumina_abi_version(void) { return 4; }  // 3: round 2 (JPEG decode, db_postprocess_ex, Otsu / Sauvola, skew estimate); 4: stream-ordered deskew decision
 LUMINA_API const char *lumina_last_error_string(void) { return g_err; }
 LUMINA_API uint64_t lumina_launch_count(void) { return g_launches.load(); }
 

@@ -23,6 +23,11 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -797,11 +802,20 @@ LUMINA_API int lumina_ppht_lines(const uint8_t *d_edges, int n, int h, int w, do
                     d_workspace, workspace_bytes, 2, stream);
 }
 
-// (iv)+(v) image_preprocessing.py:414-428 -- host on purpose (libm atan2, as numpy)
-static int cmp_double(const void *a, const void *b) {
-    const double x = *(const double *)a, y = *(const double *)b;
-    return x < y ? -1 : (x > y ? 1 : 0);
+// (iv)+(v) image_preprocessing.py:414-428 on the host.  np.median of already folded per-line angles: the middle
+// element, or the mean of the two middle elements, of the sorted values -- selection yields the same values as a sort.
+static double median_of(double *a, int n) {
+    std::nth_element(a, a + n / 2, a + n);
+    const double hi = a[n / 2];
+    if (n & 1) return hi;
+    const double lo = *std::max_element(a, a + n / 2);
+    return (lo + hi) / 2.0;
 }
+// glibc atan2 for the per-line angle.  NOTE: numpy's arctan2 is glibc's only where numpy does not dispatch to its
+// bundled SIMD math (AVX-512 builds use SVML, whose result differs from glibc's in the last place for ~0.3 % of
+// integer (dy, dx) pairs -- measured, DESIGN "deskew angle").  The Python host layer therefore computes the per-line
+// angles with numpy itself (the reference's own expression) and calls lumina_deskew_decide_angles_host; this entry
+// is for hosts without numpy.
 LUMINA_API double lumina_median_angle_host(const int32_t *h_lines, int nlines) {
     if (!h_lines || nlines <= 0) return 0.0;
     std::vector<double> ang((size_t)nlines);
@@ -813,43 +827,122 @@ LUMINA_API double lumina_median_angle_host(const int32_t *h_lines, int nlines) {
         else if (a > 45) a -= 90;
         ang[i] = a;
     }
-    qsort(ang.data(), ang.size(), sizeof(double), cmp_double);
-    return (nlines & 1) ? ang[nlines / 2] : (ang[nlines / 2 - 1] + ang[nlines / 2]) / 2.0;
+    return median_of(ang.data(), nlines);
 }
+
+// A small persistent pool for the per-page decisions (no thread creation on the path the GPU waits on).  run() is
+// serialised; the workers live for the life of the process.
+namespace {
+class DecidePool {
+  public:
+    DecidePool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int nt = hw > 1 ? (int)hw - 1 : 1;
+        if (nt > 7) nt = 7;                         // + the calling thread
+        for (int t = 0; t < nt; t++) std::thread([this] { worker(); }).detach();
+    }
+    void run(int n, const std::function<void(int)> &fn) {
+        std::lock_guard<std::mutex> serial(run_mu_);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; next_.store(0); done_ = 0; gen_++;
+        }
+        cv_.notify_all();
+        int mine = 0;
+        for (int i; (i = next_.fetch_add(1)) < n;) { fn(i); mine++; }
+        std::unique_lock<std::mutex> lk(mu_);
+        done_ += mine;
+        cv_done_.wait(lk, [&] { return done_ >= n_ && active_ == 0; });   // no worker still holds this call's fn
+        fn_ = nullptr;
+    }
+
+  private:
+    void worker() {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                fn = fn_; n = n_;
+                if (fn) active_++;
+            }
+            if (!fn) continue;
+            int mine = 0;
+            for (int i; (i = next_.fetch_add(1)) < n;) { (*fn)(i); mine++; }
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                done_ += mine;
+                active_--;
+                cv_done_.notify_all();
+            }
+        }
+    }
+    std::mutex run_mu_, mu_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, done_ = 0, active_ = 0;
+    unsigned long long gen_ = 0;
+};
+DecidePool &decide_pool() {
+    static DecidePool *p = new DecidePool();   // never destroyed: detached workers may outlive static destructors
+    return *p;
+}
+}  // namespace
 
 // The per-page decision of deskew (image_preprocessing.py:409-444) for a whole batch in one host call:
 // no lines -> (0.0, keep); |median| < 0.5 -> (median, keep); |median| > 45 -> (0.0, keep); else rotate by
 // getRotationMatrix2D((w//2, h//2), median, 1.0).
+static void deskew_gate(double a, int has_lines, int h, int w, double *angle, double *m6, uint8_t *apply) {
+    *angle = 0.0;
+    *apply = 0;
+    for (int k = 0; k < 6; k++) m6[k] = 0.0;
+    if (!has_lines) return;
+    if (fabs(a) < 0.5) { *angle = a; return; }
+    if (fabs(a) > 45) return;
+    *angle = a;
+    *apply = 1;
+    lumina_rotation_matrix_host((double)(w / 2), (double)(h / 2), a, 1.0, m6);
+}
+
 LUMINA_API void lumina_deskew_decide_host(const int32_t *h_lines, const int32_t *h_nlines, int n, int lines_stride,
                                           int h, int w, double *h_angles, double *h_m6, uint8_t *h_apply) {
     auto one = [=](int i) {
-        h_angles[i] = 0.0;
-        h_apply[i] = 0;
-        for (int k = 0; k < 6; k++) h_m6[(size_t)i * 6 + k] = 0.0;
         const int nl = h_nlines[i] < lines_stride ? h_nlines[i] : lines_stride;
-        if (nl <= 0) return;
-        const double a = lumina_median_angle_host(h_lines + (size_t)i * lines_stride * 4, nl);
-        if (fabs(a) < 0.5) { h_angles[i] = a; return; }
-        if (fabs(a) > 45) return;
-        h_angles[i] = a;
-        h_apply[i] = 1;
-        lumina_rotation_matrix_host((double)(w / 2), (double)(h / 2), a, 1.0, h_m6 + (size_t)i * 6);
+        const double a = nl > 0 ? lumina_median_angle_host(h_lines + (size_t)i * lines_stride * 4, nl) : 0.0;
+        deskew_gate(a, nl > 0, h, w, h_angles + i, h_m6 + (size_t)i * 6, h_apply + i);
     };
-    // ~25 us per page (libm atan2 per line + sort); the GPU waits for this, so a batch is spread over a few
+    // ~20 us per page (libm atan2 per line + selection); the GPU waits for this, so a batch is spread over a few
     // host threads (pages are independent; same libm, same result)
-    unsigned hw = std::thread::hardware_concurrency();
-    int nt = n / 8;
-    if (nt > 8) nt = 8;
-    if (hw > 0 && nt > (int)hw) nt = (int)hw;
-    if (nt <= 1) {
+    if (n < 16) {
         for (int i = 0; i < n; i++) one(i);
         return;
     }
-    std::vector<std::thread> pool;
-    pool.reserve(nt);
-    for (int t = 0; t < nt; t++)
-        pool.emplace_back([=]() {
-            for (int i = t; i < n; i += nt) one(i);
-        });
-    for (auto &th : pool) th.join();
+    decide_pool().run(n, one);
+}
+
+// The same decision from per-line angles the caller computed (degrees, already folded to +-45): the Python host layer
+// evaluates np.degrees(np.arctan2(dy, dx)) with numpy -- the reference's own expression, :421 -- so that the angle is
+// the reference's on every host, whatever math library its numpy dispatches to.  h_line_angles [n][angle_stride] is
+// not modified.
+LUMINA_API void lumina_deskew_decide_angles_host(const double *h_line_angles, const int32_t *h_nlines, int n, int angle_stride,
+                                                 int h, int w, double *h_angles, double *h_m6, uint8_t *h_apply) {
+    auto one = [=](int i) {
+        const int nl = h_nlines[i] < angle_stride ? h_nlines[i] : angle_stride;
+        double a = 0.0;
+        if (nl > 0) {
+            thread_local std::vector<double> tmp;
+            tmp.assign(h_line_angles + (size_t)i * angle_stride, h_line_angles + (size_t)i * angle_stride + nl);
+            a = median_of(tmp.data(), nl);
+        }
+        deskew_gate(a, nl > 0, h, w, h_angles + i, h_m6 + (size_t)i * 6, h_apply + i);
+    };
+    if (n < 16) {
+        for (int i = 0; i < n; i++) one(i);
+        return;
+    }
+    decide_pool().run(n, one);
 }

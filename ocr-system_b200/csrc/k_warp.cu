@@ -172,6 +172,17 @@ LUMINA_API void lumina_rotation_matrix_host(double cx, double cy, double angle_d
     m[3] = -beta; m[4] = alpha; m[5] = beta * cx + (1 - alpha) * cy;
 }
 
+// cv::warpAffine: invert the forward matrix in double (imgwarp.cpp, invertAffineTransform's arithmetic)
+LUMINA_API void lumina_invert_affine_host(const double *F, double *M) {
+    double D = F[0] * F[4] - F[1] * F[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = F[4] * D, A22 = F[0] * D;
+    M[0] = A11; M[1] = F[1] * (-D); M[3] = F[3] * (-D); M[4] = A22;
+    const double b1 = -M[0] * F[2] - M[1] * F[5];
+    const double b2 = -M[3] * F[2] - M[4] * F[5];
+    M[2] = b1; M[5] = b2;
+}
+
 LUMINA_API int lumina_warp_affine_cubic_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c,
                                            const double *h_m6, const uint8_t *h_apply, void *stream) {
     LUMINA_REQUIRE(d_src && d_dst && h_m6, "null pointer");
@@ -187,16 +198,7 @@ LUMINA_API int lumina_warp_affine_cubic_u8(const uint8_t *d_src, uint8_t *d_dst,
         WarpMats mats;
         memset(&mats, 0, sizeof(mats));
         for (int i = 0; i < np; i++) {
-            const double *F = h_m6 + (size_t)(p0 + i) * 6;
-            // cv::warpAffine: invert the forward matrix in double
-            double D = F[0] * F[4] - F[1] * F[3];
-            D = D != 0 ? 1. / D : 0;
-            const double A11 = F[4] * D, A22 = F[0] * D;
-            double *M = mats.m[i];
-            M[0] = A11; M[1] = F[1] * (-D); M[3] = F[3] * (-D); M[4] = A22;
-            const double b1 = -M[0] * F[2] - M[1] * F[5];
-            const double b2 = -M[3] * F[2] - M[4] * F[5];
-            M[2] = b1; M[5] = b2;
+            lumina_invert_affine_host(h_m6 + (size_t)(p0 + i) * 6, mats.m[i]);
             mats.apply[i] = h_apply ? h_apply[p0 + i] : 1;
         }
         dim3 grid(div_up(w, 32), div_up(h, 8), np);

@@ -349,10 +349,26 @@ def rgbx_to_rgb(pages_rgbx: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def line_angles(lines_host: np.ndarray) -> np.ndarray:
+    """image_preprocessing.py:421-426 for an array of segments [...,4]: ``np.degrees(np.arctan2(y2 - y1, x2 - x1))``
+    folded to +-45 -- evaluated BY NUMPY, on int32 operands like the reference's scalars.  numpy's arctan2 is not
+    glibc's on AVX-512 builds (bundled SIMD math; the last place differs for ~0.3 % of segments), and numpy's
+    vectorised result equals its scalar one, so this is the reference's value on whatever host it runs."""
+    ln = np.asarray(lines_host, dtype=np.int32)
+    a = np.arctan2(ln[..., 3] - ln[..., 1], ln[..., 2] - ln[..., 0])
+    np.degrees(a, out=a)
+    lo, hi = a < -45, a > 45            # the reference's if / elif on the unfolded value; the two sets are disjoint
+    np.add(a, 90, out=a, where=lo)
+    np.subtract(a, 90, out=a, where=hi)
+    return a
+
+
 def median_angle(lines_host: np.ndarray) -> float:
-    """image_preprocessing.py:414-428 on the host (libm atan2, like numpy)."""
-    a = np.ascontiguousarray(lines_host, dtype=np.int32)
-    return float(_L().lumina_median_angle_host(a.ctypes.data_as(C.c_void_p), int(a.shape[0])))
+    """image_preprocessing.py:414-428 on the host: per-line angles by numpy (``line_angles``), ``np.median``'s value."""
+    ln = np.ascontiguousarray(lines_host, dtype=np.int32).reshape(-1, 4)
+    if ln.shape[0] == 0:
+        return 0.0
+    return float(deskew_decide(ln[None], np.array([ln.shape[0]], np.int32), 0, 0, gate=False)[0][0])
 
 
 def rotation_matrix(cx: float, cy: float, angle: float, scale: float = 1.0) -> np.ndarray:
@@ -361,9 +377,32 @@ def rotation_matrix(cx: float, cy: float, angle: float, scale: float = 1.0) -> n
     return m.reshape(2, 3)
 
 
-def deskew_decide(lines_host: np.ndarray, nlines_host: np.ndarray, h: int, w: int):
+def deskew_decide(lines_host: np.ndarray, nlines_host: np.ndarray, h: int, w: int, gate: bool = True):
     """Reference gating (image_preprocessing.py:409-444) for a batch in one host call:
-    (angles[N] f64, forward matrices[N,6] f64, apply[N] u8)."""
+    (angles[N] f64, forward matrices[N,6] f64, apply[N] u8).  The per-line angles come from numpy (``line_angles``),
+    median / gates / getRotationMatrix2D from the library.  ``gate=False`` returns the raw medians."""
+    ln = np.asarray(lines_host, dtype=np.int32)
+    nl = np.ascontiguousarray(nlines_host, dtype=np.int32)
+    n = ln.shape[0]
+    keep = max(1, min(int(nl.max(initial=0)), ln.shape[1]))
+    la = np.ascontiguousarray(line_angles(ln[:, :keep]))
+    angles = np.zeros(n, np.float64)
+    mats = np.zeros((n, 6), np.float64)
+    apply = np.zeros(n, np.uint8)
+    if not gate:
+        for i in range(n):
+            k = min(int(nl[i]), keep)
+            angles[i] = float(np.median(la[i, :k])) if k > 0 else 0.0
+        return angles, mats, apply
+    _L().lumina_deskew_decide_angles_host(la.ctypes.data_as(C.c_void_p), nl.ctypes.data_as(C.c_void_p), n, keep, int(h), int(w),
+                                          angles.ctypes.data_as(C.c_void_p), mats.ctypes.data_as(C.c_void_p),
+                                          apply.ctypes.data_as(C.c_void_p))
+    return angles, mats, apply
+
+
+def deskew_decide_libm(lines_host: np.ndarray, nlines_host: np.ndarray, h: int, w: int):
+    """``lumina_deskew_decide_host``: the same decision with glibc's atan2 for the per-line angles (what a host
+    without numpy gets)."""
     ln = np.ascontiguousarray(lines_host, dtype=np.int32)
     nl = np.ascontiguousarray(nlines_host, dtype=np.int32)
     n, stride = ln.shape[0], ln.shape[1]

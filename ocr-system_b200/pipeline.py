@@ -152,18 +152,23 @@ class PagePipeline:
         return x, lines, nlines
 
     def _back(self, x, lines, nlines, t: "_StageTimer") -> PageBatchResult:
-        """Host median / gating (the chain's one synchronisation) and everything after it."""
+        """The reference's median / gating (the chain's one host synchronisation: the per-line angles are numpy's, like
+        the reference's) and everything after it."""
         angles = np.zeros(x.shape[0], np.float64)
         if self.deskew and self.deskew_mode == "fast":
             x, angles = t.run("angle+warp", lambda: self._rotate_fast(x, lines))
         elif self.deskew:
             x, angles = t.run("angle+warp", lambda: self._rotate(x, lines, nlines))
+        tail = self._tail(x, t)
+        return PageBatchResult(tail[0], angles, *tail[1:], t)
+
+    def _tail(self, x, t: "_StageTimer"):
         if self.enhance:
             x = t.run("contrast+sharpness", lambda: ops.contrast_sharpness(x, 1.2, 1.1))
         gray = t.run("gray_pil", lambda: ops.gray_pil(x))
         binary = t.run("adaptive_binarize", lambda: ops.adaptive_binarize(gray, 2))
         det, shape_list = t.run("det_resize_normalize", lambda: ops.det_resize_normalize(x, self.det_limit))
-        return PageBatchResult(x, angles, gray, binary, det, shape_list, t)
+        return x, gray, binary, det, shape_list
 
     def run_device_stream(self, batches, profile: bool = False):
         """``run_device`` over a sequence of resident batches, software-pipelined on two CUDA streams: the front
@@ -205,8 +210,7 @@ class PagePipeline:
 
         def finish(job):
             lo, front, t = job
-            lo.synchronize()                      # the line lists of this batch are complete
-            hi.wait_stream(lo)
+            hi.wait_stream(lo)                    # the line lists of this batch; the host waits for them inside _back
             with torch.cuda.stream(hi):
                 res = self._back(*front, t)
             main.wait_stream(hi)
@@ -242,16 +246,17 @@ class PagePipeline:
         """Host median / gating (image_preprocessing.py:414-439) + one warp launch.  The only
         host synchronisation of the chain: the line lists (a few KB per page) come back."""
         n, h, w = x.shape[0], x.shape[1], x.shape[2]
-        # one pinned staging buffer, one synchronisation: counts and line lists come back together
+        # pinned staging; the counts come back first (256 bytes), then only the line slots in use (a text page has a
+        # few hundred segments of the 4096 slots: ~0.4 MB per 64 pages instead of 4 MB)
         key = (n, lines.shape[1], x.device)
-        st = getattr(self._tls, "rotate_stage", None)   # pinned staging for the line lists: per thread, shape-keyed
+        st = getattr(self._tls, "rotate_stage", None)   # per thread, shape-keyed
         if st is None or st[0] != key:
             st = self._tls.rotate_stage = (key, torch.empty(n, dtype=torch.int32, pin_memory=True),
                                            torch.empty((n, lines.shape[1], 4), dtype=torch.int32, pin_memory=True))
         _, nl_pin, ln_pin = st
+        cur = torch.cuda.current_stream(x.device)
         nl_pin.copy_(nlines, non_blocking=True)
-        ln_pin.copy_(lines, non_blocking=True)
-        torch.cuda.current_stream(x.device).synchronize()
+        cur.synchronize()
         nl = nl_pin.numpy()
         keep = int(nl.max(initial=0))
         if keep > lines.shape[1]:  # truncated list: redo the Hough stage with room for every line
@@ -259,8 +264,12 @@ class PagePipeline:
             lines, nlines = ops.hough_lines_p(edges, max_lines=keep)
             nl = nlines.cpu().numpy()
             lh = lines.cpu().numpy()
+        elif keep == 0:
+            lh = ln_pin.numpy()[:, :1]
         else:
-            lh = ln_pin.numpy()
+            ln_pin[:, :keep].copy_(lines[:, :keep], non_blocking=True)
+            cur.synchronize()
+            lh = ln_pin.numpy()[:, :keep]
         angles, mats, apply = ops.deskew_decide(lh, nl, h, w)
         if apply.any():
             x = ops.warp_affine_cubic(x, mats, apply)

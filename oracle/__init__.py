@@ -188,6 +188,26 @@ def ppht(edges, rho=1.0, theta=np.pi / 180, threshold=100, min_len=100, max_gap=
 
 
 def median_angle(lines) -> float:
+    """image_preprocessing.py:417-428, statement by statement, WITH NUMPY: np.arctan2 is not glibc's atan2 on AVX-512
+    numpy builds (bundled SIMD math; ~0.3 % of segments differ in the last place), so the C restatement
+    (orc_median_angle, glibc) is only the reference's value where numpy dispatches to libm.  Pinned by the deskew
+    goldens (tests/test_oracle_golden.py)."""
+    lines = np.ascontiguousarray(lines, np.int32).reshape(-1, 4)
+    if len(lines) == 0:
+        return 0.0
+    angles = []
+    for x1, y1, x2, y2 in lines:
+        angle = np.degrees(np.arctan2(y2 - y1, x2 - x1))
+        if angle < -45:
+            angle = angle + 90
+        elif angle > 45:
+            angle = angle - 90
+        angles.append(angle)
+    return float(np.median(angles))
+
+
+def median_angle_libm(lines) -> float:
+    """The C restatement with glibc's atan2 (see median_angle)."""
     lines = np.ascontiguousarray(lines, np.int32)
     return float(lib().orc_median_angle(_p(lines), len(lines)))
 

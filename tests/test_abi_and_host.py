@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(abi):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/lumina_b200.h but not exported"
     assert declared == set(abi.PROTOTYPES), declared ^ set(abi.PROTOTYPES)
-    assert abi.lib().lumina_abi_version() == 3
+    assert abi.lib().lumina_abi_version() == 4
 
 
 def test_target_size_matches_reference_rule(abi, oracle):

@@ -291,6 +291,37 @@ def test_pipelined_stream_equals_sequential_steps(oracle, cuda):
         assert torch.equal(l1[i, : int(n1[i])], l2[i, : int(n2[i])])
 
 
+def test_deskew_angle_equals_the_reference_on_pages_where_numpy_and_glibc_disagree(oracle, cuda):
+    """tests/golden/angle_golden.json: angles of the unmodified reference on pages whose median Hough segment is one
+    where numpy's arctan2 (SIMD math on AVX-512 builds) and glibc's atan2 differ in the last place.  The device
+    chain + numpy host decision must give the reference's float64, through the per-page op and through the pipeline."""
+    import json
+
+    import torch
+    from ocr_system_b200 import ops
+    from ocr_system_b200.pipeline import PagePipeline
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "angle_golden.json")) as f:
+        ANGLE_GOLD = json.load(f)
+    try:
+        from numpy._core._multiarray_umath import __cpu_features__ as feats
+        skx = bool(feats.get("AVX512_SKX"))
+    except Exception:  # noqa: BLE001
+        skx = False
+    same_dispatch = np.__version__ == ANGLE_GOLD["numpy"] and skx == ANGLE_GOLD["numpy_avx512_skx"]
+    cases = ANGLE_GOLD["cases"]
+    pages = np.stack([oracle.synth_page(c["h"], c["w"], c["seed"]) for c in cases])
+    res = PagePipeline(max_dimension=cases[0]["max_dim"]).run_device(_t(pages, cuda))
+    small = ops.resize_if_needed(_t(pages, cuda), cases[0]["max_dim"])
+    _, angles = ops.deskew(small)
+    for i, c in enumerate(cases):
+        _, want, _ = oracle.deskew(small[i].cpu().numpy())
+        assert angles[i] == want and res.angles[i] == want, c["seed"]
+        if same_dispatch:
+            assert float(angles[i]).hex() == c["angle_hex"], c["seed"]
+
+
 def test_ingest_zero_copy_and_fallback_agree(cuda):
     """PIL pages reach the device the same whether Pillow's storage can be viewed through Arrow (one allocator
     block) or has to go through np.asarray (multi-block image, odd L width)."""

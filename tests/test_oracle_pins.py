@@ -114,3 +114,49 @@ def test_otsu_restatement_equals_cv2(oracle):
     for g in imgs:
         t, mask = cv2.threshold(g, 0, 255, cv2.THRESH_BINARY | cv2.THRESH_OTSU)
         assert oracle.otsu_threshold(g) == int(t)
+
+
+ANGLE_GOLD = json.load(open(os.path.join(HERE, "golden", "angle_golden.json")))
+
+
+def _numpy_simd_tag():
+    try:
+        from numpy._core._multiarray_umath import __cpu_features__ as feats
+        return bool(feats.get("AVX512_SKX"))   # numpy's bundled SVML loops are built for AVX512_SKX
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def test_deskew_angle_is_numpys_arctan2_not_glibcs(oracle):
+    """The reference's per-segment angle is np.degrees(np.arctan2(dy, dx)) (image_preprocessing.py:421).  Goldens from
+    the unmodified reference (tests/golden/make_angle_golden.py) include pages whose median segment is one where
+    numpy's SIMD arctan2 and glibc's atan2 differ in the last place: the oracle must give numpy's value.  The golden
+    values are those of the numpy build / CPU dispatch recorded in the file; on a host whose numpy dispatches
+    differently the reference itself would give other last digits, so there the test only checks self-consistency."""
+    import numpy as np
+
+    same_dispatch = np.__version__ == ANGLE_GOLD["numpy"] and _numpy_simd_tag() == ANGLE_GOLD["numpy_avx512_skx"]
+    assert ANGLE_GOLD["differing"], "the golden set must contain pages where numpy and glibc disagree"
+    for c in ANGLE_GOLD["cases"]:
+        small = oracle.resize_lanczos(oracle.synth_page(c["h"], c["w"], c["seed"]), *_target(c["w"], c["h"], c["max_dim"]))
+        _, angle, lines = oracle.deskew(small)
+        assert len(lines) == c["n_lines"]
+        if same_dispatch:
+            assert float(angle).hex() == c["angle_hex"], c["seed"]
+        # numpy's vectorised arctan2 (the product's host layer) == its scalar one (the reference's loop), always
+        from ocr_system_b200 import ops
+
+        la = ops.line_angles(lines)
+        ref = []
+        for x1, y1, x2, y2 in lines:
+            a = np.degrees(np.arctan2(y2 - y1, x2 - x1))
+            ref.append(a + 90 if a < -45 else (a - 90 if a > 45 else a))
+        assert np.array_equal(la, np.array(ref))
+        got, _, _ = ops.deskew_decide(lines[None], np.array([len(lines)], np.int32), small.shape[0], small.shape[1])
+        assert got[0] == (angle if abs(angle) <= 45 else 0.0)
+
+
+def _target(w, h, md):
+    if max(w, h) <= md:
+        return w, h
+    return (md, int(h * md / w)) if w > h else (int(w * md / h), md)
