@@ -160,3 +160,18 @@ def _target(w, h, md):
     if max(w, h) <= md:
         return w, h
     return (md, int(h * md / w)) if w > h else (int(w * md / h), md)
+
+
+def test_rotation_matrix_equals_cv2_getRotationMatrix2D(oracle):
+    """image_preprocessing.py:442: the matrix the reference hands to warpAffine (OpenCV evaluates cos / sin with the C
+    library, unlike numpy's arctan2 above) -- oracle restatement and the library's host entry, 5000 angles, bit-equal."""
+    import cv2
+    import numpy as np
+    from ocr_system_b200 import ops
+
+    rng = np.random.default_rng(5)
+    for a in np.concatenate([rng.uniform(-45, 45, 5000), [0.5, -0.5, 45.0, -45.0, 1e-9]]):
+        for cx, cy in ((339, 480), (141, 200)):
+            m = cv2.getRotationMatrix2D((cx, cy), float(a), 1.0)
+            assert np.array_equal(m, oracle.rotation_matrix(cx, cy, float(a)))
+            assert np.array_equal(m, ops.rotation_matrix(cx, cy, float(a)))
