@@ -109,9 +109,18 @@ int lumina_sauvola_u8(const uint8_t *d_gray, uint8_t *d_dst, int n, int h, int w
                       void *stream);
 
 /* ---- a9  adaptive_binarize :462-494 (cv2.adaptiveThreshold GAUSSIAN 11,C) */
-/* c==3: fused PIL gray.  dst [n][h][w] in {0,255}. */
+/* c==3: fused PIL gray.  dst [n][h][w] in {0,255}.  OpenCV's plain float path (cv2.setUseOptimized(False)). */
 int lumina_adaptive_gauss11_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, int cval,
                                void *stream);
+/* The float Gaussian behind adaptiveThreshold is the one dispatch-dependent step of the reference's OpenCV calls:
+ * LUMINA_CV_PLAIN = every product and sum rounded separately (setUseOptimized(False), CPUs without AVX2);
+ * LUMINA_CV_AVX2  = OpenCV's default dispatch on x86 hosts with AVX2 + FMA3 -- what the reference runs unless told
+ * otherwise: fused multiply-add in the vector loops, not in the scalar remainders (row pass fused for
+ * x < w - w % 4, column pass for x < w - w % 8).  Each is bit-equal to cv2 in that mode. */
+#define LUMINA_CV_PLAIN 0
+#define LUMINA_CV_AVX2 1
+int lumina_adaptive_gauss11_ex_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, int cval,
+                                  int cv_dispatch, void *stream);
 
 /* ---- a10 deskew :372-460 ------------------------------------------------ */
 /* (i)+(ii) cv gray (c==3) + cv2.Canny(low, high, aperture 3, L1): edges [n][h][w] {0,255} */

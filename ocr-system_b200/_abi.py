@@ -46,6 +46,7 @@ PROTOTYPES = {
     "lumina_binarize_u8": (_I, [_P, _P, _Z, _I, _I, _P]),
     "lumina_rgbx_to_rgb_u8": (_I, [_P, _P, _Z, _P]),
     "lumina_adaptive_gauss11_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "lumina_adaptive_gauss11_ex_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "lumina_canny_workspace_bytes": (_Z, [_I, _I, _I]),
     "lumina_canny_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "lumina_ppht_workspace_bytes": (_Z, [_I, _I, _I, _D, _D]),

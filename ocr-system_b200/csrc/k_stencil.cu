@@ -160,7 +160,12 @@ constexpr int AT_TP = 80;                          // tile pitch in bytes (word-
 constexpr int AT_FP = AT_TW + 4;                   // float pitch (16-byte aligned rows)
 struct Gauss11 { float k[11]; };
 
-template <int C>
+// FUSED = OpenCV's default dispatch on x86 hosts with AVX2 + FMA3: the 8-lane vector loops of both filter passes (and
+// the row filter's 4-lane step behind them) use fused multiply-add, the scalar remainders do not: row pass fused for
+// x < w - (w % 4), column pass fused for x < w - (w % 8) (oracle/lumina_oracle.c orc_adaptive_gauss11_x has the
+// evidence).  FUSED = false is OpenCV's plain path.  The file is compiled with -fmad=false, so only the explicit
+// __fmaf_rn below is ever fused.
+template <int C, bool FUSED>
 __global__ void __launch_bounds__(256) adaptive_gauss11_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                                int h, int w, int cval, const Gauss11 g) {
     __shared__ __align__(16) uint8_t tile[AT_ROWS][AT_TP];
@@ -195,11 +200,17 @@ __global__ void __launch_bounds__(256) adaptive_gauss11_kernel(const uint8_t *__
 #pragma unroll
         for (int b = 0; b < 14; b++) xf[b] = (float)((wd[b >> 2] >> (8 * (b & 3))) & 255u);
         float o[4];
+        const int row_fused_end = w - (w & 3);
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             float acc = __fmul_rn(xf[e], g.k[0]);
+            if (FUSED && x0 + q * 4 + e < row_fused_end) {
 #pragma unroll
-            for (int k = 1; k < 11; k++) acc = __fadd_rn(acc, __fmul_rn(xf[e + k], g.k[k]));
+                for (int k = 1; k < 11; k++) acc = __fmaf_rn(xf[e + k], g.k[k], acc);
+            } else {
+#pragma unroll
+                for (int k = 1; k < 11; k++) acc = __fadd_rn(acc, __fmul_rn(xf[e + k], g.k[k]));
+            }
             o[e] = acc;
         }
         *reinterpret_cast<float4 *>(&rowf[ty][q * 4]) = make_float4(o[0], o[1], o[2], o[3]);
@@ -218,9 +229,14 @@ __global__ void __launch_bounds__(256) adaptive_gauss11_kernel(const uint8_t *__
             const int y = y0 + ty0 + e;
             if (y >= h) break;
             float acc = __fmul_rn(g.k[5], rf[e + AT_R]);
+            if (FUSED && x < w - (w & 7)) {
 #pragma unroll
-            for (int k = 1; k <= 5; k++)
-                acc = __fadd_rn(acc, __fmul_rn(g.k[5 + k], __fadd_rn(rf[e + AT_R + k], rf[e + AT_R - k])));
+                for (int k = 1; k <= 5; k++) acc = __fmaf_rn(g.k[5 + k], __fadd_rn(rf[e + AT_R + k], rf[e + AT_R - k]), acc);
+            } else {
+#pragma unroll
+                for (int k = 1; k <= 5; k++)
+                    acc = __fadd_rn(acc, __fmul_rn(g.k[5 + k], __fadd_rn(rf[e + AT_R + k], rf[e + AT_R - k])));
+            }
             int m = __float2int_rn(acc);
             m = min(max(m, 0), 255);
             const int sv = tile[ty0 + e + AT_R][tx + AT_R];
@@ -271,11 +287,12 @@ LUMINA_API int lumina_median3_u8(const uint8_t *d_src, uint8_t *d_dst, int n, in
     return launch_stencil3<2>(d_src, d_dst, n, h, w, c, nullptr, 1.0f, 1.0f, stream, "stencil3_kernel<median>");
 }
 
-LUMINA_API int lumina_adaptive_gauss11_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, int cval,
-                                          void *stream) {
+LUMINA_API int lumina_adaptive_gauss11_ex_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, int cval,
+                                             int cv_dispatch, void *stream) {
     LUMINA_REQUIRE(d_src && d_dst, "null pointer");
     LUMINA_REQUIRE(c == 1 || c == 3, "c must be 1 or 3");
     LUMINA_REQUIRE(n > 0 && h > 0 && w > 0, "empty batch");
+    LUMINA_REQUIRE(cv_dispatch == LUMINA_CV_PLAIN || cv_dispatch == LUMINA_CV_AVX2, "cv_dispatch must be LUMINA_CV_PLAIN or LUMINA_CV_AVX2");
     // cv::getGaussianKernel(11, sigma = 0.3*((11-1)*0.5-1)+0.8 = 2.0) -> float32 taps
     Gauss11 g;
     {
@@ -288,8 +305,16 @@ LUMINA_API int lumina_adaptive_gauss11_u8(const uint8_t *d_src, uint8_t *d_dst, 
     dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), n);
     LUMINA_REQUIRE(grid.y <= 65535 && n <= 65535, "image too large for grid");
     cudaStream_t st = as_stream(stream);
-    if (c == 3) adaptive_gauss11_kernel<3><<<grid, 256, 0, st>>>(d_src, d_dst, h, w, cval, g);
-    else adaptive_gauss11_kernel<1><<<grid, 256, 0, st>>>(d_src, d_dst, h, w, cval, g);
+    const bool fused = cv_dispatch == LUMINA_CV_AVX2;
+    if (c == 3 && fused) adaptive_gauss11_kernel<3, true><<<grid, 256, 0, st>>>(d_src, d_dst, h, w, cval, g);
+    else if (c == 3) adaptive_gauss11_kernel<3, false><<<grid, 256, 0, st>>>(d_src, d_dst, h, w, cval, g);
+    else if (fused) adaptive_gauss11_kernel<1, true><<<grid, 256, 0, st>>>(d_src, d_dst, h, w, cval, g);
+    else adaptive_gauss11_kernel<1, false><<<grid, 256, 0, st>>>(d_src, d_dst, h, w, cval, g);
     LUMINA_KERNEL_CHECK("adaptive_gauss11_kernel");
     return LUMINA_OK;
+}
+
+LUMINA_API int lumina_adaptive_gauss11_u8(const uint8_t *d_src, uint8_t *d_dst, int n, int h, int w, int c, int cval,
+                                          void *stream) {
+    return lumina_adaptive_gauss11_ex_u8(d_src, d_dst, n, h, w, c, cval, LUMINA_CV_PLAIN, stream);
 }

@@ -54,10 +54,14 @@ def _setting(name: str, default):
 class ImagePreprocessor:
     """GPU image preprocessing with the reference's call signatures."""
 
-    def __init__(self, max_dimension: int = None, target_dpi: int = 300, device: Optional[str] = None):
+    def __init__(self, max_dimension: int = None, target_dpi: int = 300, device: Optional[str] = None,
+                 cv_dispatch: Optional[str] = None):
         self.max_dimension = max_dimension or _setting("OCR_MAX_IMAGE_DIMENSION", 2000)
         self.target_dpi = target_dpi
         self._device = device
+        # which OpenCV build adaptive_binarize reproduces: None = ops.default_cv_dispatch() ("avx2": OpenCV's default
+        # dispatch, what the reference runs), "plain" = cv2.setUseOptimized(False)
+        self.cv_dispatch = cv_dispatch
         # The reference singleton is stateless and is called from asyncio.to_thread workers
         # (services/ocr_service.py:674-676).  This one owns a pinned staging buffer and a JPEG workspace: both are
         # per calling thread, so concurrent callers never see each other's pixels or DCT coefficients.
@@ -409,7 +413,7 @@ class ImagePreprocessor:
         return self._to_pil(out), angle
 
     def adaptive_binarize(self, image: Image.Image) -> Image.Image:
-        return self._to_pil(ops.adaptive_binarize(self._gray_source(image), 2))
+        return self._to_pil(ops.adaptive_binarize(self._gray_source(image), 2, self.cv_dispatch))
 
     def compress_pages_for_azure(self, pages: torch.Tensor, target_size_mb: float = 2.0, initial_quality: int = 95,
                                  min_quality: int = 30) -> List[bytes]:
@@ -486,7 +490,7 @@ class ImagePreprocessor:
         if apply_deskew:
             x, angles = ops.deskew(x)
         if apply_binarize:
-            x = ops.adaptive_binarize(x, 2)
+            x = ops.adaptive_binarize(x, 2, self.cv_dispatch)
         elif apply_contrast and apply_sharpness:
             x = ops.contrast_sharpness(x, 1.2, 1.1)
         elif apply_contrast:

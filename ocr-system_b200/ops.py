@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import os
 import threading
 from typing import Optional, Tuple
 
@@ -262,11 +263,27 @@ def sauvola_binarize(gray: torch.Tensor, window: int = 25, k: float = 0.2, r: fl
     return out
 
 
+CV_DISPATCH = {"plain": 0, "avx2": 1}   # LUMINA_CV_PLAIN / LUMINA_CV_AVX2 (include/lumina_b200.h)
+
+
+def default_cv_dispatch() -> str:
+    """Which OpenCV build the float Gaussian of adaptiveThreshold reproduces when a caller does not say: "avx2" --
+    OpenCV's default dispatch on x86 hosts with AVX2 + FMA3, i.e. what the reference runs (it never calls
+    cv2.setUseOptimized) -- unless LUMINA_CV_DISPATCH=plain asks for OpenCV's plain path."""
+    v = os.environ.get("LUMINA_CV_DISPATCH", "avx2")
+    if v not in CV_DISPATCH:
+        raise ValueError(f"LUMINA_CV_DISPATCH must be one of {sorted(CV_DISPATCH)}, not {v!r}")
+    return v
+
+
 @_on_tensor_device
-def adaptive_binarize(pages: torch.Tensor, cval: int = 2) -> torch.Tensor:
+def adaptive_binarize(pages: torch.Tensor, cval: int = 2, cv_dispatch: Optional[str] = None) -> torch.Tensor:
+    """cv2.adaptiveThreshold(GAUSSIAN_C, BINARY, 11, cval) of gray planes [N,H,W] (or RGB pages: PIL gray fused),
+    bit-equal to OpenCV in the named dispatch mode (``default_cv_dispatch`` when None)."""
     x, n, h, w, c = _pages(pages)
+    mode = CV_DISPATCH[cv_dispatch if cv_dispatch is not None else default_cv_dispatch()]
     out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
-    _chk(_L().lumina_adaptive_gauss11_u8(_ptr(x), _ptr(out), n, h, w, c, int(cval), _stream()))
+    _chk(_L().lumina_adaptive_gauss11_ex_u8(_ptr(x), _ptr(out), n, h, w, c, int(cval), mode, _stream()))
     return out
 
 

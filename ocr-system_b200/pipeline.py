@@ -111,13 +111,15 @@ class PageBatchResult:
 
 class PagePipeline:
     def __init__(self, max_dimension: int = 960, deskew: bool = True, enhance: bool = False,
-                 det_limit_side_len: int = 960, device: Optional[torch.device] = None, deskew_mode: str = "exact"):
+                 det_limit_side_len: int = 960, device: Optional[torch.device] = None, deskew_mode: str = "exact",
+                 cv_dispatch: Optional[str] = None):
         """``deskew_mode``: "exact" (default) reproduces the reference's angle bit for bit (Canny + HoughLinesP +
         median); "fast" takes it from the projection-profile estimator (``ops.estimate_skew_fast``): a different,
         tolerance-certified estimate -- rasters then differ from the reference's (tests/test_gpu_fast_skew.py)."""
         if deskew_mode not in ("exact", "fast"):
             raise ValueError("deskew_mode must be 'exact' or 'fast'")
         self.deskew_mode = deskew_mode
+        self.cv_dispatch = cv_dispatch      # OpenCV build the adaptive threshold reproduces (ops.default_cv_dispatch when None)
         self.max_dimension = int(max_dimension)
         self.deskew = deskew
         self.enhance = enhance
@@ -166,7 +168,7 @@ class PagePipeline:
         if self.enhance:
             x = t.run("contrast+sharpness", lambda: ops.contrast_sharpness(x, 1.2, 1.1))
         gray = t.run("gray_pil", lambda: ops.gray_pil(x))
-        binary = t.run("adaptive_binarize", lambda: ops.adaptive_binarize(gray, 2))
+        binary = t.run("adaptive_binarize", lambda: ops.adaptive_binarize(gray, 2, self.cv_dispatch))
         det, shape_list = t.run("det_resize_normalize", lambda: ops.det_resize_normalize(x, self.det_limit))
         return x, gray, binary, det, shape_list
 

@@ -164,10 +164,16 @@ def exif_transpose(img, orientation: int):
 
 
 # --- A6 ---------------------------------------------------------------------
-def adaptive_gauss11(gray, cval: int = 2):
+CV_DISPATCH = {"plain": 0, "avx2": 1}
+
+
+def adaptive_gauss11(gray, cval: int = 2, cv_dispatch: str = "plain"):
+    """cv2.adaptiveThreshold(GAUSSIAN_C, BINARY, 11, cval).  ``cv_dispatch``: "plain" = OpenCV's plain float path
+    (cv2.setUseOptimized(False): the 217 goldens), "avx2" = OpenCV's default dispatch on x86 hosts with AVX2 + FMA3
+    (what the reference runs unless told otherwise; tests/golden/adaptive_dispatch_golden.json)."""
     gray = _u8(gray)
     out = np.empty_like(gray)
-    lib().orc_adaptive_gauss11(_p(gray), gray.shape[0], gray.shape[1], cval, _p(out))
+    lib().orc_adaptive_gauss11_x(_p(gray), gray.shape[0], gray.shape[1], cval, CV_DISPATCH[cv_dispatch], _p(out))
     return out
 
 

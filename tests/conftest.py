@@ -28,3 +28,13 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def cv2_dispatch() -> str:
+    """The lumina ``cv_dispatch`` value that names the mode the LIVE cv2 of this process is in right now
+    (cv2.setUseOptimized is process-global and some fixtures switch it off): tests that compare with a live OpenCV
+    call pass this to the product so that both sides run the same float path of adaptiveThreshold."""
+    import cv2
+
+    return "avx2" if cv2.useOptimized() and cv2.checkHardwareSupport(10) and cv2.checkHardwareSupport(12) else "plain"
+

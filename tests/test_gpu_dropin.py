@@ -53,7 +53,7 @@ def ip(cuda):
     cv2.setUseOptimized(False)
     from ocr_system_b200.image_preprocessing import ImagePreprocessor
 
-    return ImagePreprocessor(max_dimension=MAX_DIM)
+    return ImagePreprocessor(max_dimension=MAX_DIM, cv_dispatch="plain")   # the goldens were made with setUseOptimized(False)
 
 
 @pytest.mark.parametrize("case", MODE_CASES, ids=[f"{c['mode']}-{c['method']}" for c in MODE_CASES])
@@ -96,7 +96,7 @@ def _oracle_chain(O, page, md, enhance):
     if enhance:
         img = O.sharpness(O.contrast(img, 1.2), 1.1)
     g = O.gray_pil(img)
-    return img, angle, g, O.adaptive_gauss11(g, 2)
+    return img, angle, g, O.adaptive_gauss11(g, 2, cv_dispatch="avx2")   # PagePipeline's default: OpenCV's default dispatch
 
 
 def _host_batches(O, n_batches, per, h, w, seed0=0):

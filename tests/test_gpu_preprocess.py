@@ -132,15 +132,43 @@ def test_contrast_sharpness_median(oracle, cuda, h, w, c):
         assert np.array_equal(got[i], oracle.median3(img[i]))
 
 
-@pytest.mark.parametrize("h,w,c", [(960, 678, 3), (101, 77, 1), (130, 67, 3), (11, 9, 1)])
-def test_adaptive_binarize(oracle, cuda, h, w, c):
+@pytest.mark.parametrize("dispatch", ["plain", "avx2"])
+@pytest.mark.parametrize("h,w,c", [(960, 678, 3), (101, 77, 1), (130, 67, 3), (11, 9, 1), (64, 70, 1), (40, 132, 3)])
+def test_adaptive_binarize(oracle, cuda, h, w, c, dispatch):
     from ocr_system_b200 import ops
 
     img = np.stack([(_page(oracle, h, w, s) if h >= 900 else _rand(h, w, c, s)) for s in range(2)])
-    got = ops.adaptive_binarize(_t(img, cuda), 2).cpu().numpy()
+    got = ops.adaptive_binarize(_t(img, cuda), 2, cv_dispatch=dispatch).cpu().numpy()
     for i in range(2):
         g = oracle.gray_pil(img[i]) if c == 3 else img[i]
-        assert np.array_equal(got[i], oracle.adaptive_gauss11(g, 2))
+        assert np.array_equal(got[i], oracle.adaptive_gauss11(g, 2, cv_dispatch=dispatch))
+    assert ops.default_cv_dispatch() == "avx2"
+
+
+def test_adaptive_binarize_equals_the_reference_under_both_opencv_dispatch_modes(oracle, cuda):
+    """tests/golden/adaptive_dispatch_golden.json: the unmodified reference's adaptive_binarize under OpenCV's default
+    dispatch (AVX2 + FMA3: fused multiply-add in the filter's vector loops) and under the plain path, on planes where
+    the two differ, every width residue mod 8 (the scalar remainders are not fused)."""
+    import hashlib
+    import json
+    import os
+    import sys
+
+    from ocr_system_b200 import ops
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from adaptive_inputs import plane
+
+    with open(os.path.join(here, "golden", "adaptive_dispatch_golden.json")) as f:
+        gold = json.load(f)
+    assert sum(1 for c in gold["cases"] if c["differing_px"]) >= 10
+    for c in gold["cases"]:
+        g = plane(c["seed"])
+        assert g.shape == (c["h"], c["w"])
+        for mode, key in (("avx2", "sha_default"), ("plain", "sha_plain")):
+            got = ops.adaptive_binarize(_t(g[None], cuda), 2, cv_dispatch=mode).cpu().numpy()[0]
+            assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == c[key], (c["seed"], mode)
 
 
 @pytest.mark.parametrize("orientation", [1, 2, 3, 4, 5, 6, 7, 8])

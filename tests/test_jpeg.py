@@ -107,7 +107,9 @@ def test_gpu_preprocess_for_azure_files_equal_reference_sequence(cuda, oracle, b
 
     pages = [oracle.synth_page(877, 620, s) for s in (0, 1, 2)] + [oracle.synth_page(620, 877, 3)]
     imgs = [Image.fromarray(p) for p in pages]
-    ip = ImagePreprocessor(max_dimension=400)
+    from conftest import cv2_dispatch
+
+    ip = ImagePreprocessor(max_dimension=400, cv_dispatch=cv2_dispatch())   # RP runs the live cv2 of this process
     got = ip.preprocess_pages_for_azure(imgs, apply_binarize=binarize)
     for p, im, g in zip(pages, imgs, got):
         want = RP.preprocess_for_azure(p, 400, apply_binarize=binarize)

@@ -175,3 +175,26 @@ def test_rotation_matrix_equals_cv2_getRotationMatrix2D(oracle):
             m = cv2.getRotationMatrix2D((cx, cy), float(a), 1.0)
             assert np.array_equal(m, oracle.rotation_matrix(cx, cy, float(a)))
             assert np.array_equal(m, ops.rotation_matrix(cx, cy, float(a)))
+
+
+def test_adaptive_threshold_oracle_under_both_opencv_dispatch_modes(oracle):
+    """The float Gaussian of cv2.adaptiveThreshold is the one dispatch-dependent OpenCV step of the path.  Goldens from
+    the unmodified reference in both modes (tests/golden/make_adaptive_golden.py); additionally the live cv2 of this
+    process in whichever mode it is in."""
+    import hashlib
+
+    import cv2
+    import numpy as np
+    from adaptive_inputs import plane
+    from conftest import cv2_dispatch
+
+    with open(os.path.join(HERE, "golden", "adaptive_dispatch_golden.json")) as f:
+        gold = json.load(f)
+    for c in gold["cases"]:
+        g = plane(c["seed"])
+        for mode, key in (("avx2", "sha_default"), ("plain", "sha_plain")):
+            got = oracle.adaptive_gauss11(g, 2, cv_dispatch=mode)
+            assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == c[key], (c["seed"], mode)
+        live = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY, 11, 2)
+        assert np.array_equal(live, oracle.adaptive_gauss11(g, 2, cv_dispatch=cv2_dispatch())), c["seed"]
+
