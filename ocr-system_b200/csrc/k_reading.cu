@@ -162,7 +162,37 @@ __global__ void __launch_bounds__(RO_THREADS) reading_order_kernel(const double 
         line_conf[o0 + l] = cs.value() / (double)(b - a);
         line_y[o0 + l] = ys.value() / (double)(b - a);
     }
-    if (tid == 0) nlines[page] = nl;
+    // ---- merged.sort(key=lambda m: m.y_position), stable (ocr_postprocessor.py:181) ----
+    // Lines are runs of the y-sorted list, so their means ascend -- except in the last place: with a zero tolerance two
+    // lines may be one ulp apart and the rounded mean of the first may come out above the second's.  Found by the
+    // randomised sweep (tools/sweep_paddle_vs_oracle.py, 1000 jittered boxes, ratio 0).  Rare: one thread repairs it.
+    __syncthreads();
+    if (tid == 0) {
+        bool sorted = true;
+        for (int l = 1; l < nl && sorted; l++) sorted = !(line_y[o0 + l] < line_y[o0 + l - 1]);
+        if (!sorted) {
+            int *perm = lstart + npad + 1;   // [npad]
+            for (int l = 0; l < nl; l++) { perm[l] = l; yc[l] = line_y[o0 + l]; xl[l] = line_conf[o0 + l]; }   // yc / xl are free now
+            for (int i = 1; i < nl; i++) {   // stable insertion sort: a line moves only past strictly larger means
+                const int pl = perm[i];
+                const double v = yc[pl];
+                int j = i - 1;
+                while (j >= 0 && yc[perm[j]] > v) { perm[j + 1] = perm[j]; j--; }
+                perm[j + 1] = pl;
+            }
+            int pos = 0;
+            for (int j = 0; j < nl; j++) {
+                const int l = perm[j];
+                for (int k = lstart[l]; k < lstart[l + 1]; k++, pos++) {
+                    order[o0 + pos] = keys[k].idx & 0xffff;
+                    line_of[o0 + pos] = j;
+                }
+                line_conf[o0 + j] = xl[l];
+                line_y[o0 + j] = yc[l];
+            }
+        }
+        nlines[page] = nl;
+    }
 }
 
 }  // namespace lumina
@@ -178,7 +208,7 @@ LUMINA_API int lumina_reading_order(const double *d_boxes, const double *d_conf,
     LUMINA_REQUIRE(max_boxes_per_page >= 0 && max_boxes_per_page <= RO_MAX_BOXES, "more than 4096 boxes on a page");
     int npad = 32;
     while (npad < max_boxes_per_page) npad <<= 1;
-    const size_t smem = (size_t)npad * (sizeof(RoKey) + 16) + (size_t)(npad + 1) * 4;
+    const size_t smem = (size_t)npad * (sizeof(RoKey) + 16) + (size_t)(npad + 1) * 4 + (size_t)npad * 4;   // keys, yc, xl, lstart, perm
     if (smem > 48 * 1024)
         LUMINA_CUDA_TRY(cudaFuncSetAttribute(reading_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reading_order_kernel<<<n_pages, RO_THREADS, smem, as_stream(stream)>>>(d_boxes, d_conf, d_offsets, y_tolerance_ratio, one_line, d_order,
