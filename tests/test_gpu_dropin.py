@@ -386,3 +386,27 @@ def test_tiff_and_png_files_take_the_host_codec_and_match_the_reference_sequence
         want = RP.preprocess_for_azure(np.asarray(ref_in), max_dim=600, target_size_mb=0.2)
         assert ip_.preprocess_for_azure(path, target_size_mb=0.2) == want, name
         assert ip_.preprocess_pages_for_azure([path, path.read_bytes()], target_size_mb=0.2) == [want, want], name
+
+
+def test_dropin_equals_the_real_reference_module_on_random_calls(oracle, cuda):
+    """The unmodified reference module travels with the snapshot (oracle/_ref, placed by oracle/make_ref.py): run it
+    beside the drop-in on random PIL images (modes, sizes, contents) through every public method with random arguments
+    and require identical results -- PIL mode / size / bytes, float64 angle, JPEG file bytes, exception type
+    (tools/sweep_dropin_vs_reference.py; 5720 calls of the full sweep: profiles/r2_sweep_dropin_vs_reference.json).
+    cv2 must be in its default dispatch here, like in the application."""
+    import cv2
+
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    from sweep_dropin_vs_reference import sweep
+
+    was = cv2.useOptimized()
+    cv2.setUseOptimized(True)
+    try:
+        res = sweep(1000, 1016, verbose=False)
+    finally:
+        cv2.setUseOptimized(was)
+    if res is None:
+        pytest.skip("oracle/_ref is not in this snapshot (no /root/reference when build() ran)")
+    checked, bad = res
+    assert checked == 16 * 11 and not bad, bad[:3]
+
