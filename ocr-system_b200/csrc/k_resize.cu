@@ -1050,12 +1050,20 @@ LUMINA_API void lumina_resize_plan_destroy(lumina_resize_plan *pl) {
     delete pl;
 }
 
+// Pillow (12.2.0) runs the VERTICAL pass first on very tall images that shrink vertically: both passes needed,
+// in_h > 100 * in_w and out_h < in_h (rule and evidence: oracle/lumina_oracle.c orc_vertical_first).  The uint8
+// intermediate makes the order visible, so such geometries (strips a few pixels wide) take the generic kernels in that order.
+static bool vertical_first(const lumina_resize_plan *pl) {
+    return pl->in_w != pl->out_w && pl->in_h != pl->out_h && (long long)pl->in_h > 100LL * pl->in_w && pl->out_h < pl->in_h;
+}
+
 static bool fused_ok(const lumina_resize_plan *pl) {
-    return pl->kx <= 32 && pl->ky + RB <= RING && pl->in_w != pl->out_w && pl->in_h != pl->out_h;
+    return pl->kx <= 32 && pl->ky + RB <= RING && pl->in_w != pl->out_w && pl->in_h != pl->out_h && !vertical_first(pl);
 }
 
 LUMINA_API size_t lumina_resize_workspace_bytes(const lumina_resize_plan *pl, int n, int c) {
     if (!pl || fused_ok(pl)) return 0;
+    if (vertical_first(pl)) return (size_t)n * pl->out_h * pl->in_w * c;
     return (size_t)n * pl->in_h * pl->out_w * c;  // HBM intermediate of the generic two-pass path
 }
 
@@ -1233,6 +1241,26 @@ LUMINA_API int lumina_resize_lanczos_u8(const lumina_resize_plan *pl, const uint
     }
     // generic two-pass path
     const size_t need = lumina_resize_workspace_bytes(pl, n, c);
+    if (vertical_first(pl)) {
+        if (!d_workspace || workspace_bytes < need)
+            return set_error(LUMINA_E_NOMEM, "resize workspace too small: need %zu bytes", need);
+        const int row_bytes = pl->in_w * c;
+        LUMINA_REQUIRE(pl->out_h <= 65535 && n <= 65535, "image too tall for grid");
+        resize_v_generic_kernel<<<dim3(div_up(row_bytes, 256), pl->out_h, n), 256, 0, st>>>(d_src, (uint8_t *)d_workspace, pl->d_by, pl->d_cy,
+                                                                                          pl->ky, pl->in_h, pl->out_h, row_bytes);
+        LUMINA_KERNEL_CHECK("resize_v_generic_kernel");
+        const long long rows_v = (long long)n * pl->out_h;
+        for (long long r0 = 0; r0 < rows_v; r0 += 65535) {
+            const int rows = (int)((rows_v - r0 < 65535) ? rows_v - r0 : 65535);
+            dim3 grid(div_up(pl->out_w, 256), rows);
+            const uint8_t *s = (const uint8_t *)d_workspace + (size_t)r0 * pl->in_w * c;
+            uint8_t *d = d_dst + (size_t)r0 * pl->out_w * c;
+            if (c == 3) resize_h_generic_kernel<3><<<grid, 256, 0, st>>>(s, d, pl->d_bx, pl->d_cx, pl->kx, rows, pl->in_w, pl->out_w);
+            else resize_h_generic_kernel<1><<<grid, 256, 0, st>>>(s, d, pl->d_bx, pl->d_cx, pl->kx, rows, pl->in_w, pl->out_w);
+            LUMINA_KERNEL_CHECK("resize_h_generic_kernel");
+        }
+        return LUMINA_OK;
+    }
     const uint8_t *hsrc = d_src;
     const long long rows_total = (long long)n * pl->in_h;
     LUMINA_REQUIRE(rows_total <= 65535LL * 32768LL, "batch too large");

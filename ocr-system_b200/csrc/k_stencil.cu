@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) stencil3_kernel(const uint8_t *__restrict
             const long long q = q0 + j;
             valid[j] = q >= 0 && q < page_bytes;
             long long yy = y, xx = xb + j;
-            if (xx >= pitch) { xx -= pitch; yy += 1; }
+            while (xx >= pitch) { xx -= pitch; yy += 1; }   // a 4-byte group spans several rows when a row has fewer than 4 bytes
             const int kc = 4 + j;
             const int center = win_byte(mid, kc);
             uint32_t o;

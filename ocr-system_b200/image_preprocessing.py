@@ -222,6 +222,8 @@ class ImagePreprocessor:
             return image
         new_w, new_h = ops.target_size(width, height, max_dim)
         logger.info(f"Resizing image from {width}x{height} to {new_w}x{new_h}")
+        if new_w < 1 or new_h < 1:    # Pillow's Image.resize raises this for every mode (reference :110)
+            raise ValueError("height and width must be > 0")
         if image.mode in ("RGB", "L"):
             return self._to_pil(ops.resize_lanczos(self._to_device(image), new_w, new_h))
         if image.mode in ("P", "1"):      # Pillow's Image.resize forces NEAREST for these two modes

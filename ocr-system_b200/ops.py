@@ -150,6 +150,8 @@ def resize_if_needed(pages: torch.Tensor, max_dim: int) -> torch.Tensor:
     if max(w, h) <= max_dim:
         return pages
     ow, oh = target_size(w, h, max_dim)
+    if ow < 1 or oh < 1:      # a strip so thin that its short side rounds to 0: Pillow's Image.resize raises this
+        raise ValueError("height and width must be > 0")
     return resize_lanczos(pages, ow, oh)
 
 

@@ -87,50 +87,67 @@ ORC_API void orc_lanczos_coeffs(int in_size, int out_size, int32_t *bounds, int3
     free(k);
 }
 
-/* src: h x w x c (tight), dst: oh x ow x c.  Horizontal pass first, uint8
- * intermediate, then vertical (Resample.c ImagingResampleInner). */
-ORC_API void orc_resize_lanczos_u8(const uint8_t *src, int h, int w, int c, uint8_t *dst, int oh, int ow) {
-    int kx = orc_lanczos_ksize(w, ow), ky = orc_lanczos_ksize(h, oh);
+/* src: h x w x c (tight), dst: oh x ow x c.  Two passes with a uint8 intermediate (Resample.c ImagingResampleInner).
+ * Pass order: horizontal first -- except for very tall images that shrink vertically, where Pillow (12.2.0) runs the
+ * vertical pass first: both passes needed, h > 100 * w and oh < h.  The intermediate is rounded to uint8, so the order
+ * is visible in the result.  Rule found by probing Image.resize here (boundary exact at h = 100 w + 1 for L and RGB,
+ * independent of the target width; oh >= h keeps the horizontal pass first) after the degenerate-shape sweep
+ * (tools/sweep_dropin_vs_reference.py --tiny) showed differences on 4 x 2212 -> 3 x 2000 pages. */
+static int orc_vertical_first(int h, int w, int oh, int ow) {
+    return ow != w && oh != h && (long long)h > 100LL * w && oh < h;
+}
+static void orc_resize_h(const uint8_t *src, int h, int w, int c, uint8_t *dst, int ow) {
+    int kx = orc_lanczos_ksize(w, ow);
     int32_t *bx = (int32_t *)malloc(sizeof(int32_t) * 2 * ow);
     int32_t *cx = (int32_t *)malloc(sizeof(int32_t) * (size_t)kx * ow);
+    orc_lanczos_coeffs(w, ow, bx, cx);
+    for (int y = 0; y < h; y++) {
+        const uint8_t *row = src + (size_t)y * w * c;
+        uint8_t *orow = dst + (size_t)y * ow * c;
+        for (int xx = 0; xx < ow; xx++) {
+            int xmin = bx[xx * 2], n = bx[xx * 2 + 1];
+            const int32_t *k = cx + (size_t)xx * kx;
+            for (int ch = 0; ch < c; ch++) {
+                int ss = 1 << (ORC_PREC_BITS - 1);
+                for (int x = 0; x < n; x++) ss += row[(xmin + x) * c + ch] * k[x];
+                orow[xx * c + ch] = sat_u8(ss >> ORC_PREC_BITS);
+            }
+        }
+    }
+    free(bx); free(cx);
+}
+static void orc_resize_v(const uint8_t *src, int h, int row_bytes, uint8_t *dst, int oh) {
+    int ky = orc_lanczos_ksize(h, oh);
     int32_t *by = (int32_t *)malloc(sizeof(int32_t) * 2 * oh);
     int32_t *cy = (int32_t *)malloc(sizeof(int32_t) * (size_t)ky * oh);
-    orc_lanczos_coeffs(w, ow, bx, cx);
     orc_lanczos_coeffs(h, oh, by, cy);
-    const uint8_t *hsrc = src;
-    uint8_t *tmp = NULL;
-    if (ow != w) {
-        tmp = (uint8_t *)malloc((size_t)h * ow * c);
-        for (int y = 0; y < h; y++) {
-            const uint8_t *row = src + (size_t)y * w * c;
-            uint8_t *orow = tmp + (size_t)y * ow * c;
-            for (int xx = 0; xx < ow; xx++) {
-                int xmin = bx[xx * 2], n = bx[xx * 2 + 1];
-                const int32_t *k = cx + (size_t)xx * kx;
-                for (int ch = 0; ch < c; ch++) {
-                    int ss = 1 << (ORC_PREC_BITS - 1);
-                    for (int x = 0; x < n; x++) ss += row[(xmin + x) * c + ch] * k[x];
-                    orow[xx * c + ch] = sat_u8(ss >> ORC_PREC_BITS);
-                }
-            }
+    for (int yy = 0; yy < oh; yy++) {
+        int ymin = by[yy * 2], n = by[yy * 2 + 1];
+        const int32_t *k = cy + (size_t)yy * ky;
+        uint8_t *orow = dst + (size_t)yy * row_bytes;
+        for (int i = 0; i < row_bytes; i++) {
+            int ss = 1 << (ORC_PREC_BITS - 1);
+            for (int y = 0; y < n; y++) ss += src[(size_t)(ymin + y) * row_bytes + i] * k[y];
+            orow[i] = sat_u8(ss >> ORC_PREC_BITS);
         }
-        hsrc = tmp;
     }
-    if (oh != h) {
-        for (int yy = 0; yy < oh; yy++) {
-            int ymin = by[yy * 2], n = by[yy * 2 + 1];
-            const int32_t *k = cy + (size_t)yy * ky;
-            uint8_t *orow = dst + (size_t)yy * ow * c;
-            for (int i = 0; i < ow * c; i++) {
-                int ss = 1 << (ORC_PREC_BITS - 1);
-                for (int y = 0; y < n; y++) ss += hsrc[(size_t)(ymin + y) * ow * c + i] * k[y];
-                orow[i] = sat_u8(ss >> ORC_PREC_BITS);
-            }
-        }
+    free(by); free(cy);
+}
+ORC_API void orc_resize_lanczos_u8(const uint8_t *src, int h, int w, int c, uint8_t *dst, int oh, int ow) {
+    if (ow == w && oh == h) { memcpy(dst, src, (size_t)h * w * c); return; }
+    if (ow == w) { orc_resize_v(src, h, w * c, dst, oh); return; }
+    if (oh == h) { orc_resize_h(src, h, w, c, dst, ow); return; }
+    if (orc_vertical_first(h, w, oh, ow)) {
+        uint8_t *tmp = (uint8_t *)malloc((size_t)oh * w * c);
+        orc_resize_v(src, h, w * c, tmp, oh);
+        orc_resize_h(tmp, oh, w, c, dst, ow);
+        free(tmp);
     } else {
-        memcpy(dst, hsrc, (size_t)oh * ow * c);
+        uint8_t *tmp = (uint8_t *)malloc((size_t)h * ow * c);
+        orc_resize_h(src, h, w, c, tmp, ow);
+        orc_resize_v(tmp, h, ow * c, dst, oh);
+        free(tmp);
     }
-    free(tmp); free(bx); free(cx); free(by); free(cy);
 }
 
 /* ------------------------------------------------------------------------- *

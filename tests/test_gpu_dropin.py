@@ -403,10 +403,18 @@ def test_dropin_equals_the_real_reference_module_on_random_calls(oracle, cuda):
     cv2.setUseOptimized(True)
     try:
         res = sweep(1000, 1016, verbose=False)
+        import sweep_dropin_vs_reference as S
+
+        S.TINY = True          # degenerate sizes (1 x 1 ... ), extreme aspect ratios, target sides that round to 0
+        try:
+            tiny = sweep(2000, 2040, verbose=False)
+        finally:
+            S.TINY = False
     finally:
         cv2.setUseOptimized(was)
     if res is None:
         pytest.skip("oracle/_ref is not in this snapshot (no /root/reference when build() ran)")
     checked, bad = res
     assert checked == 16 * 11 and not bad, bad[:3]
+    assert tiny[0] == 40 * 11 and not tiny[1], tiny[1][:3]
 

@@ -350,6 +350,32 @@ def test_deskew_angle_equals_the_reference_on_pages_where_numpy_and_glibc_disagr
             assert float(angles[i]).hex() == c["angle_hex"], c["seed"]
 
 
+def test_degenerate_shapes_resize_pass_order_median_and_zero_size(oracle, cuda):
+    """What the degenerate-shape sweep against the real reference found (tools/sweep_dropin_vs_reference.py --tiny):
+    Pillow's vertical-first pass order on images taller than 100 x their width, the median on planes narrower than
+    4 bytes, and the ValueError for a target side that rounds to 0."""
+    from test_oracle_pins import TALL
+    from ocr_system_b200 import ops
+
+    for (w, h, tw, th) in TALL:
+        rng = np.random.default_rng(w * 7919 + h)
+        for c in (1, 3):
+            a = rng.integers(0, 256, (2, h, w, 3) if c == 3 else (2, h, w), dtype=np.uint8)
+            got = ops.resize_lanczos(_t(a, cuda), tw, th).cpu().numpy()
+            for i in range(2):
+                assert np.array_equal(got[i], oracle.resize_lanczos(a[i], tw, th)), (w, h, tw, th, c)
+    for (h, w) in [(10, 1), (687, 1), (5, 2), (1, 1), (1, 3), (7, 3), (1, 2000), (2000, 1)]:
+        for c in (1, 3):
+            a = np.random.default_rng(h * 31 + w).integers(0, 256, (3, h, w, 3) if c == 3 else (3, h, w), dtype=np.uint8)
+            got = ops.median3(_t(a, cuda)).cpu().numpy()
+            sharp = ops.contrast_sharpness(_t(a, cuda), 1.2, 1.1).cpu().numpy()
+            for i in range(3):
+                assert np.array_equal(got[i], oracle.median3(a[i])), (h, w, c)
+                assert np.array_equal(sharp[i], oracle.sharpness(oracle.contrast(a[i], 1.2), 1.1)), (h, w, c)
+    with pytest.raises(ValueError, match="height and width must be > 0"):
+        ops.resize_if_needed(_t(np.zeros((1, 1034, 2, 3), np.uint8), cuda), 16)
+
+
 def test_ingest_zero_copy_and_fallback_agree(cuda):
     """PIL pages reach the device the same whether Pillow's storage can be viewed through Arrow (one allocator
     block) or has to go through np.asarray (multi-block image, odd L width)."""

@@ -198,3 +198,22 @@ def test_adaptive_threshold_oracle_under_both_opencv_dispatch_modes(oracle):
         live = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY, 11, 2)
         assert np.array_equal(live, oracle.adaptive_gauss11(g, 2, cv_dispatch=cv2_dispatch())), c["seed"]
 
+
+TALL = [(4, 2212, 3, 2000), (8, 800, 6, 723), (8, 801, 6, 724), (8, 801, 6, 801), (8, 801, 6, 900), (8, 801, 12, 700),
+        (20, 2001, 15, 1000), (20, 2000, 15, 1000), (1, 101, 1, 50), (2, 201, 1, 100), (3000, 8, 2000, 6), (5, 530, 2, 300)]
+
+
+@pytest.mark.parametrize("w,h,tw,th", TALL)
+def test_resize_pass_order_of_very_tall_images_equals_pillow(oracle, w, h, tw, th):
+    """Pillow (12.2.0) runs the vertical pass FIRST when both passes are needed, h > 100 * w and the image shrinks
+    vertically; the uint8 intermediate makes that visible (found by the degenerate-shape sweep of the drop-in against
+    the real reference: 4 x 2212 -> 3 x 2000).  Live Pillow is the reference's own resampler (image_preprocessing.py:110)."""
+    import numpy as np
+    from PIL import Image
+
+    rng = np.random.default_rng(w * 7919 + h)
+    for c in (1, 3):
+        a = rng.integers(0, 256, (h, w, 3) if c == 3 else (h, w), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(a).resize((tw, th), Image.Resampling.LANCZOS))
+        assert np.array_equal(oracle.resize_lanczos(a, tw, th), ref), (w, h, tw, th, c)
+

@@ -23,8 +23,21 @@ from oracle import reference_port as RP
 MODES = ["RGB", "RGB", "RGB", "L", "L", "RGBA", "LA", "P", "1", "CMYK", "YCbCr", "RGBX"]
 
 
+TINY = False   # --tiny: degenerate sizes (1 x 1 ... 24 x 24) and extreme aspect ratios
+
+
 def make_image(rng, seed):
     h, w = int(rng.integers(24, 1400)), int(rng.integers(24, 1400))
+    if TINY:
+        pick = seed % 4
+        if pick == 0:
+            h, w = int(rng.integers(1, 25)), int(rng.integers(1, 25))
+        elif pick == 1:
+            h, w = int(rng.integers(1, 6)), int(rng.integers(200, 3000))
+        elif pick == 2:
+            h, w = int(rng.integers(200, 3000)), int(rng.integers(1, 6))
+        else:
+            h, w = int(rng.integers(8, 40)), int(rng.integers(8, 40))
     kind = seed % 4
     if kind == 0:
         rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
@@ -85,7 +98,7 @@ def sweep(seed_lo: int, seed_hi: int, verbose: bool = True):
     for seed in range(seed_lo, seed_hi):
         rng = np.random.default_rng(seed)
         img = make_image(rng, seed)
-        md = int(rng.choice([128, 300, 600, 960, 2000]))
+        md = int(rng.choice([128, 300, 600, 960, 2000] + ([4, 16, 33] if TINY else [])))
         ref = ref_mod.ImagePreprocessor(max_dimension=md)
         # the live cv2 beside us runs its default dispatch: tell the drop-in to reproduce that one (its default)
         ours = ImagePreprocessor(max_dimension=md)
@@ -132,9 +145,12 @@ def sweep(seed_lo: int, seed_hi: int, verbose: bool = True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, nargs=2, default=[0, 100])
+    ap.add_argument("--tiny", action="store_true")
     a = ap.parse_args()
     import cv2
 
+    global TINY
+    TINY = a.tiny
     t0 = time.time()
     res = sweep(*a.seeds)
     if res is None:
