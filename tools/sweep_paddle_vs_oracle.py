@@ -33,17 +33,24 @@ def blob_map(rng, h, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, nargs=2, default=[0, 40])
+    ap.add_argument("--tiny", action="store_true", help="maps from 1 x 1 to 48 x 48 and thin strips")
     a = ap.parse_args()
     bad, checked, t0 = [], 0, time.time()
     for seed in range(*a.seeds):
         rng = np.random.default_rng(seed)
         # ---- DBPostProcess
         h, w = int(rng.choice([96, 320, 640, 736, 960])), int(rng.choice([128, 352, 800, 960, 1120]))
-        pred = blob_map(rng, h, w) if seed % 3 == 0 else D.synth_prob_map(h, w, seed, n_boxes=int(rng.integers(5, 400)))
+        if a.tiny:
+            h, w = (int(rng.integers(1, 49)), int(rng.integers(1, 49))) if seed % 2 else (int(rng.integers(1, 5)), int(rng.integers(50, 900)))
+            if seed % 4 == 2:
+                h, w = w, h
+            pred = blob_map(rng, max(h, 32), max(w, 32))[:h, :w].copy() if seed % 3 else (rng.random((h, w)) > 0.4).astype(np.float32) * 0.9
+        else:
+            pred = blob_map(rng, h, w) if seed % 3 == 0 else D.synth_prob_map(h, w, seed, n_boxes=int(rng.integers(5, 400)))
         kw = dict(thresh=float(rng.choice([0.2, 0.3, 0.5])), box_thresh=float(rng.choice([0.5, 0.6, 0.7])),
                   unclip_ratio=float(rng.choice([1.5, 1.6, 2.0])), max_candidates=int(rng.choice([50, 1000])),
                   use_dilation=bool(rng.integers(0, 2)), score_mode=str(rng.choice(["fast", "slow"])))
-        dst = (int(h * rng.choice([1.0, 1.5, 0.75])), int(w * rng.choice([1.0, 1.333, 2.0])))
+        dst = (max(1, int(h * rng.choice([1.0, 1.5, 0.75]))), max(1, int(w * rng.choice([1.0, 1.333, 2.0]))))
         sl = [(dst[0], dst[1], h / dst[0], w / dst[1])]
         ref = D.DBPostProcess(**kw)({"maps": pred[None, None]}, sl, with_scores=True)[0]
         got = DBPostProcess(**kw)({"maps": pred[None, None]}, sl, with_scores=True)[0]
