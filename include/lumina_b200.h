@@ -142,6 +142,9 @@ int lumina_ppht_prepare(const uint8_t *d_edges, int n, int h, int w, double rho,
 int lumina_ppht_lines(const uint8_t *d_edges, int n, int h, int w, double rho, double theta, int threshold,
                       int min_line_length, int max_line_gap, int32_t *d_lines, int32_t *d_nlines, int max_lines,
                       void *d_workspace, size_t workspace_bytes, void *stream);
+/* the first `lines` (<= max_lines) segments of every page of d_lines [n][max_lines][4] -> h_lines [n][lines][4]
+ * (pinned host memory), one strided copy on `stream` */
+int lumina_copy_lines_to_host(const int32_t *d_lines, int n, int max_lines, int lines, int32_t *h_lines, void *stream);
 /* (iv)+(v) host: per-line degrees(arctan2) folded to +-45, np.median, with glibc's atan2.  nlines==0 -> 0.0.
  * numpy's arctan2 is glibc's only where numpy does not dispatch to its bundled SIMD math (AVX-512 builds: the last
  * place differs for ~0.3 % of (dy, dx) pairs); a host that has numpy computes the per-line angles with it and calls

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "lumina_ppht_prepare": (_I, [_P, _I, _I, _I, _D, _D, _P, _Z, _P]),
     "lumina_ppht_lines": (_I, [_P, _I, _I, _I, _D, _D, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "lumina_median_angle_host": (_D, [_P, _I]),
+    "lumina_copy_lines_to_host": (_I, [_P, _I, _I, _I, _P, _P]),
     "lumina_deskew_decide_host": (None, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "lumina_deskew_decide_angles_host": (None, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "lumina_rotation_matrix_host": (None, [_D, _D, _D, _D, _P]),

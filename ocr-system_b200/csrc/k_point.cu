@@ -229,9 +229,20 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(const uint8_t *__re
 
 using namespace lumina;
 
-LUMINA_API int lumina_abi_version(void) { return 4; }  // 3: round 2 (JPEG decode, db_postprocess_ex, Otsu / Sauvola, skew estimate); 4: stream-ordered deskew decision
+LUMINA_API int lumina_abi_version(void) { return 4; }  // 3: round 2 (JPEG decode, db_postprocess_ex, Otsu / Sauvola, skew estimate); 4: deskew decision from caller-computed angles, adaptive threshold dispatch modes, line-list copy
 LUMINA_API const char *lumina_last_error_string(void) { return g_err; }
 LUMINA_API uint64_t lumina_launch_count(void) { return g_launches.load(); }
+
+// The first `lines` segments of every page of a HoughLinesP result [n][stride][4] int32 to (pinned) host memory
+// [n][lines][4]: one strided copy on the stream (cudaMemcpy2DAsync), so that the few hundred segments a text page
+// yields travel instead of the whole max_lines capacity -- and no library kernel packs them first.
+LUMINA_API int lumina_copy_lines_to_host(const int32_t *d_lines, int n, int stride, int lines, int32_t *h_lines, void *stream) {
+    LUMINA_REQUIRE(d_lines && h_lines, "null pointer");
+    LUMINA_REQUIRE(n > 0 && stride > 0 && lines > 0 && lines <= stride, "bad line-list shape");
+    LUMINA_CUDA_TRY(cudaMemcpy2DAsync(h_lines, (size_t)lines * 16, d_lines, (size_t)stride * 16, (size_t)lines * 16, (size_t)n,
+                                      cudaMemcpyDeviceToHost, as_stream(stream)));
+    return LUMINA_OK;
+}
 
 LUMINA_API void lumina_target_size(int width, int height, int max_dim, int *out_w, int *out_h) {
     // image_preprocessing.py:94-105 -- python float division then int() truncation

@@ -368,6 +368,16 @@ def rgbx_to_rgb(pages_rgbx: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def copy_lines_to_host(lines: torch.Tensor, keep: int, out_pinned: torch.Tensor) -> None:
+    """The first ``keep`` segments of every page of a Hough result [N,max_lines,4] into the front of a pinned int32
+    buffer (viewed as [N,keep,4] by the caller) -- one strided copy on the current stream of the lists' device."""
+    n, stride = int(lines.shape[0]), int(lines.shape[1])
+    if not lines.is_contiguous() or lines.dtype != torch.int32 or out_pinned.numel() < n * keep * 4:
+        raise ValueError("copy_lines_to_host: contiguous int32 [N,max_lines,4] and a large enough pinned buffer expected")
+    with torch.cuda.device(lines.device):
+        _chk(_L().lumina_copy_lines_to_host(_ptr(lines), n, stride, int(keep), out_pinned.data_ptr(), _stream()))
+
+
 def line_angles(lines_host: np.ndarray) -> np.ndarray:
     """image_preprocessing.py:421-426 for an array of segments [...,4]: ``np.degrees(np.arctan2(y2 - y1, x2 - x1))``
     folded to +-45 -- evaluated BY NUMPY, on int32 operands like the reference's scalars.  numpy's arctan2 is not

@@ -269,9 +269,9 @@ class PagePipeline:
         elif keep == 0:
             lh = ln_pin.numpy()[:, :1]
         else:
-            ln_pin[:, :keep].copy_(lines[:, :keep], non_blocking=True)
+            ops.copy_lines_to_host(lines, keep, ln_pin)       # [n][keep][4] packed at the front of the pinned buffer
             cur.synchronize()
-            lh = ln_pin.numpy()[:, :keep]
+            lh = ln_pin.numpy().reshape(-1)[: n * keep * 4].reshape(n, keep, 4)
         angles, mats, apply = ops.deskew_decide(lh, nl, h, w)
         if apply.any():
             x = ops.warp_affine_cubic(x, mats, apply)
