@@ -18,6 +18,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference/backend")
 
 
+A4 = False
+
+
 def one(seed: int):
     import cv2
     import numpy as np
@@ -32,6 +35,8 @@ def one(seed: int):
     h, w = int(rng.integers(300, 1300)), int(rng.integers(300, 1300))
     md = int(rng.choice([256, 400, 600, 960, 2000]))
     kind = seed % 4
+    if A4:                                        # the headline geometry: A4 at 300 dpi through max_dimension 960 / 2000
+        h, w, md, kind = 3508, 2480, (960 if seed & 2 else 2000), 0
     if kind == 3:
         rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
     elif kind == 2:
@@ -69,7 +74,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, nargs=2, default=[0, 64])
     ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--a4", action="store_true", help="full-size A4 300-dpi pages through max_dimension 960 / 2000")
     a = ap.parse_args()
+    global A4
+    A4 = a.a4
     with mp.get_context("fork").Pool(a.procs) as pool:
         n_bad = 0
         for i, bad in enumerate(pool.imap_unordered(one, range(*a.seeds), chunksize=1)):
