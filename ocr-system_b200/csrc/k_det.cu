@@ -18,7 +18,7 @@
 namespace lumina {
 
 struct DetNorm { float mean[3], stdv[3], scale; };
-constexpr int DT_W = 128, DT_H = 32;
+constexpr int DT_W = 64, DT_H = 32, DT_PX = 2;   // 2 pixels per thread per step: 40 registers, twice the resident warps of the 4-pixel form
 
 __global__ void __launch_bounds__(256) det_resize_normalize_kernel(const uint8_t *__restrict__ src, float *__restrict__ dst,
                                                                    int h, int w, int oh, int ow, double sx, double sy,
@@ -57,13 +57,13 @@ __global__ void __launch_bounds__(256) det_resize_normalize_kernel(const uint8_t
     const uint8_t *s = src + (size_t)page * h * w * 3;
     const size_t plane = (size_t)oh * ow;
     float *o_page = dst + (size_t)page * 3 * plane;
-    const int q = tid & 31, tx = q * 4;          // 4 consecutive columns
+    const int q = tid & 31, tx = q * DT_PX;      // DT_PX consecutive columns
     const int x = bx0 + tx;
     if (x >= ow) return;
-    const bool vec = (ow & 3) == 0 && x + 4 <= ow && ((((uintptr_t)dst) & 15) == 0);
-    int xo0[4], xo1[4], a0[4], a1[4];
+    const bool vec = (ow & 1) == 0 && x + DT_PX <= ow && ((((uintptr_t)dst) & 7) == 0);
+    int xo0[DT_PX], xo1[DT_PX], a0[DT_PX], a1[DT_PX];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
+    for (int e = 0; e < DT_PX; e++) {
         const int2 t = xtab[tx + e];
         xo0[e] = t.x; xo1[e] = xoff1[tx + e];
         a0[e] = t.y & 0xffff; a1[e] = t.y >> 16;
@@ -73,9 +73,9 @@ __global__ void __launch_bounds__(256) det_resize_normalize_kernel(const uint8_t
         if (y >= oh) break;
         const int4 yt = ytab[ty];
         const uint8_t *r0 = s + (size_t)yt.x * w * 3, *r1 = s + (size_t)yt.y * w * 3;
-        float out[3][4];
+        float out[3][DT_PX];
 #pragma unroll
-        for (int e = 0; e < 4; e++)
+        for (int e = 0; e < DT_PX; e++)
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
                 const int S0 = (int)__ldg(r0 + xo0[e] + ch) * a0[e] + (int)__ldg(r0 + xo1[e] + ch) * a1[e];
@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(256) det_resize_normalize_kernel(const uint8_t
         float *o = o_page + (size_t)y * ow + x;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            if (vec) *reinterpret_cast<float4 *>(o + ch * plane) = make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]);
+            if (vec) *reinterpret_cast<float2 *>(o + ch * plane) = make_float2(out[ch][0], out[ch][1]);
             else {
 #pragma unroll
-                for (int e = 0; e < 4; e++)
+                for (int e = 0; e < DT_PX; e++)
                     if (x + e < ow) o[ch * plane + e] = out[ch][e];
             }
         }
