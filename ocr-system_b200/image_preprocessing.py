@@ -181,8 +181,8 @@ class ImagePreprocessor:
             return self._to_device(image)
         if image.mode == "YCbCr":                      # Pillow: YCbCr -> L is the Y band
             return self._to_device(image.getchannel(0))
-        # every other mode: convert('L') == convert('RGB').convert('L') (same L24 weights; verified per mode in
-        # tests/test_gpu_modes.py), so the mode change is Pillow's and the grayscale is the kernel's
+        # every other mode: convert('L') == convert('RGB').convert('L') (same L24 weights; pinned per mode by
+        # tests/test_abi_and_host.py::test_gray_source_rule_holds_for_every_pil_mode), so the mode change is Pillow's and the grayscale is the kernel's
         return self._to_device(image.convert("RGB"))
 
     @staticmethod

@@ -388,6 +388,9 @@ class PagePipeline:
                 if dev_buf[k] is None or dev_buf[k].shape != hb.shape:
                     dev_buf[k] = torch.empty(hb.shape, dtype=torch.uint8, device=dev)
                     free[k] = None
+                    # a fresh slot comes from the compute stream's allocator pool: the block may belong to a tensor
+                    # whose last kernels are still queued there, so the first upload into it is ordered behind them
+                    copy_stream.wait_stream(comp)
                 with torch.cuda.stream(copy_stream):
                     if free[k] is not None:
                         copy_stream.wait_event(free[k])

@@ -122,3 +122,30 @@ def test_ctc_dictionary_handling(abi, tmp_path):
     dec = CTCLabelDecode(str(d), use_space_char=True)
     assert dec.character == ["blank", "a", "b", "क", " "]
     assert len(CTCLabelDecode().character) == 37
+
+
+def test_gray_source_rule_holds_for_every_pil_mode():
+    """``ImagePreprocessor._gray_source`` (the input of convert_to_grayscale / binarize / adaptive_binarize / deskew for
+    PIL objects that are neither RGB nor L) rests on two Pillow facts: ``convert('L')`` of a YCbCr image is its Y band,
+    and for every other mode ``convert('L') == convert('RGB').convert('L')``.  Pin both against the Pillow in this image
+    so that a Pillow upgrade that breaks the rule fails here, not as a silent pixel difference on the GPU box."""
+    from PIL import Image
+
+    rng = np.random.default_rng(7)
+    rgb = Image.fromarray(rng.integers(0, 256, (37, 53, 3), dtype=np.uint8))
+    rgba = Image.fromarray(rng.integers(0, 256, (37, 53, 4), dtype=np.uint8), "RGBA")
+    pal_t = rgb.convert("P")
+    pal_t.info["transparency"] = 3
+    images = [rgba, rgba.convert("LA"), rgb.convert("RGBX"), rgb.convert("CMYK"), rgb.convert("HSV"), rgb.convert("P"), pal_t,
+              rgb.convert("1"), rgba.convert("RGBa"),
+              Image.fromarray(rng.integers(-500, 1000, (37, 53)).astype(np.int32), "I"),
+              Image.fromarray((rng.random((37, 53)) * 400 - 50).astype(np.float32), "F"),
+              Image.fromarray(rng.integers(0, 65536, (37, 53)).astype(np.uint16))]
+    for im in images:
+        assert np.array_equal(np.asarray(im.convert("L")), np.asarray(im.convert("RGB").convert("L"))), im.mode
+    ycc = rgb.convert("YCbCr")
+    assert np.array_equal(np.asarray(ycc.convert("L")), np.asarray(ycc.getchannel(0)))
+    la_pre = rgba.convert("La")            # Pillow refuses La -> L and La -> RGB alike: the drop-in raises the same error type
+    for target in ("L", "RGB"):
+        with pytest.raises(ValueError):
+            la_pre.convert(target)
