@@ -110,7 +110,41 @@ class CTCLabelDecode:
         """Device part only: (idx[N,T], pos[N,T], len[N], conf[N]) CUDA tensors."""
         return ops.ctc_greedy(_to_cuda(preds, torch.float32))
 
-    def __call__(self, preds, label=None, *args, **kwargs) -> List[Tuple[str, float]]:
+    _LATIN = frozenset("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789 :*./%+-")
+
+    @classmethod
+    def pred_reverse(cls, symbols: Sequence[str]) -> str:
+        """upstream BaseRecLabelDecode.pred_reverse (right-to-left dictionaries): the order of the decoded symbols is
+        reversed, but a run of Latin letters / digits / `` :*./%+-`` keeps its own left-to-right order."""
+        parts: List[str] = []
+        run = ""
+        for c in symbols:
+            if any(ch in cls._LATIN for ch in c):
+                run += c
+            else:
+                if run:
+                    parts.append(run)
+                parts.append(c)
+                run = ""
+        if run:
+            parts.append(run)
+        return "".join(reversed(parts))
+
+    def _text(self, symbols: Sequence[str]) -> str:
+        return self.pred_reverse(symbols) if self.reverse else "".join(symbols)
+
+    def decode_label(self, label) -> List[Tuple[str, float]]:
+        """upstream ``decode(label)`` (no duplicate removal): drop the blank class, map the rest; the confidence of a
+        ground-truth string is 1.0 (0.0 for an empty one: upstream's ``conf_list = [0]`` before ``np.mean``)."""
+        out = []
+        for row in np.asarray(label):
+            symbols = [self.character[int(k)] for k in row if int(k) != 0]
+            out.append((self._text(symbols), 1.0 if symbols else 0.0))
+        return out
+
+    def __call__(self, preds, label=None, *args, **kwargs):
+        """-> [(text, conf)]; with ``label`` (int [N,L], 0 = blank / padding) -> ([(text, conf)], [(label_text, 1.0)])
+        like upstream."""
         if isinstance(preds, (tuple, list)):
             preds = preds[-1]
         n_cls = preds.shape[2]
@@ -119,10 +153,7 @@ class CTCLabelDecode:
         idx, _pos, ln, conf = self.decode_indices(preds)
         idx, ln, conf = idx.cpu().numpy(), ln.cpu().numpy(), conf.cpu().numpy()
         chars = self.character
-        out = []
-        for b in range(idx.shape[0]):
-            text = "".join(chars[k] for k in idx[b, : ln[b]])
-            if self.reverse:
-                text = text[::-1]
-            out.append((text, float(conf[b])))
-        return out
+        out = [(self._text([chars[k] for k in idx[b, : ln[b]]]), float(conf[b])) for b in range(idx.shape[0])]
+        if label is None:
+            return out
+        return out, self.decode_label(label)

@@ -149,3 +149,41 @@ def test_gray_source_rule_holds_for_every_pil_mode():
     for target in ("L", "RGB"):
         with pytest.raises(ValueError):
             la_pre.convert(target)
+
+
+def test_ctc_right_to_left_and_label_decode(abi, tmp_path):
+    """Host half of CTCLabelDecode: upstream's pred_reverse for right-to-left dictionaries (Latin / digit runs keep
+    their order) and ``decode(label)`` for the ground-truth strings; checked against a literal restatement of upstream's
+    regex loop (ppocr/postprocess/rec_postprocess.py, BaseRecLabelDecode.pred_reverse)."""
+    import re
+
+    from ocr_system_b200.paddle_ops import CTCLabelDecode
+
+    def upstream_pred_reverse(pred):
+        pred_re, cur = [], ""
+        for c in pred:
+            if not bool(re.search("[a-zA-Z0-9 :*./%+-]", c)):
+                if cur != "":
+                    pred_re.append(cur)
+                pred_re.append(c)
+                cur = ""
+            else:
+                cur += c
+        if cur != "":
+            pred_re.append(cur)
+        return "".join(pred_re[::-1])
+
+    d = tmp_path / "arabic_dict.txt"
+    alphabet = list("ابتثجحخ") + list("abXY019") + list(" :*./%+-") + ["،", "ـ"]
+    d.write_text("\n".join(alphabet) + "\n", encoding="utf-8")
+    dec = CTCLabelDecode(str(d))
+    assert dec.reverse and not CTCLabelDecode(character=alphabet).reverse
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        symbols = [alphabet[k] for k in rng.integers(0, len(alphabet), int(rng.integers(0, 24)))]
+        assert dec.pred_reverse(symbols) == upstream_pred_reverse(symbols)
+    assert dec.pred_reverse(list("اب12 ab.ت")) == "ت12 ab.با"
+    label = np.array([[1, 2, 0, 8, 9, 0], [0, 0, 0, 0, 0, 0]])
+    assert dec.decode_label(label) == [(upstream_pred_reverse([dec.character[k] for k in (1, 2, 8, 9)]), 1.0), ("", 0.0)]
+    plain = CTCLabelDecode(character=list("abc"))
+    assert plain.decode_label([[1, 1, 0, 3]]) == [("aac", 1.0)]
