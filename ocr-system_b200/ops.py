@@ -8,6 +8,8 @@ non-CUDA tensor is an error.
 """
 from __future__ import annotations
 
+import collections
+import contextlib
 import ctypes as C
 import functools
 import os
@@ -95,22 +97,58 @@ def target_size(width: int, height: int, max_dim: int) -> Tuple[int, int]:
 
 
 class _ResizePlans:
-    """Device coefficient tables per (device, in, out) geometry; created once."""
+    """Device coefficient tables per (device, in, out) geometry, created on first use and kept in a bounded LRU: a
+    long-lived service sees arbitrary scan sizes, and every geometry holds a few hundred KB of device tables.  A plan
+    is only evicted while no caller is between ``use().__enter__`` and the end of its launch call; kernels that were
+    launched with it and are still running are covered by ``lumina_resize_plan_destroy`` itself (its ``cudaFree``s wait
+    for the device).  ``LUMINA_RESIZE_PLAN_CACHE`` sets the bound (default 256 geometries)."""
 
-    def __init__(self):
-        self._plans = {}
+    def __init__(self, capacity: Optional[int] = None, create=None, destroy=None):
+        self._plans = collections.OrderedDict()      # key -> [handle, callers inside use()]
         self._lock = threading.Lock()
+        self.capacity = max(1, int(capacity if capacity is not None else os.environ.get("LUMINA_RESIZE_PLAN_CACHE", "256")))
+        self._create = create or self._create_native
+        self._destroy = destroy or self._destroy_native
 
-    def get(self, dev: int, in_h: int, in_w: int, out_h: int, out_w: int) -> C.c_void_p:
+    @staticmethod
+    def _create_native(dev, in_h, in_w, out_h, out_w):
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _chk(_L().lumina_resize_plan_create(in_h, in_w, out_h, out_w, C.byref(h)))
+        return h
+
+    @staticmethod
+    def _destroy_native(dev, handle):
+        with torch.cuda.device(dev):
+            _L().lumina_resize_plan_destroy(handle)
+
+    @contextlib.contextmanager
+    def use(self, dev: int, in_h: int, in_w: int, out_h: int, out_w: int):
         key = (dev, in_h, in_w, out_h, out_w)
         with self._lock:
-            p = self._plans.get(key)
-            if p is None:
-                h = C.c_void_p()
-                with torch.cuda.device(dev):
-                    _chk(_L().lumina_resize_plan_create(in_h, in_w, out_h, out_w, C.byref(h)))
-                p = self._plans[key] = h
-            return p
+            ent = self._plans.get(key)
+            if ent is None:
+                ent = self._plans[key] = [self._create(*key), 0]
+            self._plans.move_to_end(key)
+            ent[1] += 1
+            victims = []
+            if len(self._plans) > self.capacity:
+                for k in list(self._plans):
+                    if len(self._plans) - len(victims) <= self.capacity:
+                        break
+                    if self._plans[k][1] == 0:
+                        victims.append(k)
+                victims = [(k, self._plans.pop(k)[0]) for k in victims]
+        try:
+            for k, h in victims:       # outside the lock: destroy waits for the device
+                self._destroy(k[0], h)
+            yield ent[0]
+        finally:
+            with self._lock:
+                ent[1] -= 1
+
+    def __len__(self) -> int:
+        return len(self._plans)
 
 
 _plans = _ResizePlans()
@@ -121,11 +159,11 @@ def resize_lanczos(pages: torch.Tensor, out_w: int, out_h: int) -> torch.Tensor:
     """PIL Image.resize((out_w,out_h), LANCZOS) (image_preprocessing.py:110), byte-exact."""
     sq = pages.dim() == 3
     x, n, h, w, c = _pages(pages)
-    plan = _plans.get(x.device.index, h, w, out_h, out_w)
     out = torch.empty((n, out_h, out_w, c), dtype=torch.uint8, device=x.device)
-    wsb = int(_L().lumina_resize_workspace_bytes(plan, n, c))
-    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=x.device) if wsb else None
-    _chk(_L().lumina_resize_lanczos_u8(plan, _ptr(x), _ptr(out), n, c, _ptr(ws), wsb, _stream()))
+    with _plans.use(x.device.index, h, w, out_h, out_w) as plan:
+        wsb = int(_L().lumina_resize_workspace_bytes(plan, n, c))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=x.device) if wsb else None
+        _chk(_L().lumina_resize_lanczos_u8(plan, _ptr(x), _ptr(out), n, c, _ptr(ws), wsb, _stream()))
     return _like(out, sq)
 
 

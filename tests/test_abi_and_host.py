@@ -1,6 +1,7 @@
 """CPU-side checks: the C-ABI library loads and exports every symbol include/lumina_b200.h
 declares (no compute calls), host-only entry points agree with the oracle / reference rules,
 the product path never touches oracle/, and the drop-in keeps the reference's error behaviour."""
+import collections
 import ctypes as C
 import os
 import re
@@ -187,3 +188,63 @@ def test_ctc_right_to_left_and_label_decode(abi, tmp_path):
     assert dec.decode_label(label) == [(upstream_pred_reverse([dec.character[k] for k in (1, 2, 8, 9)]), 1.0), ("", 0.0)]
     plain = CTCLabelDecode(character=list("abc"))
     assert plain.decode_label([[1, 1, 0, 3]]) == [("aac", 1.0)]
+
+
+def test_resize_plan_cache_is_a_bounded_lru_that_never_evicts_a_plan_in_use(abi):
+    """ops._ResizePlans: device coefficient tables per geometry are kept in a bounded LRU (a service sees arbitrary scan
+    sizes); a plan that a caller is launching with is never destroyed.  Host logic only: create / destroy are injected."""
+    import threading
+
+    from ocr_system_b200 import ops
+
+    created, destroyed = [], []
+    cache = ops._ResizePlans(capacity=3, create=lambda *k: created.append(k) or ("plan", k),
+                             destroy=lambda dev, h: destroyed.append(h[1]))
+    geo = [(0, 100 + i, 200, 50, 100) for i in range(6)]
+    for g in geo[:3]:
+        with cache.use(*g) as h:
+            assert h == ("plan", g)
+    with cache.use(*geo[0]):                       # refresh geo[0]: geo[1] is now the oldest
+        pass
+    assert created == geo[:3] and destroyed == [] and len(cache) == 3
+    with cache.use(*geo[3]):
+        assert destroyed == [geo[1]] and len(cache) == 3
+    with cache.use(*geo[0]) as h0:                 # geo[0] is held while two more geometries arrive
+        with cache.use(*geo[4]):
+            with cache.use(*geo[5]):
+                assert geo[0] not in destroyed and h0 == ("plan", geo[0])
+    assert set(destroyed) == {geo[1], geo[2], geo[3]} and len(cache) == 3
+    assert created.count(geo[0]) == 1
+    # every plan in use: the cache may exceed its bound rather than free tables under a running launch
+    tight = ops._ResizePlans(capacity=1, create=lambda *k: k, destroy=lambda dev, h: destroyed.append(("tight", h)))
+    with tight.use(*geo[0]):
+        with tight.use(*geo[1]):
+            assert len(tight) == 2 and not any(d[0] == "tight" for d in destroyed if isinstance(d[0], str))
+    with tight.use(*geo[2]):
+        pass
+    assert len(tight) == 1
+    # threads hammering a small cache: a handle is never destroyed between __enter__ and __exit__ of its user
+    live, errors = collections.Counter(), []
+    lock = threading.Lock()
+
+    def destroy(dev, h):
+        with lock:
+            if live[h] > 0:
+                errors.append(h)
+
+    shared = ops._ResizePlans(capacity=2, create=lambda *k: k, destroy=destroy)
+
+    def worker(seed):
+        rng = np.random.default_rng(seed)
+        for _ in range(400):
+            g = geo[int(rng.integers(0, 6))]
+            with shared.use(*g) as h:
+                with lock:
+                    live[h] += 1
+                with lock:
+                    live[h] -= 1
+
+    ts = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors and len(shared) <= 2 + 4
