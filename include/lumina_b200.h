@@ -179,6 +179,9 @@ int lumina_skew_estimate_fast(const uint8_t *d_edges, int n, int h, int w, doubl
 
 /* ---- a15 [upstream PaddleOCR] DetResizeForTest + NormalizeImage + ToCHW - */
 void lumina_det_target_size(int h, int w, int limit_side_len, int *out_h, int *out_w);
+/* upstream's other limit types (resize_image_type0): limit_type 0 = "max" (the entry above), 1 = "min" (enlarge
+ * when the shorter side is below the limit), 2 = "resize_long".  Host only. */
+int lumina_det_target_size_ex(int h, int w, int limit_side_len, int limit_type, int *out_h, int *out_w);
 /* src [n][h][w][3] u8 -> dst [n][3][oh][ow] f32; cv2.resize INTER_LINEAR
  * (11-bit fixed point) then (x*scale - mean[c]) / std[c]. */
 int lumina_det_resize_normalize(const uint8_t *d_src, float *d_dst, int n, int h, int w, int oh, int ow,

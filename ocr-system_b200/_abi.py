@@ -61,6 +61,7 @@ PROTOTYPES = {
     "lumina_warp_affine_cubic_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "lumina_invert_affine_host": (None, [_P, _P]),
     "lumina_det_target_size": (None, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
+    "lumina_det_target_size_ex": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "lumina_skew_workspace_bytes_for": (_Z, [_I, _I, _I]),
     "lumina_skew_estimate_fast": (_I, [_P, _I, _I, _I, _P, _P, _Z, _P]),
     "lumina_otsu_u8": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

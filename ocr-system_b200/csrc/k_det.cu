@@ -101,15 +101,29 @@ __global__ void __launch_bounds__(256) det_resize_normalize_kernel(const uint8_t
 
 using namespace lumina;
 
-LUMINA_API void lumina_det_target_size(int h, int w, int limit, int *out_h, int *out_w) {
+// upstream DetResizeForTest.resize_image_type0: the three limit types differ only in the ratio
+//   "max" (0): shrink when the longer side exceeds the limit      "min" (1): enlarge when the shorter side is below it
+//   "resize_long" (2): the longer side always becomes the limit
+// then int(h * ratio), int(w * ratio), each rounded to a multiple of 32 (python round(): half to even), at least 32.
+LUMINA_API int lumina_det_target_size_ex(int h, int w, int limit, int limit_type, int *out_h, int *out_w) {
+    LUMINA_REQUIRE(out_h && out_w, "null pointer");
+    LUMINA_REQUIRE(h > 0 && w > 0 && limit > 0, "empty image or limit");
+    LUMINA_REQUIRE(limit_type >= 0 && limit_type <= 2, "limit_type must be 0 (max), 1 (min) or 2 (resize_long)");
     double ratio = 1.0;
-    const int mx = h > w ? h : w;
-    if (mx > limit) ratio = (double)limit / mx;
+    const int mx = h > w ? h : w, mn = h < w ? h : w;
+    if (limit_type == 0) { if (mx > limit) ratio = (double)limit / mx; }
+    else if (limit_type == 1) { if (mn < limit) ratio = (double)limit / mn; }
+    else ratio = (double)limit / mx;
     int a = (int)(h * ratio), b = (int)(w * ratio);
     a = (int)(lrint(a / 32.0) * 32);  // python round(): half to even
     b = (int)(lrint(b / 32.0) * 32);
     *out_h = a < 32 ? 32 : a;
     *out_w = b < 32 ? 32 : b;
+    return LUMINA_OK;
+}
+
+LUMINA_API void lumina_det_target_size(int h, int w, int limit, int *out_h, int *out_w) {
+    if (lumina_det_target_size_ex(h, w, limit, 0, out_h, out_w) != LUMINA_OK && out_h && out_w) *out_h = *out_w = 32;
 }
 
 LUMINA_API int lumina_det_resize_normalize(const uint8_t *d_src, float *d_dst, int n, int h, int w, int oh, int ow,

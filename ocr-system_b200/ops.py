@@ -561,20 +561,28 @@ DET_MEAN = (0.485, 0.456, 0.406)
 DET_STD = (0.229, 0.224, 0.225)
 
 
-def det_target_size(h: int, w: int, limit_side_len: int = 960) -> Tuple[int, int]:
+DET_LIMIT_TYPES = {"max": 0, "min": 1, "resize_long": 2}
+
+
+def det_target_size(h: int, w: int, limit_side_len: int = 960, limit_type: str = "max") -> Tuple[int, int]:
+    """upstream DetResizeForTest.resize_image_type0: (resize_h, resize_w), multiples of 32."""
+    if limit_type not in DET_LIMIT_TYPES:
+        raise ValueError(f"limit_type must be one of {sorted(DET_LIMIT_TYPES)}, got {limit_type!r}")
     oh, ow = C.c_int(), C.c_int()
-    _L().lumina_det_target_size(h, w, limit_side_len, C.byref(oh), C.byref(ow))
+    _chk(_L().lumina_det_target_size_ex(int(h), int(w), int(limit_side_len), DET_LIMIT_TYPES[limit_type], C.byref(oh), C.byref(ow)))
     return oh.value, ow.value
 
 
 @_on_tensor_device
 def det_resize_normalize(pages: torch.Tensor, limit_side_len: int = 960, mean=DET_MEAN, std=DET_STD,
-                         scale: float = 1.0 / 255.0):
-    """PaddleOCR DetResizeForTest('max') + NormalizeImage + ToCHWImage -> ([N,3,oh,ow] f32, shape_list)."""
+                         scale: float = 1.0 / 255.0, limit_type: str = "max"):
+    """PaddleOCR DetResizeForTest(limit_side_len, limit_type) + NormalizeImage + ToCHWImage -> ([N,3,oh,ow] f32,
+    shape_list).  ``limit_type``: "max" (inference default), "min" or "resize_long" (may enlarge: the same
+    cv2.resize(INTER_LINEAR) arithmetic, which does not depend on the direction)."""
     x, n, h, w, c = _pages(pages)
     if c != 3:
         raise ValueError("det preprocess expects RGB/BGR pages")
-    oh, ow = det_target_size(h, w, limit_side_len)
+    oh, ow = det_target_size(h, w, limit_side_len, limit_type)
     out = torch.empty((n, 3, oh, ow), dtype=torch.float32, device=x.device)
     m = np.asarray(mean, np.float32)
     s = np.asarray(std, np.float32)

@@ -5,7 +5,7 @@ ops BASELINE.json's north_star names, restated from upstream PaddleOCR
 (ppocr/postprocess/{db_postprocess,rec_postprocess}.py, ppocr/data/imaug/operators.py)
 -- parity unpinned by the reference; pinned by the restated oracle + cv2.
 
-  DetResizeNormalize  DetResizeForTest(limit_side_len, 'max') + NormalizeImage + ToCHWImage
+  DetResizeNormalize  DetResizeForTest(limit_side_len, limit_type) + NormalizeImage + ToCHWImage
   DBPostProcess       (outs_dict{"maps": [N,1,H,W]}, shape_list) -> [{"points": int32[K,4,2]}]
   CTCLabelDecode      (preds[N,T,C]) -> [(text, conf)]
 """
@@ -30,13 +30,18 @@ def _to_cuda(x, dtype) -> torch.Tensor:
 
 
 class DetResizeNormalize:
-    def __init__(self, limit_side_len: int = 960, mean=ops.DET_MEAN, std=ops.DET_STD, scale: float = 1.0 / 255.0):
+    def __init__(self, limit_side_len: int = 960, mean=ops.DET_MEAN, std=ops.DET_STD, scale: float = 1.0 / 255.0,
+                 limit_type: str = "max"):
+        """``limit_type``: upstream's "max" (PaddleOCR's inference default, det_limit_type), "min" or "resize_long"."""
+        if limit_type not in ops.DET_LIMIT_TYPES:
+            raise ValueError(f"limit_type must be one of {sorted(ops.DET_LIMIT_TYPES)}, got {limit_type!r}")
         self.limit_side_len, self.mean, self.std, self.scale = limit_side_len, mean, std, scale
+        self.limit_type = limit_type
 
     def __call__(self, pages) -> Tuple[torch.Tensor, np.ndarray]:
         """pages: uint8 [N,H,W,3] (ndarray or tensor) -> (CUDA f32 [N,3,oh,ow], shape_list [N,4])."""
         return ops.det_resize_normalize(_to_cuda(pages, torch.uint8), self.limit_side_len, self.mean, self.std,
-                                        self.scale)
+                                        self.scale, self.limit_type)
 
 
 class DBPostProcess:

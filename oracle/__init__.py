@@ -262,10 +262,36 @@ DET_MEAN = np.array([0.485, 0.456, 0.406], np.float32)
 DET_STD = np.array([0.229, 0.224, 0.225], np.float32)
 
 
-def det_target_size(h: int, w: int, limit: int = 960):
+def det_target_size(h: int, w: int, limit: int = 960, limit_type: str = "max"):
+    if limit_type != "max":
+        return det_target_size_upstream(h, w, limit, limit_type)
     rh, rw = C.c_int(), C.c_int()
     lib().orc_det_target_size(h, w, limit, C.byref(rh), C.byref(rw))
     return rh.value, rw.value
+
+
+def det_target_size_upstream(h: int, w: int, limit_side_len: int = 960, limit_type: str = "max"):
+    """[upstream PaddleOCR, from memory; parity unpinned] ppocr/data/imaug/operators.py DetResizeForTest.resize_image_type0,
+    the size arithmetic only, statement for statement (python floats, python round)."""
+    if limit_type == "max":
+        if max(h, w) > limit_side_len:
+            ratio = float(limit_side_len) / h if h > w else float(limit_side_len) / w
+        else:
+            ratio = 1.0
+    elif limit_type == "min":
+        if min(h, w) < limit_side_len:
+            ratio = float(limit_side_len) / h if h < w else float(limit_side_len) / w
+        else:
+            ratio = 1.0
+    elif limit_type == "resize_long":
+        ratio = float(limit_side_len) / max(h, w)
+    else:
+        raise Exception("not support limit type, image ")
+    resize_h = int(h * ratio)
+    resize_w = int(w * ratio)
+    resize_h = max(int(round(resize_h / 32) * 32), 32)
+    resize_w = max(int(round(resize_w / 32) * 32), 32)
+    return resize_h, resize_w
 
 
 def resize_linear(img, out_w: int, out_h: int):
@@ -275,10 +301,10 @@ def resize_linear(img, out_w: int, out_h: int):
     return out
 
 
-def det_resize_normalize(img, limit: int = 960):
+def det_resize_normalize(img, limit: int = 960, limit_type: str = "max"):
     img = _u8(img)
     h, w = img.shape[:2]
-    rh, rw = det_target_size(h, w, limit)
+    rh, rw = det_target_size(h, w, limit, limit_type)
     r = resize_linear(img, rw, rh)
     out = np.empty((3, rh, rw), np.float32)
     lib().orc_normalize_chw(_p(r), rh, rw, _p(DET_MEAN), _p(DET_STD), C.c_float(np.float32(1.0 / 255.0)), _p(out))

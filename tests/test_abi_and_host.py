@@ -248,3 +248,30 @@ def test_resize_plan_cache_is_a_bounded_lru_that_never_evicts_a_plan_in_use(abi)
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errors and len(shared) <= 2 + 4
+
+
+def test_det_target_size_limit_types_match_upstream_rule(abi, oracle):
+    """lumina_det_target_size_ex (host entry) against the literal python restatement of upstream's resize_image_type0 for
+    all three limit types; the old entry stays the "max" rule; bad arguments are status codes / ValueError."""
+    from ocr_system_b200 import ops
+    from ocr_system_b200.paddle_ops import DetResizeNormalize
+
+    rng = np.random.default_rng(11)
+    for _ in range(6000):
+        h, w = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
+        limit = int(rng.choice([32, 64, 320, 640, 736, 960, 1280, 1536, 2000, int(rng.integers(1, 3000))]))
+        for lt in ("max", "min", "resize_long"):
+            assert ops.det_target_size(h, w, limit, lt) == oracle.det_target_size_upstream(h, w, limit, lt), (h, w, limit, lt)
+        assert ops.det_target_size(h, w, limit) == oracle.det_target_size(h, w, limit)
+    for (h, w, limit) in [(48, 48, 96), (80, 80, 100), (1008, 1008, 960), (3508, 2480, 960)]:   # round-half-even ties and the headline
+        for lt in ("max", "min", "resize_long"):
+            assert ops.det_target_size(h, w, limit, lt) == oracle.det_target_size_upstream(h, w, limit, lt)
+    with pytest.raises(ValueError):
+        ops.det_target_size(100, 100, 960, "area")
+    with pytest.raises(ValueError):
+        DetResizeNormalize(limit_type="area")
+    oh, ow = C.c_int(), C.c_int()
+    L = abi.lib()
+    assert L.lumina_det_target_size_ex(100, 100, 960, 3, C.byref(oh), C.byref(ow)) < 0
+    assert L.lumina_det_target_size_ex(0, 100, 960, 0, C.byref(oh), C.byref(ow)) < 0
+    assert L.lumina_det_target_size_ex(100, 100, 960, 1, C.byref(oh), C.byref(ow)) == 0 and (oh.value, ow.value) == (960, 960)

@@ -39,6 +39,28 @@ def test_det_resize_normalize_equals_cv2_resize_plus_numpy(oracle, h, w):
     assert tuple(shape) == (h, w, rh / h, rw / w)
 
 
+@pytest.mark.parametrize("limit_type,limit,h,w", [("min", 736, 300, 200), ("min", 736, 501, 1333), ("min", 960, 64, 1999),
+                                                 ("resize_long", 960, 333, 501), ("resize_long", 640, 2000, 1413),
+                                                 ("resize_long", 1280, 31, 17), ("min", 64, 7, 5)])
+def test_det_resize_normalize_other_limit_types_equal_cv2_resize_plus_numpy(oracle, limit_type, limit, h, w):
+    """upstream's "min" / "resize_long" limit types enlarge images: the same cv2.resize(INTER_LINEAR) + NumPy float
+    stage, exact, with the target size from a literal restatement of resize_image_type0."""
+    import cv2
+
+    rng = np.random.default_rng(h * 11 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got, shape = oracle.det_resize_normalize(img, limit, limit_type)
+    rh, rw = oracle.det_target_size_upstream(h, w, limit, limit_type)
+    assert rh % 32 == 0 and rw % 32 == 0 and (limit_type != "min" or min(rh, rw) >= min(h, w))
+    r = cv2.resize(img, (int(rw), int(rh)))
+    mean = np.array([0.485, 0.456, 0.406], np.float32).reshape(1, 1, 3)
+    std = np.array([0.229, 0.224, 0.225], np.float32).reshape(1, 1, 3)
+    want = ((r.astype("float32") * np.float32(1.0 / 255.0) - mean) / std).transpose(2, 0, 1)
+    assert got.shape == want.shape == (3, rh, rw)
+    assert np.array_equal(got, want)
+    assert tuple(shape) == (h, w, rh / h, rw / w)
+
+
 def test_ctc_greedy_equals_numpy(oracle):
     """upstream CTCLabelDecode: argmax (first max wins), max, drop repeats / blank, mean."""
     rng = np.random.default_rng(0)
