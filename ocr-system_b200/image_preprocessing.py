@@ -609,13 +609,20 @@ class ImagePreprocessor:
 
 class _LazySingleton:
     """``image_preprocessor`` singleton (reference :632) built on first use, so importing
-    the module never touches CUDA."""
+    the module never touches CUDA.  ``isinstance(image_preprocessor, ImagePreprocessor)`` holds, as in the reference."""
 
     _inst: Optional[ImagePreprocessor] = None
+    _lock = threading.Lock()
+
+    @property
+    def __class__(self):       # isinstance() consults obj.__class__ after type(obj)
+        return ImagePreprocessor
 
     def __getattr__(self, name):
         if _LazySingleton._inst is None:
-            _LazySingleton._inst = ImagePreprocessor()
+            with _LazySingleton._lock:
+                if _LazySingleton._inst is None:
+                    _LazySingleton._inst = ImagePreprocessor()
         return getattr(_LazySingleton._inst, name)
 
 

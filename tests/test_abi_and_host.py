@@ -275,3 +275,40 @@ def test_det_target_size_limit_types_match_upstream_rule(abi, oracle):
     assert L.lumina_det_target_size_ex(100, 100, 960, 3, C.byref(oh), C.byref(ow)) < 0
     assert L.lumina_det_target_size_ex(0, 100, 960, 0, C.byref(oh), C.byref(ow)) < 0
     assert L.lumina_det_target_size_ex(100, 100, 960, 1, C.byref(oh), C.byref(ow)) == 0 and (oh.value, ow.value) == (960, 960)
+
+
+def test_dropin_accepts_every_call_the_reference_accepts(abi):
+    """Public surface of the reference's two hot-path modules (tests/golden/signature_golden.json, recorded from the
+    unmodified reference by tests/golden/make_signature_golden.py): every public method / function exists in the drop-in
+    with the same parameter names, kinds and defaults in the same positions (extra trailing parameters must have
+    defaults), and the boundary dataclasses carry the same fields in the same order."""
+    import dataclasses
+    import inspect
+    import json
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_signature_golden import params
+
+    from ocr_system_b200 import image_preprocessing as ip
+    from ocr_system_b200 import ocr_postprocessor as pp
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "signature_golden.json")))
+    assert len(gold["ImagePreprocessor"]) >= 20 and len(gold["ocr_postprocessor"]) >= 5
+
+    def check(want, fn, label):
+        got = params(fn)
+        assert got[: len(want)] == want, (label, want, got)
+        for name, kind, default in got[len(want):]:
+            assert default is not None or kind in ("VAR_POSITIONAL", "VAR_KEYWORD"), (label, name)
+
+    for name, want in gold["ImagePreprocessor"].items():
+        check(want, getattr(ip.ImagePreprocessor, name), f"ImagePreprocessor.{name}")
+    for name, want in gold["ocr_postprocessor"].items():
+        check(want, getattr(pp, name), f"ocr_postprocessor.{name}")
+    for name, fields in gold["dataclasses"].items():
+        assert [f.name for f in dataclasses.fields(getattr(pp, name))] == fields, name
+    assert gold["module_singleton"] == "ImagePreprocessor" and isinstance(ip.image_preprocessor, ip.ImagePreprocessor)
+    for name in gold["ImagePreprocessor"]:
+        if name != "__init__":
+            assert callable(getattr(ip.image_preprocessor, name)), name      # the lazy singleton forwards every method
