@@ -239,3 +239,28 @@ def test_resize_pass_order_of_very_tall_images_equals_pillow(oracle, w, h, tw, t
         ref = np.asarray(Image.fromarray(a).resize((tw, th), Image.Resampling.LANCZOS))
         assert np.array_equal(oracle.resize_lanczos(a, tw, th), ref), (w, h, tw, th, c)
 
+
+
+def test_sauvola_restatement_equals_the_per_pixel_definition(oracle):
+    """No library in this image implements Sauvola and the reference has no such operator ("parity unpinned"): what can
+    be pinned is that the integral-image restatement (which the GPU kernel is compared with) equals the operator's
+    definition evaluated window by window -- mean and population standard deviation of the window clipped to the page,
+    T = m (1 + k (s / R - 1)), pixel > T -> 255 -- including windows larger than the page and 1-pixel pages."""
+    rng = np.random.default_rng(5)
+    for (h, w, window, k, r) in [(23, 31, 5, 0.2, 128.0), (17, 9, 25, 0.34, 128.0), (40, 40, 15, 0.5, 64.0), (1, 1, 25, 0.2, 128.0),
+                                 (3, 50, 7, 0.1, 128.0)]:
+        g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        g[: h // 2] = (g[: h // 2] // 64) * 64          # flat-ish areas: ties of pixel and threshold are likely
+        got = oracle.sauvola(g, window, k, r)
+        rad = window // 2
+        want = np.zeros_like(g)
+        near_tie = np.zeros(g.shape, bool)
+        for y in range(h):
+            for x in range(w):
+                win = g[max(0, y - rad): y + rad + 1, max(0, x - rad): x + rad + 1].astype(np.float64)
+                m, s = win.mean(), win.std()            # numpy's two-pass population std: an independent evaluation
+                t = m * (1.0 + k * (s / r - 1.0))
+                want[y, x] = 255 if float(g[y, x]) > t else 0
+                near_tie[y, x] = abs(float(g[y, x]) - t) < 1e-9
+        assert np.array_equal(got[~near_tie], want[~near_tie]), (h, w, window)
+        assert near_tie.mean() < 0.05
