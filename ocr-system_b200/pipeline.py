@@ -68,6 +68,24 @@ def shard_range(n_pages: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, min(n_pages, lo + per)
 
 
+def batch_ranges(n_pages: int, rank: int, world_size: int, batch: int, resume_from: Optional[int] = None):
+    """The page-index ranges ``[lo, hi)`` of ``rank``'s batches over a stream of ``n_pages`` pages: its contiguous shard
+    (``shard_range``) cut into batches of ``batch`` pages, the last one ragged.  Pages are identified by their index in the
+    stream, so a stream is restartable: ``resume_from`` = the first page index of this rank that is not finished yet (what a
+    caller records after each yielded batch) skips the batches before it.  Recorded after a yielded batch it is one of the
+    first run's batch boundaries, so the restarted run cuts the remainder into the very same batches; any other index inside
+    the shard works too (pages are independent: the per-page results do not depend on the batch they travel in)."""
+    if batch <= 0:
+        raise ValueError("batch must be positive")
+    lo, hi = shard_range(n_pages, rank, world_size)
+    if resume_from is not None:
+        if not (lo <= resume_from <= hi):
+            raise ValueError(f"resume_from={resume_from} is outside this rank's shard [{lo}, {hi}]")
+        lo = resume_from
+    for q in range(lo, hi, batch):
+        yield q, min(hi, q + batch)
+
+
 class _StageTimer:
     """CUDA-event brackets around each stage on the launching stream (only when profiling)."""
 

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ocr_system_b200.pipeline import shard_range
+from ocr_system_b200.pipeline import batch_ranges, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -22,6 +22,24 @@ def test_shard_range_partitions_exactly():
             assert covered == list(range(n))
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def test_batch_ranges_cover_the_shard_and_restart_by_page_index():
+    """The stream of config 5 is restartable by page index (checkpoint / resume row): the batches of a rank
+    partition its shard, and a run resumed at any recorded page index processes exactly the pages that were left."""
+    for n, g, b in [(10000, 8, 64), (10001, 4, 64), (63, 2, 64), (0, 2, 64), (130, 1, 64), (5, 8, 2)]:
+        for r in range(g):
+            lo, hi = shard_range(n, r, g)
+            rs = list(batch_ranges(n, r, g, b))
+            assert [p for a, z in rs for p in range(a, z)] == list(range(lo, hi))
+            assert all(0 < z - a <= b for a, z in rs) and all(z - a == b for a, z in rs[:-1])
+            for done in {lo, hi, lo + (hi - lo) // 2, min(hi, lo + b), min(hi, lo + b + 1)}:
+                rest = list(batch_ranges(n, r, g, b, resume_from=done))
+                assert [p for a, z in rest for p in range(a, z)] == list(range(done, hi))
+    with pytest.raises(ValueError):
+        list(batch_ranges(100, 1, 2, 64, resume_from=10))      # page 10 belongs to rank 0
+    with pytest.raises(ValueError):
+        list(batch_ranges(100, 0, 2, 0))
 
 
 def _worker(rank, world, port, n_pages, q):
