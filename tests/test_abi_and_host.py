@@ -312,3 +312,71 @@ def test_dropin_accepts_every_call_the_reference_accepts(abi):
     for name in gold["ImagePreprocessor"]:
         if name != "__init__":
             assert callable(getattr(ip.image_preprocessor, name)), name      # the lazy singleton forwards every method
+
+
+def test_batching_preprocessor_host_logic_with_a_stub_device(abi):
+    """ocr_service_adapter.BatchingPreprocessor (the reference's page loop, ocr_service.py:604-660, as one batched
+    submission): look-ahead, max_batch split, argument change mid-document, unknown images, per-thread state -- against a
+    stub inner preprocessor, so the host logic is covered without a GPU (the GPU test checks the bytes)."""
+    import threading
+
+    from PIL import Image
+
+    from ocr_system_b200.ocr_service_adapter import BatchingPreprocessor, install
+
+    class Inner:
+        max_dimension = 2000
+
+        def __init__(self):
+            self.batches, self.singles = [], []
+
+        def pdf_to_images(self, path, dpi=None):
+            return [Image.new("RGB", (8, 8), (i, 0, 0)) for i in range(int(path))]
+
+        def preprocess_pages_for_azure(self, pages, *flags):
+            self.batches.append((len(pages), flags))
+            return [b"B%d|%r" % (p.getpixel((0, 0))[0], flags) for p in pages]
+
+        def preprocess_for_azure(self, image, *flags):
+            self.singles.append(flags)
+            return b"S%d|%r" % (image.getpixel((0, 0))[0], flags)
+
+    inner = Inner()
+    bp = BatchingPreprocessor(inner, max_batch=4)
+    assert bp.max_dimension == 2000                                  # everything else is forwarded
+    flags = (True, False, True, True, 2.0)
+    pages = bp.pdf_to_images("10")
+    got = [bp.preprocess_for_azure(p, apply_deskew=True, apply_binarize=False) for p in pages]
+    assert got == [b"B%d|%r" % (i, flags) for i in range(10)]
+    assert [n for n, _ in inner.batches] == [4, 4, 2] and bp.batched_calls == 3 and not inner.singles
+    # an image the adapter has not seen takes the per-image path with the caller's arguments
+    other = Image.new("RGB", (8, 8), (99, 0, 0))
+    assert bp.preprocess_for_azure(other, False, True) == b"S99|%r" % ((False, True, True, True, 2.0),)
+    # arguments change in the middle of a document: the pages from there on are resubmitted with the new ones
+    inner.batches.clear()
+    pages = bp.pdf_to_images("3")
+    a = bp.preprocess_for_azure(pages[0])
+    b = bp.preprocess_for_azure(pages[1], apply_binarize=True)
+    c = bp.preprocess_for_azure(pages[2], apply_binarize=True)
+    f2 = (True, True, True, True, 2.0)
+    assert (a, b, c) == (b"B0|%r" % (flags,), b"B1|%r" % (f2,), b"B2|%r" % (f2,))
+    assert [n for n, _ in inner.batches] == [3, 2]
+    # a page asked for twice is preprocessed again (per image), never answered from a stale entry
+    assert bp.preprocess_for_azure(pages[0]).startswith(b"S0|")
+    # two threads, two documents: the look-ahead state is per thread
+    results = {}
+
+    def doc(n):
+        ps = bp.pdf_to_images(str(n))
+        results[n] = [bp.preprocess_for_azure(p) for p in ps]
+
+    ts = [threading.Thread(target=doc, args=(n,)) for n in (5, 7)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert [len(results[n]) for n in (5, 7)] == [5, 7] and all(r.startswith(b"B") for n in (5, 7) for r in results[n])
+
+    class Svc:
+        image_preprocessor = None
+
+    proxy = install(Svc, preprocessor=inner, max_batch=2)
+    assert Svc.image_preprocessor is proxy and proxy._max_batch == 2
