@@ -83,6 +83,8 @@ class ImagePreprocessor:
     # block size (16 MB by default) is raised once so that A4 300-dpi pages (35 MB as RGBX) qualify; images that
     # were allocated earlier, other modes or a missing pyarrow simply take the np.asarray path.
     _BLOCK_MB = int(os.environ.get("LUMINA_PIL_BLOCK_MB", "64"))
+    # pages of one (size, mode) group that preprocess_pages_for_azure sends through the device at once
+    _MAX_BATCH_PAGES = max(1, int(os.environ.get("LUMINA_MAX_BATCH_PAGES", "64")))
 
     @classmethod
     def _raise_pil_block_size(cls) -> None:
@@ -566,7 +568,11 @@ class ImagePreprocessor:
         for i in host_idx:
             if imgs[i] is None:
                 imgs[i] = self._open(images[i])
-        for key, members in enc_groups.items():
+        cap = self._MAX_BATCH_PAGES
+        # a group larger than the cap (a 1000-page PDF) goes through in slices: pinned staging and HBM stay bounded
+        # (64 A4 pages = 2.2 GB of pinned RGBX + 1.7 GB of rasters); pages are independent, so the bytes do not change
+        enc_chunks = [m[k:k + cap] for m in enc_groups.values() for k in range(0, len(m), cap)]
+        for members in enc_chunks:
             dec = self._jpeg_decoder()
             blob, offs = dec.pack([d for _, d, _ in members])
             x, status = dec.decode(blob, offs, self.device, members[0][2])
@@ -587,16 +593,18 @@ class ImagePreprocessor:
         for i, im in enumerate(imgs):
             if im is not None:
                 groups.setdefault((im.size, im.mode), []).append(i)
-        for ((w, h), mode), idx in groups.items():
+        for ((w, h), mode), members in groups.items():
             if mode not in ("RGB", "L"):   # rare: such objects take the per-image path
-                for i in idx:
+                for i in members:
                     out[i] = self.preprocess_for_azure(imgs[i], apply_deskew, apply_binarize, apply_contrast,
                                                        apply_sharpness, target_size_mb)
                 continue
-            x = self._upload([imgs[i] for i in idx])
-            x, _ = self.preprocess_device(x, apply_deskew, apply_binarize, apply_contrast, apply_sharpness)
-            for i, b in zip(idx, self.compress_pages_for_azure(x, target_size_mb=target_size_mb)):
-                out[i] = b
+            for k in range(0, len(members), cap):
+                idx = members[k:k + cap]
+                x = self._upload([imgs[i] for i in idx])
+                x, _ = self.preprocess_device(x, apply_deskew, apply_binarize, apply_contrast, apply_sharpness)
+                for i, b in zip(idx, self.compress_pages_for_azure(x, target_size_mb=target_size_mb)):
+                    out[i] = b
         return out  # type: ignore[return-value]
 
     def _host_stage(self, n: int, h: int, w: int, c: int) -> torch.Tensor:

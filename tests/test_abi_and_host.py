@@ -380,3 +380,35 @@ def test_batching_preprocessor_host_logic_with_a_stub_device(abi):
 
     proxy = install(Svc, preprocessor=inner, max_batch=2)
     assert Svc.image_preprocessor is proxy and proxy._max_batch == 2
+
+
+def test_preprocess_pages_for_azure_grouping_and_slicing_host_logic(abi):
+    """Host half of the batched Azure path with the device calls stubbed out: pages are grouped by (size, mode), a group
+    larger than the cap is submitted in slices, results come back in input order."""
+    from PIL import Image
+
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+
+    calls = []
+
+    class Stub(ImagePreprocessor):
+        _MAX_BATCH_PAGES = 3
+
+        def _upload(self, images):
+            calls.append((images[0].size, images[0].mode, len(images)))
+            return [im.getpixel((0, 0)) for im in images]
+
+        def preprocess_device(self, x, *flags):
+            return x, None
+
+        def compress_pages_for_azure(self, x, target_size_mb=2.0, **kw):
+            return [repr(v).encode() for v in x]
+
+    ip = Stub(max_dimension=400)
+    imgs = []
+    for i in range(11):
+        size, mode = [((8, 8), "RGB"), ((8, 6), "RGB"), ((8, 8), "L")][i % 3 if i < 9 else 0]
+        imgs.append(Image.new(mode, size, i if mode == "L" else (i, 0, 0)))
+    got = ip.preprocess_pages_for_azure(imgs)
+    assert got == [repr(im.getpixel((0, 0))).encode() for im in imgs]
+    assert sorted(calls) == sorted([((8, 8), "RGB", 3), ((8, 8), "RGB", 2), ((8, 6), "RGB", 3), ((8, 8), "L", 3)])

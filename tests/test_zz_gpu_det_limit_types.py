@@ -24,3 +24,27 @@ def test_det_resize_normalize_limit_types(oracle, cuda, limit_type, limit, h, w)
         assert tuple(shape_list[i]) == tuple(sl)
         # float stage tolerance from north_star: <= 1e-4 abs
         assert np.max(np.abs(got[i].cpu().numpy() - ref)) <= 1e-4
+
+
+def test_preprocess_pages_for_azure_slices_large_groups(cuda, oracle):
+    """A (size, mode) group larger than the per-submission cap (LUMINA_MAX_BATCH_PAGES, 64 by default) goes through the
+    device in slices -- raster objects and JPEG files alike -- and the bytes are those of the per-page call."""
+    import io
+
+    from PIL import Image
+
+    from ocr_system_b200.image_preprocessing import ImagePreprocessor
+
+    pages = [Image.fromarray(oracle.synth_page(640, 452, s)) for s in range(5)]
+    files = []
+    for p in pages:
+        buf = io.BytesIO()
+        p.save(buf, format="JPEG", quality=80)
+        files.append(buf.getvalue())
+    ip = ImagePreprocessor(max_dimension=400)
+    ip._MAX_BATCH_PAGES = 2
+    want = [ip.preprocess_for_azure(p, target_size_mb=0.05) for p in pages]
+    assert ip.preprocess_pages_for_azure(pages, target_size_mb=0.05) == want
+    want_f = [ip.preprocess_for_azure(f, target_size_mb=0.05) for f in files]
+    assert ip.preprocess_pages_for_azure(files, target_size_mb=0.05) == want_f
+    assert ip.preprocess_pages_for_azure(pages + files, target_size_mb=0.05) == want + want_f
