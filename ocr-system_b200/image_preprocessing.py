@@ -356,12 +356,15 @@ class ImagePreprocessor:
                 out[i] = pg
             else:
                 groups.setdefault((pg.size, pg.mode), []).append(i)
-        for (size, _mode), idxs in groups.items():
-            batch = torch.from_numpy(np.stack([np.asarray(pages[i]) for i in idxs])).to(self.device)
+        cap = self._MAX_BATCH_PAGES      # a long document goes through in slices: host / HBM copies stay bounded
+        for (size, _mode), members in groups.items():
             nw, nh = ops.target_size(size[0], size[1], self.max_dimension)
-            res = ops.resize_lanczos(batch, nw, nh).cpu().numpy()
-            for k, i in enumerate(idxs):
-                out[i] = Image.fromarray(res[k])
+            for k0 in range(0, len(members), cap):
+                idxs = members[k0:k0 + cap]
+                batch = torch.from_numpy(np.stack([np.asarray(pages[i]) for i in idxs])).to(self.device)
+                res = ops.resize_lanczos(batch, nw, nh).cpu().numpy()
+                for k, i in enumerate(idxs):
+                    out[i] = Image.fromarray(res[k])
         return out  # type: ignore[return-value]
 
     def get_pdf_page_count(self, pdf_path: Union[str, Path]) -> int:
