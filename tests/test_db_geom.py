@@ -277,3 +277,51 @@ def test_fillpoly_of_a_contour_is_the_enclosed_region():
                 holes += 1
             total += 1
     assert total > 2000 and holes > 200
+
+
+def test_clipper_offset_is_the_round_join_offset_of_the_quad():
+    """pyclipper is not in this image, so the Clipper restatement (oracle/db_post.py, which db_geom.h is held to above) is
+    "parity unpinned" against the library.  What does not need the library is the geometry it must produce -- the
+    Minkowski sum of the quad with a disc of radius d, joins rounded (JT_ROUND, arc tolerance 0.25), coordinates rounded
+    to integers: every vertex lies d from the quad (never a mitred or squared corner, never short of d), the arcs are
+    there (the point d along each corner's bisector lies on the outline), and the area is Steiner's A + P d + pi d^2 up
+    to the integer rounding of the outline."""
+    from oracle import db_post as D
+
+    def seg_dist(p, poly):
+        a, b = poly, np.roll(poly, -1, axis=0)
+        ab = b - a
+        t = np.clip(((p - a) * ab).sum(1) / np.maximum((ab * ab).sum(1), 1e-30), 0.0, 1.0)
+        return float(np.min(np.hypot(*(p - (a + t[:, None] * ab)).T)))
+
+    def shoelace(q):
+        return 0.5 * abs(float(np.dot(q[:, 0], np.roll(q[:, 1], -1)) - np.dot(q[:, 1], np.roll(q[:, 0], -1))))
+
+    rng = np.random.default_rng(4)
+    checked = 0
+    for _ in range(400):
+        rect = cv2.boxPoints(((rng.uniform(100, 800), rng.uniform(100, 800)), (rng.uniform(8, 400), rng.uniform(6, 80)),
+                              rng.uniform(-90, 90)))
+        box = np.round(rect).astype(np.float64)
+        area = shoelace(box)
+        length = float(np.sum(np.hypot(*(np.roll(box, -1, axis=0) - box).T)))
+        if area < 4:
+            continue
+        ratio = float(rng.choice([1.5, 1.6, 2.0]))
+        d = area * ratio / length
+        ex = D.unclip(box, ratio).astype(np.float64)
+        dist = np.array([seg_dist(p, box) for p in ex])
+        assert d - 1.0 <= dist.min() and dist.max() <= d + 0.75, (d, dist.min(), dist.max())
+        centre = box.mean(0)
+        if d >= 5:
+            for k in range(4):
+                e0 = box[k] - box[k - 1]
+                e1 = box[k] - box[(k + 1) % 4]
+                u = e0 / np.linalg.norm(e0) + e1 / np.linalg.norm(e1)
+                u /= np.linalg.norm(u)
+                assert np.dot(u, box[k] - centre) > 0
+                assert seg_dist(box[k] + d * u, ex) <= 1.0, (d, k)     # a chord instead of the arc would be 0.29 d away
+        per = float(np.sum(np.hypot(*(np.roll(ex, -1, axis=0) - ex).T)))
+        assert abs(shoelace(ex) - (area + length * d + np.pi * d * d)) <= 0.75 * per
+        checked += 1
+    assert checked > 300
