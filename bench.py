@@ -480,7 +480,8 @@ def bench_chain(cx: Ctx):
         state["i"] += K
 
     launches0 = ops.launch_count()
-    pip_ms, R_pip = cx.timed_rounds(round_pipelined, K, unp_ms / (R_unp * K))
+    # the pipelined step is ~0.7 of the unpipelined one: estimate with 0.6 so that the timed region stays >= MIN_TIMED_S
+    pip_ms, R_pip = cx.timed_rounds(round_pipelined, K, 0.6 * unp_ms / (R_unp * K))
     launches = ops.launch_count() - launches0
     clocks = sampler.stop()
 
